@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Generate golden fixtures by running the UNMODIFIED reference (PRBonn/PIN_SLAM,
+mounted read-only at /root/reference) on seeded synthetic inputs, CPU, fp32.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference has no tests/golden vectors of its own, so these
+fixtures are what pins the oracle (``oracle/pin_oracle.py``) and, through it,
+the CUDA path.  Each fixture stores the full map state, the inputs, and the
+outputs of the reference functions on the hot path:
+
+  NeuralPoints.radius_neighborhood_search   model/neural_points.py:950
+  NeuralPoints.query_feature                model/neural_points.py:530
+  NeuralPoints.query_certainty              model/neural_points.py:1011
+  Decoder.sdf / regress_color               model/decoder.py:83,112
+  Tracker.query_source_points               utils/tracker.py:227
+  Tracker.registration_step / implicit_reg  utils/tracker.py:367,615
+  Mapper.mapping                            utils/mapper.py:600
+
+Optional reference imports (open3d, gtsam, ...) that are absent here and unused
+by the hot path are stubbed in sys.modules before import.
+"""
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+for _m in ["open3d", "matplotlib", "matplotlib.cm", "matplotlib.pyplot", "roma", "wandb", "natsort",
+           "skimage", "skimage.measure", "pypose", "gtsam", "dtyper", "pyquaternion", "laspy", "evo"]:
+    sys.modules[_m] = MagicMock()
+sys.path.insert(0, "/root/reference")
+
+import torch  # noqa: E402
+
+from model.decoder import Decoder  # noqa: E402
+from model.neural_points import NeuralPoints  # noqa: E402
+from utils.config import Config  # noqa: E402
+from utils.mapper import Mapper  # noqa: E402
+from utils.tracker import Tracker  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def scene_points(n, seed, lo=-10.0, hi=10.0):
+    """Random points on a floor, two walls and a box (metres)."""
+    g = torch.Generator().manual_seed(seed)
+    u = lambda k: torch.rand(k, generator=g) * (hi - lo) + lo  # noqa: E731
+    k = n // 4
+    floor = torch.stack([u(k), u(k), torch.zeros(k)], 1)
+    wall1 = torch.stack([u(k), torch.full((k,), hi), torch.rand(k, generator=g) * 4], 1)
+    wall2 = torch.stack([torch.full((k,), lo), u(k), torch.rand(k, generator=g) * 4], 1)
+    box = torch.stack([torch.rand(k, generator=g) * 3 + 2, torch.rand(k, generator=g) * 3 - 5,
+                       torch.full((k,), 1.5)], 1)
+    p = torch.cat([floor, wall1, wall2, box], 0)
+    return p + 0.01 * torch.randn(p.shape, generator=g)
+
+
+def make_config(kind):
+    cfg = Config()
+    if kind == "kitti":
+        cfg.load("/root/reference/config/lidar_slam/run_kitti.yaml")
+    elif kind == "replica":
+        cfg.load("/root/reference/config/rgbd_slam/run_replica.yaml")
+        cfg.voxel_size_m = 0.25  # keep the fixture small (synthetic scene is 20 m wide)
+    else:  # cfg2-like: defaults + non-default sizes reachable via yaml
+        cfg.feature_dim = 32
+        cfg.query_nn_k = 8
+        cfg.geo_mlp_level = 2
+        cfg.voxel_size_m = 0.4
+        cfg.track_on = True
+    cfg.device = "cpu"
+    cfg.pgo_on = False
+    cfg.silence = True
+    cfg.setup_dtype()
+    torch.set_default_dtype(cfg.dtype)
+    return cfg
+
+
+def map_state(npm):
+    tab = npm.buffer_pt_index
+    occ = torch.nonzero(tab >= 0).flatten()
+    d = dict(
+        resolution=np.float64(npm.resolution),
+        buffer_size=np.int64(npm.buffer_size),
+        neural_points=npm.neural_points.numpy(),
+        point_orientations=npm.point_orientations.numpy(),
+        geo_features=npm.geo_features.numpy(),
+        point_ts_create=npm.point_ts_create.numpy(),
+        point_ts_update=npm.point_ts_update.numpy(),
+        point_certainties=npm.point_certainties.numpy(),
+        table_slots=occ.numpy(),
+        table_vals=tab[occ].numpy(),
+        travel_dist=npm.travel_dist.numpy(),
+        cur_ts=np.int64(npm.cur_ts),
+        diff_travel_dist_local=np.float64(npm.diff_travel_dist_local),
+        max_valid_dist2=np.float64(npm.max_valid_dist2),
+        neighbor_dx=npm.neighbor_dx.numpy(),
+        after_pgo=np.bool_(npm.after_pgo),
+        temporal_local_map_on=np.bool_(npm.temporal_local_map_on),
+        local_mask=npm.local_mask.numpy(),
+        global2local=npm.global2local.numpy(),
+        local_neural_points=npm.local_neural_points.numpy(),
+        local_point_orientations=npm.local_point_orientations.numpy(),
+        local_geo_features=npm.local_geo_features.detach().numpy(),
+        local_point_certainties=npm.local_point_certainties.numpy(),
+        local_point_ts_update=npm.local_point_ts_update.numpy(),
+    )
+    if npm.color_features is not None:
+        d["color_features"] = npm.color_features.numpy()
+        d["local_color_features"] = npm.local_color_features.detach().numpy()
+    return {"map." + k: np.array(v, copy=True) for k, v in d.items()}  # copies: later in-place scatters must not leak in
+
+
+def dec_state(dec, name):
+    d = {}
+    for k, v in dec.state_dict().items():
+        d[f"{name}.{k}"] = v.numpy().copy()
+    d[f"{name}.sdf_scale"] = np.float64(dec.sdf_scale)
+    return d
+
+
+def build_reference_map(cfg, seed, n_frames=3, radius=9.0, diff_td=4.5, feat_std=0.1):
+    """Grow a map through the reference's own NeuralPoints.update()."""
+    torch.manual_seed(seed)
+    cfg.local_map_radius = radius
+    npm = NeuralPoints(cfg)
+    npm.diff_travel_dist_local = diff_td
+    npm.travel_dist = torch.tensor([0.0, 2.0, 4.0, 6.0, 8.0][: n_frames + 1])
+    for f in range(n_frames):
+        pts = scene_points(6000, seed * 10 + f)
+        pts[:, 0] += 1.5 * f
+        pos = torch.tensor([1.5 * f, 0.0, 1.0])
+        npm.update(pts, pos, torch.eye(3), f)
+    # non-zero features / certainties so that errors cannot hide behind zeros
+    g = torch.Generator().manual_seed(seed + 100)
+    npm.geo_features = feat_std * torch.randn(npm.geo_features.shape, generator=g)
+    if npm.color_features is not None:
+        npm.color_features = feat_std * torch.randn(npm.color_features.shape, generator=g)
+    npm.point_certainties = torch.rand(npm.count(), generator=g) * 3.0
+    npm.reset_local_map(pos, torch.eye(3), n_frames - 1)
+    return npm, pos
+
+
+def query_points_near(npm, n, seed, sigma=0.15):
+    g = torch.Generator().manual_seed(seed)
+    sel = torch.randint(0, npm.count(), (n,), generator=g)
+    q = npm.neural_points[sel] + sigma * torch.randn(n, 3, generator=g)
+    # a few far-away queries (nn_count == 0 rows) and negative coordinates
+    q[:8] = torch.tensor([500.0, -300.0, 40.0]) + torch.randn(8, 3, generator=g)
+    return q.contiguous()
+
+
+def gen_query_fixture(kind, seed, weighted_first, after_pgo=False, color=False, nq=640, name=None):
+    cfg = make_config(kind)
+    cfg.weighted_first = weighted_first
+    cfg.buffer_size = 40009  # small table -> real hash collisions are exercised
+    if color:
+        cfg.color_on = True
+        cfg.color_channel = 3
+    npm, pos = build_reference_map(cfg, seed)
+    if after_pgo:
+        g = torch.Generator().manual_seed(seed + 7)
+        qn = torch.randn(npm.count(), 4, generator=g)
+        npm.point_orientations = qn / qn.norm(dim=1, keepdim=True)
+        npm.after_pgo = True
+        npm.reset_local_map(pos, torch.eye(3), npm.cur_ts)
+    torch.manual_seed(seed + 1)
+    sdf_mlp = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    color_mlp = Decoder(cfg, cfg.color_mlp_hidden_dim, cfg.color_mlp_level, cfg.color_channel) if color else None
+    out = {}
+    out.update(map_state(npm))
+    out.update(dec_state(sdf_mlp, "sdf_mlp"))
+    if color:
+        out.update(dec_state(color_mlp, "color_mlp"))
+    out["cfg.query_nn_k"] = np.int64(cfg.query_nn_k)
+    out["cfg.weighted_first"] = np.bool_(cfg.weighted_first)
+    out["cfg.feature_dim"] = np.int64(cfg.feature_dim)
+    out["cfg.local_map_radius"] = np.float64(cfg.local_map_radius)
+    out["sensor_pos"] = pos.numpy()
+
+    q = query_points_near(npm, nq, seed + 2)
+    out["q"] = q.numpy()
+
+    # a3
+    d2, idx = npm.radius_neighborhood_search(q.clone(), time_filtering=True)
+    out["rs.dist2"] = d2.numpy()
+    out["rs.idx"] = idx.numpy().astype(np.int32)
+    d2g, idxg = npm.radius_neighborhood_search(q.clone(), time_filtering=False)
+    out["rs_nofilter.idx"] = idxg.numpy().astype(np.int32)
+    # a5
+    out["query_certainty"] = npm.query_certainty(q.clone()).numpy()
+
+    # a4 (inference mode, local + global)
+    for loc in (True, False):
+        geo, col, w, nnc, cert = npm.query_feature(q.clone(), training_mode=False, query_locally=loc,
+                                                   query_color_feature=color)
+        tag = "qf_local" if loc else "qf_global"
+        out[f"{tag}.geo"] = geo.detach().numpy()
+        if col is not None:
+            out[f"{tag}.color"] = col.detach().numpy()
+        out[f"{tag}.weight"] = w.numpy()
+        out[f"{tag}.nn_counts"] = nnc.numpy()
+        out[f"{tag}.certainty"] = cert.numpy()
+
+    # a8: Tracker.query_source_points
+    trk = Tracker(cfg, npm, {"sdf": sdf_mlp, "semantic": None, "color": color_mlp})
+    photo = color
+    res = trk.query_source_points(q.clone(), cfg.infer_bs, True, True, color, photo,
+                                  query_locally=True, mask_min_nn_count=cfg.track_mask_query_nn_k)
+    sdf_pred, sdf_grad, color_pred, color_grad, _, mask, certainty, sdf_std = res
+    out["trk.sdf"] = sdf_pred.numpy()
+    out["trk.grad"] = sdf_grad.numpy()
+    out["trk.mask"] = mask.numpy()
+    out["trk.certainty"] = certainty.numpy()
+    out["trk.sdf_std"] = sdf_std.numpy()
+    out["cfg.track_mask_query_nn_k"] = np.int64(cfg.track_mask_query_nn_k)
+    if color:
+        out["trk.color"] = color_pred.numpy()
+        out["trk.color_grad"] = color_grad.numpy()
+
+    # a9/a10: one registration step on the same points (geometry branch)
+    if not color:
+        cfg_photo = cfg.photometric_loss_on
+        cfg.photometric_loss_on = False
+        source_sdf = torch.zeros(q.shape[0])
+        gnorm = None
+        # random-init decoder => tiny |grad|; widen the validity band so the GN system is non-trivial
+        min_gn, max_gn = 1e-3, 10.0
+        T, cov, eig, _, valid_points, res_cm, _ = trk.registration_step(
+            q.clone(), None, source_sdf, None, min_gn, max_gn,
+            cfg.reg_GM_dist_m, cfg.reg_GM_grad, cfg.reg_lm_lambda, False)
+        cfg.photometric_loss_on = cfg_photo
+        out["reg.T"] = T.numpy()
+        out["reg.valid_count"] = np.int64(valid_points.shape[0])
+        out["reg.residual_cm"] = np.float64(res_cm)
+        out["reg.params"] = np.array([min_gn, max_gn,
+                                      cfg.surface_sample_range_m * cfg.max_sdf_std_ratio,
+                                      cfg.reg_GM_dist_m, cfg.reg_GM_grad, cfg.reg_lm_lambda], dtype=np.float64)
+
+    # a4 training-mode side effects (certainty scatter_add, ts amax) on a copy
+    ts = torch.full((q.shape[0],), int(npm.cur_ts), dtype=torch.int32)
+    ts[::3] = int(npm.cur_ts) + 1
+    cert_before = npm.local_point_certainties.clone()
+    tsu_before = npm.local_point_ts_update.clone()
+    npm.query_feature(q.clone(), ts, training_mode=True, query_color_feature=color)
+    out["train_fx.ts"] = ts.numpy()
+    out["train_fx.certainties_after"] = npm.local_point_certainties.numpy().copy()
+    out["train_fx.ts_update_after"] = npm.local_point_ts_update.numpy().copy()
+    npm.local_point_certainties = cert_before
+    npm.local_point_ts_update = tsu_before
+
+    name = name or f"query_{kind}_{'wf' if weighted_first else 'nwf'}{'_pgo' if after_pgo else ''}{'_color' if color else ''}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "Mg=", npm.count(), "M=", npm.local_count(), "valid=", int(out["reg.valid_count"]) if "reg.valid_count" in out else "-")
+
+
+def gen_train_fixture(kind, seed, weighted_first, iters=3, bs=2048, color=False, name=None):
+    cfg = make_config(kind)
+    cfg.weighted_first = weighted_first
+    cfg.buffer_size = 40009
+    cfg.bs = bs
+    cfg.bs_new_sample = 0
+    if color:
+        cfg.color_on = True
+        cfg.color_channel = 3
+    npm, pos = build_reference_map(cfg, seed, feat_std=0.05)
+    torch.manual_seed(seed + 1)
+    sdf_mlp = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    color_mlp = Decoder(cfg, cfg.color_mlp_hidden_dim, cfg.color_mlp_level, cfg.color_channel) if color else None
+    dataset = types.SimpleNamespace(processed_frame=npm.cur_ts, lose_track=False, stop_status=False,
+                                    gt_pose_provided=False, odom_poses=None, pgo_poses=None, gt_poses=None)
+    mapper = Mapper(cfg, dataset, npm, {"sdf": sdf_mlp, "semantic": None, "color": color_mlp})
+    # synthetic replay pool: samples around the surface with sdf labels along a fake normal
+    g = torch.Generator().manual_seed(seed + 5)
+    npool = 20000
+    sel = torch.randint(0, npm.count(), (npool,), generator=g)
+    label = 0.15 * torch.randn(npool, generator=g)
+    label[::4] = 0.0
+    coord = npm.neural_points[sel] + 0.1 * torch.randn(npool, 3, generator=g)
+    coord[:, 2] += label
+    mapper.global_coord_pool = coord
+    mapper.coord_pool = coord.clone()
+    mapper.sdf_label_pool = label
+    mapper.weight_pool = (torch.rand(npool, generator=g) * 0.8 + 0.6) * torch.where(label.abs() < 0.05, 1.0, -1.0)
+    mapper.time_pool = torch.randint(0, npm.cur_ts + 1, (npool,), generator=g).to(torch.int32)
+    mapper.color_pool = torch.rand(npool, 3, generator=g) if color else None
+    mapper.sem_label_pool = None
+    mapper.normal_label_pool = None
+    mapper.pool_sample_count = npool
+    mapper.used_poses = torch.eye(4, dtype=torch.float64).repeat(npm.cur_ts + 1, 1, 1)
+
+    out = {}
+    out.update(map_state(npm))
+    out.update(dec_state(sdf_mlp, "sdf_mlp"))
+    if color:
+        out.update(dec_state(color_mlp, "color_mlp"))
+    for k in ["query_nn_k", "feature_dim", "bs", "gradient_decimation", "iters"]:
+        out["cfg." + k] = np.int64(getattr(cfg, k))
+    out["cfg.weighted_first"] = np.bool_(cfg.weighted_first)
+    out["cfg.loss_weight_on"] = np.bool_(cfg.loss_weight_on)
+    out["cfg.floats"] = np.array([cfg.sigma_sigmoid_m, mapper.sdf_scale, cfg.weight_e,
+                                  cfg.voxel_size_m * cfg.num_grad_step_ratio, cfg.lr, cfg.adam_eps,
+                                  cfg.weight_decay, cfg.surface_sample_range_m, cfg.weight_i], dtype=np.float64)
+
+    batches = []
+    orig = mapper.get_batch
+
+    def rec(global_coord=False):
+        b = orig(global_coord)
+        batches.append(b)
+        return b
+
+    mapper.get_batch = rec
+    torch.manual_seed(seed + 9)
+    mapper.mapping(iters)
+    out["n_iters"] = np.int64(len(batches))
+    for i, b in enumerate(batches):
+        coord_b, label_b, ts_b, _, _, color_b, weight_b = b
+        out[f"batch{i}.coord"] = coord_b.detach().numpy()
+        out[f"batch{i}.sdf_label"] = label_b.numpy()
+        out[f"batch{i}.ts"] = ts_b.numpy()
+        out[f"batch{i}.weight"] = weight_b.numpy()
+        if color_b is not None:
+            out[f"batch{i}.color"] = color_b.numpy()
+    out["after.local_geo_features"] = npm.local_geo_features.detach().numpy()
+    if color:
+        out["after.local_color_features"] = npm.local_color_features.detach().numpy()
+    out["after.local_point_certainties"] = npm.local_point_certainties.numpy()
+    out["after.local_point_ts_update"] = npm.local_point_ts_update.numpy()
+    out.update(dec_state(sdf_mlp, "after.sdf_mlp"))
+    if color:
+        out.update(dec_state(color_mlp, "after.color_mlp"))
+    name = name or f"train_{kind}_{'wf' if weighted_first else 'nwf'}{'_color' if color else ''}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "iters", len(batches))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    gen_query_fixture("kitti", 1, weighted_first=False)
+    gen_query_fixture("kitti", 2, weighted_first=True)
+    gen_query_fixture("cfg2", 3, weighted_first=True)
+    gen_query_fixture("cfg2", 4, weighted_first=False, after_pgo=True)
+    gen_query_fixture("replica", 5, weighted_first=True, color=True)
+    gen_train_fixture("kitti", 11, weighted_first=False)
+    gen_train_fixture("cfg2", 12, weighted_first=True)
+    gen_train_fixture("replica", 13, weighted_first=True, color=True)
+    with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
+        f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
+                f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

@@ -1,0 +1,151 @@
+"""Pin the CPU oracle (oracle/pin_oracle.py) against outputs of the unmodified
+reference recorded by tests/golden/make_golden.py.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pin_oracle as po
+from tests.helpers import decoder_from_fixture, load_npz, map_from_fixture, t
+
+QUERY_FIXTURES = ["query_kitti_nwf", "query_kitti_wf", "query_cfg2_wf", "query_cfg2_nwf_pgo", "query_replica_wf_color"]
+TRAIN_FIXTURES = ["train_kitti_nwf", "train_cfg2_wf", "train_replica_wf_color"]
+
+
+def close(a, b, rtol=1e-6, atol=1e-7):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_radius_search_bit_exact(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    q = t(fx["q"])
+    d2, idx = po.radius_search(m, q.clone(), time_filtering=True)
+    assert np.array_equal(idx.numpy(), fx["rs.idx"].astype(np.int64))
+    assert np.array_equal(d2.numpy(), fx["rs.dist2"])
+    _, idxg = po.radius_search(m, q.clone(), time_filtering=False)
+    assert np.array_equal(idxg.numpy(), fx["rs_nofilter.idx"].astype(np.int64))
+    close(po.query_certainty(m, q.clone()), fx["query_certainty"], 0, 0)
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_probe_offsets_and_local_map(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    assert np.array_equal(po.probe_offsets(2, 0.2).numpy(), fx["map.neighbor_dx"])
+    m2 = m.clone()
+    po.reset_local_map(m2, t(fx["sensor_pos"]), float(fx["cfg.local_map_radius"]), int(fx["map.cur_ts"]))
+    assert np.array_equal(m2.local_mask.numpy(), fx["map.local_mask"])
+    assert np.array_equal(m2.global2local.numpy(), fx["map.global2local"])
+    assert np.array_equal(m2.local_geo_features.numpy(), fx["map.local_geo_features"])
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+@pytest.mark.parametrize("local", [True, False])
+def test_query_feature(name, local):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    q = t(fx["q"])
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    color = "map.color_features" in fx
+    geo, col, w, nnc, cert = po.query_feature(m, q.clone(), None, k, wf, training_mode=False,
+                                              query_locally=local, query_color_feature=color)
+    tag = "qf_local" if local else "qf_global"
+    assert np.array_equal(nnc.numpy(), fx[tag + ".nn_counts"])
+    close(w, fx[tag + ".weight"], 0, 0)
+    close(geo, fx[tag + ".geo"], 0, 0)
+    close(cert, fx[tag + ".certainty"], 0, 0)
+    if color:
+        close(col, fx[tag + ".color"], 0, 0)
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_training_side_effects(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    po.query_feature(m, t(fx["q"]).clone(), t(fx["train_fx.ts"]), k, wf, training_mode=True,
+                     query_color_feature="map.color_features" in fx)
+    close(m.local_point_certainties, fx["train_fx.certainties_after"], 1e-6, 1e-6)
+    assert np.array_equal(m.local_point_ts_update.numpy(), fx["train_fx.ts_update_after"])
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_tracker_query(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    color = "map.color_features" in fx
+    cdec = decoder_from_fixture(fx, "color_mlp") if color else None
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    out = po.query_sdf(m, dec, t(fx["q"]), k, wf, color_dec=cdec, color_grad=color)
+    close(out["sdf"], fx["trk.sdf"], 1e-6, 1e-8)
+    close(out["grad"], fx["trk.grad"], 1e-5, 1e-8)
+    close(out["sdf_std"], fx["trk.sdf_std"], 1e-5, 1e-8)
+    close(out["certainty"], fx["trk.certainty"], 1e-6, 1e-7)
+    assert np.array_equal((out["nn_count"] >= int(fx["cfg.track_mask_query_nn_k"])).numpy(), fx["trk.mask"])
+    if color:
+        close(out["color"], fx["trk.color"], 1e-6, 1e-7)
+        close(out["color_grad"], fx["trk.color_grad"], 1e-5, 1e-8)
+
+
+@pytest.mark.parametrize("name", [n for n in QUERY_FIXTURES if "color" not in n])
+def test_registration_step(name):
+    fx = load_npz(name)
+    q = t(fx["q"])
+    mn, mx, max_std, gmd, gmg, lam = [float(v) for v in fx["reg.params"]]
+    out = po.registration_step(
+        q, t(fx["trk.sdf"]), t(fx["trk.grad"]), t(fx["trk.sdf_std"]),
+        torch.where(t(fx["trk.mask"]), 100, 0), torch.zeros(q.shape[0]),
+        1, mn, mx, max_std, gmd, gmg, lam)
+    assert out["valid_count"] == int(fx["reg.valid_count"])
+    close(out["residual_cm"], float(fx["reg.residual_cm"]), 1e-6, 0)
+    # fp32 J^T W J summation order depends on the BLAS thread count; the random-decoder system is
+    # poorly conditioned, so compare the fp64 solve at 2e-5
+    close(out["T"], fx["reg.T"], 2e-5, 2e-6)
+
+
+@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def test_mapping_iterations(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    color = "map.color_features" in fx
+    cdec = decoder_from_fixture(fx, "color_mlp") if color else None
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    sigma_m, sdf_scale, weight_e, eps_num, lr, adam_eps, wd, surf_range, weight_i = [float(v) for v in fx["cfg.floats"]]
+    m.local_geo_features.requires_grad_(True)
+    feats = [m.local_geo_features]
+    if color:
+        m.local_color_features.requires_grad_(True)
+        feats.append(m.local_color_features)
+    dec.requires_grad_(True)
+    groups = [dec.tensors()]
+    if color:
+        cdec.requires_grad_(True)
+        groups.append(cdec.tensors())
+    groups.append(feats)
+    opt = po.make_adam(groups, lr, adam_eps, wd)
+    for i in range(int(fx["n_iters"])):
+        loss, _ = po.mapping_loss(
+            m, dec, t(fx[f"batch{i}.coord"]), t(fx[f"batch{i}.sdf_label"]), t(fx[f"batch{i}.ts"]),
+            t(fx[f"batch{i}.weight"]), k, wf, sdf_scale, bool(fx["cfg.loss_weight_on"]), weight_e,
+            int(fx["cfg.gradient_decimation"]), eps_num, color_dec=cdec,
+            color_label=t(fx[f"batch{i}.color"]) if color else None, surface_range=surf_range, weight_i=weight_i)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    close(m.local_geo_features.detach(), fx["after.local_geo_features"], 1e-5, 1e-6)
+    close(m.local_point_certainties, fx["after.local_point_certainties"], 1e-5, 1e-5)
+    assert np.array_equal(m.local_point_ts_update.numpy(), fx["after.local_point_ts_update"])
+    for i, (w, b) in enumerate(dec.hidden):
+        close(w.detach(), fx[f"after.sdf_mlp.layers.{i}.weight"], 1e-5, 1e-6)
+        close(b.detach(), fx[f"after.sdf_mlp.layers.{i}.bias"], 1e-5, 1e-6)
+    close(dec.out[0].detach(), fx["after.sdf_mlp.lout.weight"], 1e-5, 1e-6)
+    if color:
+        close(m.local_color_features.detach(), fx["after.local_color_features"], 1e-5, 1e-6)
+        close(cdec.out[0].detach(), fx["after.color_mlp.lout.weight"], 1e-5, 1e-6)
