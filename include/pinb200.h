@@ -1,0 +1,205 @@
+/*
+ * pinb200.h -- C ABI of the B200-native (sm_100a) PIN-SLAM hot path.
+ *
+ * The reference (PRBonn/PIN_SLAM) is 100 % Python/PyTorch and has no native
+ * boundary of its own; the boundary it *does* have for this path is the Python
+ * method surface of model/neural_points.py::NeuralPoints and
+ * model/decoder.py::Decoder.  The entry points below are
+ * what a ctypes binding inside those methods calls (INTEGRATION.md shows the
+ * stub); each one names the reference code it replaces (file:line relative to
+ * the reference checkout).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller
+ *    (PyTorch) owns every buffer, outputs are pre-allocated by the caller;
+ *  - all floating data is fp32, ids are int32 (the library keeps int32 mirrors
+ *    of the reference's int64 `buffer_pt_index` / `global2local`), timestamps
+ *    int32, the optional rigid transform is fp64 (poses are fp64 in the
+ *    reference, utils/config.py:316);
+ *  - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and
+ *    never synchronise;
+ *  - return value 0 = ok, negative = error (pinb200_last_error() has the text);
+ *    no global mutable state apart from that thread-local error string.
+ */
+#ifndef PINB200_H
+#define PINB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINB200_VERSION 100 /* round 1 */
+#define PINB200_MAX_HIDDEN_LAYERS 4
+#define PINB200_MAX_K 16
+
+#define PINB200_OK 0
+#define PINB200_ERR_BAD_ARG (-1)
+#define PINB200_ERR_UNSUPPORTED (-2)
+#define PINB200_ERR_CUDA (-3)
+
+/* State of a neural point map as the kernels see it.
+ * Mirrors NeuralPoints' tensors, model/neural_points.py:82-136. */
+typedef struct pinb200_map_view {
+  /* voxel hash over the GLOBAL map */
+  const int32_t* slot_table;   /* [buffer_size] hash slot -> global point id, -1 empty   (buffer_pt_index, :88) */
+  int64_t buffer_size;         /* must be < 2^31 */
+  const float* points;         /* [n_global,3] neural_points (:92) */
+  const int32_t* ts_create;    /* [n_global] point_ts_create (:112) */
+  int64_t n_global;
+  const float* travel_dist;    /* [n_travel] travel_dist (:77), NULL if !time_filter */
+  int64_t n_travel;
+  const int32_t* global2local; /* [n_global+1] (:498-507) or NULL => query the global arrays (query_locally=False) */
+  /* arrays of the index space being queried: local_* if global2local != NULL, else the global ones */
+  const float* nb_points;      /* [n_nb,3] */
+  const float* nb_orient;      /* [n_nb,4] wxyz quaternions; may be NULL when !after_pgo */
+  const float* geo_feat;       /* [n_nb+1,F] last row = padding */
+  const float* color_feat;     /* [n_nb+1,F] or NULL */
+  float* certainty;            /* [n_nb]  read; atomically += IDW weight in training mode (:691) */
+  int32_t* ts_update;          /* [n_nb]  atomic max with the query ts in training mode (:699); may be NULL */
+  int64_t n_nb;
+  int32_t feature_dim;         /* F */
+  /* search neighbourhood, set_search_neighborhood (:910-947) */
+  const int32_t* probe_dx;     /* [n_probe,3] integer cell offsets (neighbor_dx) */
+  int32_t n_probe;             /* C */
+  float resolution;            /* voxel_size_m */
+  float max_valid_dist2;       /* 3*((n+1)*res)^2 */
+  /* temporal (travel-distance) window, :982-988 */
+  int32_t time_filter;         /* temporal_local_map_on && query_locally */
+  int32_t cur_ts;
+  float diff_travel_dist_local;
+  int32_t after_pgo;           /* rotate neighbour vectors by the point quaternion (:645) */
+} pinb200_map_view;
+
+/* Weights of one Decoder (model/decoder.py:43-51), torch nn.Linear layout. */
+typedef struct pinb200_decoder_view {
+  const float* w[PINB200_MAX_HIDDEN_LAYERS]; /* w[l]: [hidden_dim, in_l] row-major; in_0 = in_dim, in_l = hidden_dim */
+  const float* b[PINB200_MAX_HIDDEN_LAYERS]; /* b[l]: [hidden_dim] or NULL (mlp_bias_on False) */
+  const float* w_out;                        /* [out_dim, hidden_dim] */
+  const float* b_out;                        /* [out_dim] or NULL */
+  int32_t n_hidden;                          /* hidden_level */
+  int32_t hidden_dim;
+  int32_t in_dim;                            /* feature_dim + 3 (positional encoding off) */
+  int32_t out_dim;
+  float out_scale;                           /* sdf_scale (decoder.py:54-56); 1 for colour */
+  int32_t leaky_relu;                        /* mlp_leaky_relu */
+  int32_t sigmoid_out;                       /* 0: out*out_scale (Decoder.sdf), 1: sigmoid(out) (Decoder.regress_color) */
+} pinb200_decoder_view;
+
+typedef struct pinb200_query_opts {
+  int32_t nn_k;             /* config.query_nn_k */
+  int32_t weighted_first;   /* config.weighted_first */
+  int32_t training_mode;    /* certainty / ts scatter side effects (:685-710) */
+  int32_t need_grad;        /* also produce d sdf / d query (replaces tools.py:247 autograd.grad) */
+  const double* transform;  /* optional device ptr, 4x4 row-major fp64: q = T*p evaluated in fp32 (tools.py:534-553) */
+} pinb200_query_opts;
+
+/* Outputs of the fused query; any pointer may be NULL to skip that output. */
+typedef struct pinb200_query_out {
+  float* sdf;          /* [N]   IDW-combined SDF prediction in metres */
+  float* grad;         /* [N,3] d sdf / d q (w.r.t. the transformed point when `transform` is set) */
+  float* sdf_std;      /* [N]   IDW std of the per-neighbour SDFs (0 when weighted_first; tracker.py:317-323) */
+  int32_t* nn_count;   /* [N]   valid probes before top-K (:577) */
+  float* certainty;    /* [N]   IDW-averaged point certainty (:714) */
+  float* color;        /* [N,Cc] sigmoid colour head, needs color decoder */
+  float* color_grad;   /* [N,Cc,3] */
+  int32_t* knn_idx;    /* [N,K] ids in the queried index space, -1 invalid, ascending distance */
+  float* knn_dist2;    /* [N,K] squared distances (9e3 for invalid, :583) */
+  float* knn_weight;   /* [N,K] normalised IDW weights (:667-683) */
+  float* xyz;          /* [N,3] the (transformed) query points actually used */
+} pinb200_query_out;
+
+int pinb200_version(void);
+const char* pinb200_last_error(void);
+
+/* K1 -- fused voxel-hash kNN + IDW interpolation + decoder MLP (+ analytic
+ * gradient).  Replaces, in ONE launch:
+ *   NeuralPoints.radius_neighborhood_search  model/neural_points.py:950-1009
+ *   NeuralPoints.query_feature               model/neural_points.py:530-746
+ *   Decoder.mlp / sdf / regress_color        model/decoder.py:61-85,112
+ *   get_gradient (autograd.grad)             utils/tools.py:247-260
+ *   the IDW mean/std over K                  utils/tracker.py:313-328, utils/mapper.py:945-952
+ * color_dec may be NULL.  query_ts may be NULL. */
+int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_decoder_view* sdf_dec,
+                      const pinb200_decoder_view* color_dec, const float* query_xyz,
+                      const int32_t* query_ts, int64_t n, const pinb200_query_opts* opts,
+                      const pinb200_query_out* out, void* stream);
+
+/* Search only (no decoder): top-K ids / distances / weights / nn_count.
+ * model/neural_points.py:562-589,665-683. */
+int pinb200_knn_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, int32_t nn_k,
+                       int32_t* knn_idx, float* knn_dist2, float* knn_weight, int32_t* nn_count,
+                       void* stream);
+
+/* All-probe form of the radius search: dist2 [N,C] and GLOBAL ids [N,C] exactly
+ * as NeuralPoints.radius_neighborhood_search returns them (:950-1009). */
+int pinb200_radius_search(const pinb200_map_view* map, const float* query_xyz, int64_t n,
+                          float* dist2, int32_t* idx, void* stream);
+
+/* NeuralPoints.query_certainty (:1011-1032): max certainty over the probed
+ * cells, global arrays (map->global2local must be NULL, time_filter 0). */
+int pinb200_query_certainty(const pinb200_map_view* map, const float* query_xyz, int64_t n,
+                            float* out_certainty, void* stream);
+
+/* Materialise query_feature's per-neighbour feature vectors from saved kNN ids
+ * (compat path for callers that index the features, e.g. utils/mesher.py:127):
+ * out [N,K,F+3] (weighted_first=0) or [N,F+3] (weighted_first=1). `feat` is
+ * map->geo_feat or map->color_feat. model/neural_points.py:597-663,722-731. */
+int pinb200_gather_features(const pinb200_map_view* map, const float* feat, const float* query_xyz,
+                            const int32_t* knn_idx, const float* knn_weight, int64_t n, int32_t nn_k,
+                            int32_t weighted_first, float* out, void* stream);
+
+/* Flat layout of decoder gradients / Adam state used by K2/K3:
+ * [w0 | b0 | w1 | b1 | ... | w_out | b_out], each row-major as in the view. */
+int64_t pinb200_decoder_param_count(const pinb200_decoder_view* dec);
+
+/* K2 -- backward of one map-training batch.  Given the saved kNN ids/weights of
+ * the forward (pinb200_query_sdf with training_mode=1) and d loss / d sdf per
+ * query row, recomputes the decoder activations and accumulates
+ *   grad_feat [n_nb+1,F]  += d loss / d local_geo_features   (atomic scatter)
+ *   grad_dec  [param_count] += d loss / d decoder parameters (block-reduced, then atomic)
+ * Replaces loss.backward() for the SDF branch, utils/mapper.py:816-817
+ * (autograd reverse pass through neural_points.py:597-731 and decoder.py:61-85). */
+int pinb200_train_backward(const pinb200_map_view* map, const pinb200_decoder_view* dec,
+                           const float* feat, const float* query_xyz, const int32_t* knn_idx,
+                           const float* knn_weight, const float* dloss_dout, int64_t n, int32_t nn_k,
+                           int32_t weighted_first, float* grad_feat, float* grad_dec, void* stream);
+
+/* Loss heads of Mapper.mapping (utils/mapper.py:728-780, utils/loss.py:45-63):
+ * BCE-with-logits on the first n_main rows, Eikonal on the 6*n_eik numerical-
+ * gradient rows laid out [x+ | x- | y+ | y- | z+ | z-] after them
+ * (mapper.py:1002-1014).  Writes d loss / d sdf for every row (of the total loss
+ * bce + weight_e * eikonal) and losses[0]=bce, [1]=eikonal (unweighted). */
+int pinb200_mapping_loss(const float* sdf, const float* sdf_label, const float* weight, int64_t n_main,
+                         int64_t n_eik, float sigma, int32_t loss_weight_on, float weight_e,
+                         float eik_eps, float* dloss_dsdf, float* losses, void* stream);
+
+/* K3 -- Adam step, arithmetic of torch.optim.Adam (betas .9/.99, no amsgrad)
+ * as set up by utils/tools.py:153-203; `step` is the 1-based step count.
+ * Zeroes `grad` after use (opt.zero_grad folded in). */
+int pinb200_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                      void* stream);
+
+/* K4 -- registration: validity mask, Geman-McClure weights, and the 6x6 normal
+ * equations of point-to-implicit registration accumulated in one pass, then
+ * solved on device.  Replaces utils/tracker.py:409-524 (registration_step) and
+ * :652-679 (implicit_reg).  Inputs are per source point.
+ *  sums [64] fp64 workspace/outputs (zeroed by the call):
+ *    [0..35] J^T W J (row-major 6x6, unnormalised w), [36..41] -J^T W r,
+ *    [42] sum w, [43] sum |r|, [44] valid count, [45] sum w r^2
+ *  result [32] fp64: [0..15] delta T (4x4 row-major), [16] valid count,
+ *    [17] mean |r| in cm, [18..20] eigen-proxy: diag of normalised N[3:,3:], [21] w r^2 mean
+ *  If t_inout != NULL (device 4x4 fp64) it is updated in place: T <- delta_T @ T
+ *  (tracker.py:147). */
+int pinb200_gn_step(const float* xyz, const float* sdf, const float* grad, const float* sdf_std,
+                    const int32_t* nn_count, const float* sdf_label, const float* normals, int64_t n,
+                    int32_t min_nn, float min_grad_norm, float max_grad_norm, float max_sdf_std,
+                    float gm_dist, float gm_grad, float lm_lambda, double* sums, double* result,
+                    double* t_inout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINB200_H */

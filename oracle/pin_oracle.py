@@ -155,10 +155,10 @@ def build_map(
     assert geo_features.shape[0] == mg + 1
     table = torch.full((int(buffer_size),), -1, dtype=torch.int64, device=dev)
     slots = wrap_slot(hash_cells(cell_of(sample_points, resolution), buffer_size), buffer_size)
-    # serial last-writer-wins (deterministic restatement)
-    slots_l = slots.tolist()
-    for i, s in enumerate(slots_l):
-        table[s] = i
+    # serial last-writer-wins (numpy fancy assignment applies duplicates in order => deterministic)
+    tnp = table.cpu().numpy()
+    tnp[slots.cpu().numpy()] = __import__("numpy").arange(mg, dtype="int64")
+    table = torch.from_numpy(tnp).to(dev)
     m = OracleMap(
         resolution=float(resolution),
         buffer_size=int(buffer_size),

@@ -1,0 +1,98 @@
+"""ctypes binding of libpinb200.so (C ABI declared in include/pinb200.h).
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpinb200.so")
+
+MAX_HIDDEN = 4
+MAX_K = 16
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+c_f64p = C.c_void_p
+
+
+class MapView(C.Structure):
+    _fields_ = [
+        ("slot_table", c_i32p), ("buffer_size", C.c_int64), ("points", c_f32p), ("ts_create", c_i32p),
+        ("n_global", C.c_int64), ("travel_dist", c_f32p), ("n_travel", C.c_int64), ("global2local", c_i32p),
+        ("nb_points", c_f32p), ("nb_orient", c_f32p), ("geo_feat", c_f32p), ("color_feat", c_f32p),
+        ("certainty", c_f32p), ("ts_update", c_i32p), ("n_nb", C.c_int64), ("feature_dim", C.c_int32),
+        ("probe_dx", c_i32p), ("n_probe", C.c_int32), ("resolution", C.c_float), ("max_valid_dist2", C.c_float),
+        ("time_filter", C.c_int32), ("cur_ts", C.c_int32), ("diff_travel_dist_local", C.c_float),
+        ("after_pgo", C.c_int32),
+    ]
+
+
+class DecoderView(C.Structure):
+    _fields_ = [
+        ("w", c_f32p * MAX_HIDDEN), ("b", c_f32p * MAX_HIDDEN), ("w_out", c_f32p), ("b_out", c_f32p),
+        ("n_hidden", C.c_int32), ("hidden_dim", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
+        ("out_scale", C.c_float), ("leaky_relu", C.c_int32), ("sigmoid_out", C.c_int32),
+    ]
+
+
+class QueryOpts(C.Structure):
+    _fields_ = [("nn_k", C.c_int32), ("weighted_first", C.c_int32), ("training_mode", C.c_int32),
+                ("need_grad", C.c_int32), ("transform", c_f64p)]
+
+
+class QueryOut(C.Structure):
+    _fields_ = [("sdf", c_f32p), ("grad", c_f32p), ("sdf_std", c_f32p), ("nn_count", c_i32p),
+                ("certainty", c_f32p), ("color", c_f32p), ("color_grad", c_f32p), ("knn_idx", c_i32p),
+                ("knn_dist2", c_f32p), ("knn_weight", c_f32p), ("xyz", c_f32p)]
+
+
+# name -> (restype, argtypes); every symbol include/pinb200.h declares
+SIGNATURES = {
+    "pinb200_version": (C.c_int, []),
+    "pinb200_last_error": (C.c_char_p, []),
+    "pinb200_query_sdf": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,
+                                    c_i32p, C.c_int64, C.POINTER(QueryOpts), C.POINTER(QueryOut), C.c_void_p]),
+    "pinb200_knn_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, C.c_int32, c_i32p, c_f32p, c_f32p,
+                                     c_i32p, C.c_void_p]),
+    "pinb200_radius_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, c_f32p, c_i32p, C.c_void_p]),
+    "pinb200_query_certainty": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, c_f32p, C.c_void_p]),
+    "pinb200_gather_features": (C.c_int, [C.POINTER(MapView), c_f32p, c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int32,
+                                          C.c_int32, c_f32p, C.c_void_p]),
+    "pinb200_decoder_param_count": (C.c_int64, [C.POINTER(DecoderView)]),
+    "pinb200_train_backward": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), c_f32p, c_f32p, c_i32p, c_f32p,
+                                         c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
+    "pinb200_mapping_loss": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_float, C.c_int32,
+                                       C.c_float, C.c_float, c_f32p, c_f32p, C.c_void_p]),
+    "pinb200_adam_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, C.c_double, C.c_int32, C.c_void_p]),
+    "pinb200_gn_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
+                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f64p, c_f64p,
+                                  c_f64p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libpinb200.so (once) and declare every prototype.  Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or pin_slam_b200/csrc/build.sh -- there is no CPU/PyTorch fallback for the hot path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pinb200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,122 @@
+// K3 (Adam) and the loss heads of one map-training iteration.
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pinb {
+
+// torch.optim.Adam single-tensor arithmetic (torch/optim/adam.py, _single_tensor_adam),
+// as configured by the reference's setup_optimizer (utils/tools.py:153-203):
+//   grad += wd * param ; m.lerp_(grad, 1-b1) ; v = v*b2 + (1-b2)*g*g ;
+//   denom = sqrt(v)/sqrt(bc2) + eps ; param += -(lr/bc1) * m/denom
+__global__ void adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float one_minus_b1, float b2, float one_minus_b2,
+                            float bc2_sqrt, float eps, float neg_step_size, float wd) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = grad[i];
+    grad[i] = 0.f;  // opt.zero_grad() for the next iteration
+    float p = param[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    float mi = m[i], vi = v[i];
+    mi = mi + one_minus_b1 * (g - mi);
+    vi = vi * b2 + one_minus_b2 * g * g;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p = p + neg_step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+    param[i] = p;
+  }
+}
+
+// BCE-with-logits on the main rows + Eikonal on the numerical-gradient rows.
+// utils/mapper.py:728-780, utils/loss.py:45-63, utils/mapper.py:1002-1014.
+__global__ void mapping_loss_kernel(const float* __restrict__ sdf, const float* __restrict__ label,
+                                    const float* __restrict__ weight, long long n_main, long long n_eik, float sigma,
+                                    int weighted, float weight_e, float eik_eps, float* __restrict__ dl,
+                                    float* __restrict__ losses) {
+  float bce = 0.f, eik = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float inv_n = 1.f / (float)n_main;
+  for (long long i = t0; i < n_main; i += stride) {
+    const float z = sdf[i] / sigma;
+    const float t = 1.f / (1.f + expf(-label[i] / sigma));
+    const float w = weighted ? fabsf(weight[i]) : 1.f;  // |weight| (mapper.py:729)
+    // (1-t)*z + log1p(exp(-|z|)) + max(-z,0)
+    bce += w * ((1.f - t) * z + log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f));
+    const float sg = 1.f / (1.f + expf(-z));
+    dl[i] = w * (sg - t) * inv_n / sigma;
+  }
+  if (n_eik > 0) {
+    const float* s = sdf + n_main;
+    float* d = dl + n_main;
+    const float inv2e = 1.f / (2.f * eik_eps);
+    for (long long j = t0; j < n_eik; j += stride) {
+      const float gx = (s[j] - s[n_eik + j]) * inv2e;
+      const float gy = (s[2 * n_eik + j] - s[3 * n_eik + j]) * inv2e;
+      const float gz = (s[4 * n_eik + j] - s[5 * n_eik + j]) * inv2e;
+      const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+      const float e = nrm - 1.f;
+      eik += e * e;
+      const float c = nrm > 0.f ? weight_e * 2.f * e / ((float)n_eik * nrm) * inv2e : 0.f;
+      d[j] = c * gx;
+      d[n_eik + j] = -c * gx;
+      d[2 * n_eik + j] = c * gy;
+      d[3 * n_eik + j] = -c * gy;
+      d[4 * n_eik + j] = c * gz;
+      d[5 * n_eik + j] = -c * gz;
+    }
+  }
+  if (losses) {
+    bce = warp_sum(bce);
+    eik = warp_sum(eik);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(losses + 0, bce * inv_n);
+      if (n_eik > 0) atomicAdd(losses + 1, eik / (float)n_eik);
+    }
+  }
+}
+
+}  // namespace pinb
+
+using namespace pinb;
+
+extern "C" int pinb200_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                                 double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                                 void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) {
+    set_error("adam_step: null argument or step < 1");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const double step_size = lr / bc1;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1),
+                                                      (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps,
+                                                      (float)(-step_size), (float)weight_decay);
+  return check_launch("adam_kernel");
+}
+
+extern "C" int pinb200_mapping_loss(const float* sdf, const float* sdf_label, const float* weight, int64_t n_main,
+                                    int64_t n_eik, float sigma, int32_t loss_weight_on, float weight_e, float eik_eps,
+                                    float* dloss_dsdf, float* losses, void* stream) {
+  if (!sdf || !sdf_label || !dloss_dsdf || n_main <= 0 || (loss_weight_on && !weight)) {
+    set_error("mapping_loss: null argument / empty batch");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (losses) {
+    const cudaError_t e = cudaMemsetAsync(losses, 0, 2 * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+      return PINB200_ERR_CUDA;
+    }
+  }
+  const long long work = std::max<long long>(n_main, n_eik);
+  const int grid = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 4);
+  mapping_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sdf, sdf_label, weight, n_main, n_eik, sigma,
+                                                              loss_weight_on, weight_e, eik_eps, dloss_dsdf, losses);
+  return check_launch("mapping_loss_kernel");
+}

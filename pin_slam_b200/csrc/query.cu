@@ -1,0 +1,780 @@
+// K1: fused voxel-hash kNN + IDW interpolation + decoder MLP + analytic d/dq.
+//
+// One CTA (128 threads) owns a tile of 128 decoder rows:
+//   weighted_first=1 : 128 queries, one row each (features IDW-averaged first)
+//   weighted_first=0 : floor(128/K) queries, K rows each (decode every neighbour)
+// Phase A (warp per query): hash the query's cell, probe the C neighbour cells of
+//   the voxel hash table (one probe per lane, 32 at a time), age/distance filter,
+//   in-register warp top-K, IDW weights, coalesced gather of the neighbour feature
+//   rows (a 32-float row == one 128 B warp load), write the decoder input into the
+//   transposed shared-memory tile.
+// Phase B (thread per row): the tiny MLP forward and, if requested, the backward
+//   pass w.r.t. the decoder input, weights broadcast from shared memory.
+// Phase C (warp per query / thread per query): chain rule through the IDW weights
+//   and the neighbour vectors -> d sdf / d query, sdf std, outputs.
+//
+// Replaces model/neural_points.py:530-746,950-1009, model/decoder.py:61-85,112,
+// utils/tools.py:247-260, utils/tracker.py:313-328 of the reference.
+#include <algorithm>
+
+#include "mlp.cuh"
+
+namespace pinb {
+
+struct QueryLayout {  // float offsets into dynamic smem
+  DecSmem dec;
+  int delta, act, knn_idx, knn_d2, q, out, nn, mask, total;
+};
+
+struct QueryParams {
+  pinb200_map_view map;
+  pinb200_decoder_view dec;
+  pinb200_query_opts opts;
+  pinb200_query_out out;
+  const float* query_xyz;
+  const int32_t* query_ts;
+  const float* feat;  // feature table decoded by `dec` (geo or colour)
+  long long n;
+  int use_saved_knn;  // 1: take kNN from out.knn_idx / out.knn_dist2 (decode-only launch, e.g. colour head)
+  int is_color;       // outputs go to out.color / out.color_grad instead of sdf / grad
+  int n_tiles;
+  int qpt;  // queries per tile
+  QueryLayout lay;
+};
+
+// ---------------------------------------------------------------------------
+// phase A helpers
+// ---------------------------------------------------------------------------
+
+// IDW-average the K neighbour feature rows into act[0..F) of `row` (weighted_first).
+__device__ __forceinline__ void gather_weighted(const float* __restrict__ feat, int F, int K, int my_idx, float my_w,
+                                                int lane, float* s_act, int row) {
+  if (F >= 32) {
+    const int nj = F >> 5;  // F is a multiple of 32 (checked on the host), <= 128
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) {
+      const int lk = __shfl_sync(FULL, my_idx, k);
+      const float wk = __shfl_sync(FULL, my_w, k);
+      if (lk >= 0) {
+        const float* fr = feat + (size_t)lk * F + lane;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (jj < nj) acc[jj] = fmaf(wk, __ldg(fr + 32 * jj), acc[jj]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (jj < nj) s_act[(32 * jj + lane) * ACT_LD + row] = acc[jj];
+  } else {
+    // F in {4,8,16}: 32/F neighbours per warp load
+    const int g = 32 / F, ksub = lane / F, j = lane - ksub * F;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += g) {
+      const int k = k0 + ksub;
+      const int lk = __shfl_sync(FULL, my_idx, k < K ? k : 0);
+      const float wk = __shfl_sync(FULL, my_w, k < K ? k : 0);
+      if (k < K && lk >= 0) acc = fmaf(wk, __ldg(feat + (size_t)lk * F + j), acc);
+    }
+    for (int off = F; off < 32; off <<= 1) acc += __shfl_xor_sync(FULL, acc, off);
+    if (lane < F) s_act[lane * ACT_LD + row] = acc;
+  }
+}
+
+// Copy the K neighbour feature rows into act[0..F) of rows row0..row0+K (decode every neighbour).
+__device__ __forceinline__ void gather_rows(const float* __restrict__ feat, int F, int K, int my_idx, int lane,
+                                            float* s_act, int row0) {
+  const int items = K * F;
+  for (int it0 = 0; it0 < items; it0 += 32) {
+    const int it = it0 + lane;
+    const int k = it / F, j = it - k * F;
+    const int lk = __shfl_sync(FULL, my_idx, k < K ? k : 0);
+    if (it < items) s_act[j * ACT_LD + row0 + k] = lk >= 0 ? __ldg(feat + (size_t)lk * F + j) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------
+template <int H, int DP>
+__global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ QueryParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const pinb200_map_view& m = p.map;
+  const int K = p.opts.nn_k, F = m.feature_dim, D = F + 3, L = p.dec.n_hidden;
+  const int OC = p.dec.out_dim;
+  const bool wf = p.opts.weighted_first != 0;
+  const bool need_grad = p.opts.need_grad != 0;
+  const bool leaky = p.dec.leaky_relu != 0;
+  const float* __restrict__ feat = p.feat;
+
+  uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem + p.lay.delta);
+  float* s_act = smem + p.lay.act;
+  int* s_idx = reinterpret_cast<int*>(smem + p.lay.knn_idx);
+  float* s_d2 = smem + p.lay.knn_d2;
+  float* s_q = smem + p.lay.q;
+  float* s_out = smem + p.lay.out;
+  int* s_nn = reinterpret_cast<int*>(smem + p.lay.nn);
+  uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + p.lay.mask);
+
+  stage_decoder(p.dec, p.lay.dec, smem, DP, need_grad);
+  if (!p.use_saved_knn) fill_probe_deltas(m, s_delta);
+  __syncthreads();
+
+  const int QPT = p.qpt;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const long long q0 = (long long)tile * QPT;
+
+    // ===================== phase A: search + gather (warp per query) =====================
+    for (int ql = warp; ql < QPT; ql += TILE / 32) {
+      const long long qi = q0 + ql;
+      const int row0 = wf ? ql : ql * K;
+      const int nrows = wf ? 1 : K;
+      if (qi >= p.n) {  // tail padding: keep phase B finite
+        for (int e = lane; e < D * nrows; e += 32) s_act[(e / nrows) * ACT_LD + row0 + (e % nrows)] = 0.f;
+        if (lane < K) {
+          s_idx[ql * K + lane] = -1;
+          s_d2[ql * K + lane] = INVALID_D2;
+        }
+        if (lane == 0) s_nn[ql] = 0;
+        continue;
+      }
+      float qx = __ldg(p.query_xyz + 3 * qi + 0), qy = __ldg(p.query_xyz + 3 * qi + 1),
+            qz = __ldg(p.query_xyz + 3 * qi + 2);
+      if (p.opts.transform) {  // q = T p in fp32 (utils/tools.py:534-553)
+        const double* T = p.opts.transform;
+        const float t00 = (float)T[0], t01 = (float)T[1], t02 = (float)T[2], t03 = (float)T[3];
+        const float t10 = (float)T[4], t11 = (float)T[5], t12 = (float)T[6], t13 = (float)T[7];
+        const float t20 = (float)T[8], t21 = (float)T[9], t22 = (float)T[10], t23 = (float)T[11];
+        const float x = fmaf(qz, t02, fmaf(qy, t01, qx * t00)) + t03;
+        const float y = fmaf(qz, t12, fmaf(qy, t11, qx * t10)) + t13;
+        const float z = fmaf(qz, t22, fmaf(qy, t21, qx * t20)) + t23;
+        qx = x;
+        qy = y;
+        qz = z;
+      }
+      Knn kn;
+      if (p.use_saved_knn) {
+        kn.idx = lane < K ? __ldg(p.out.knn_idx + qi * K + lane) : -1;
+        kn.d2 = lane < K ? __ldg(p.out.knn_dist2 + qi * K + lane) : INVALID_D2;
+        kn.count = __ldg(p.out.nn_count + qi);
+      } else {
+        kn = knn_search_warp(m, s_delta, qx, qy, qz, K, lane);
+      }
+      const bool valid = kn.idx >= 0;
+      float u, inv_s;
+      const float w = idw_weight(kn.d2, valid, kn.count, K, lane, u, inv_s);
+
+      // neighbour vector n_k = q - p_k (rotated into the point frame after PGO), zero if invalid (:632-651)
+      float nx = 0.f, ny = 0.f, nz = 0.f, cert = 0.f;
+      if (valid) {
+        const float* pp = m.nb_points + 3 * (size_t)kn.idx;
+        nx = __fsub_rn(qx, __ldg(pp + 0));
+        ny = __fsub_rn(qy, __ldg(pp + 1));
+        nz = __fsub_rn(qz, __ldg(pp + 2));
+        if (m.after_pgo) {
+          const float* qq = m.nb_orient + 4 * (size_t)kn.idx;
+          quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
+        }
+        cert = m.certainty[kn.idx];
+      }
+      if (!p.is_color) {
+        // queried certainty (:713-718) uses the values gathered before this query's own scatter
+        const float qc = warp_sum(cert * w);
+        if (p.opts.training_mode && valid) {  // (:685-710); invalid entries add 0 / max with 0 in the reference
+          atomicAdd(m.certainty + kn.idx, w);
+          if (m.ts_update && p.query_ts) atomicMax(m.ts_update + kn.idx, __ldg(p.query_ts + qi));
+        }
+        if (lane == 0) {
+          if (p.out.certainty) p.out.certainty[qi] = qc;
+          if (p.out.nn_count && !p.use_saved_knn) p.out.nn_count[qi] = kn.count;
+          if (p.out.xyz) {
+            p.out.xyz[3 * qi + 0] = qx;
+            p.out.xyz[3 * qi + 1] = qy;
+            p.out.xyz[3 * qi + 2] = qz;
+          }
+        }
+        if (lane < K && !p.use_saved_knn) {
+          if (p.out.knn_idx) p.out.knn_idx[qi * K + lane] = kn.idx;
+          if (p.out.knn_dist2) p.out.knn_dist2[qi * K + lane] = kn.d2;
+          if (p.out.knn_weight) p.out.knn_weight[qi * K + lane] = w;
+        }
+      }
+      if (lane < K) {
+        s_idx[ql * K + lane] = kn.idx;
+        s_d2[ql * K + lane] = kn.d2;
+      }
+      if (lane == 0) {
+        s_nn[ql] = kn.count;
+        s_q[3 * ql + 0] = qx;
+        s_q[3 * ql + 1] = qy;
+        s_q[3 * ql + 2] = qz;
+      }
+      if (wf) {
+        gather_weighted(feat, F, K, kn.idx, w, lane, s_act, row0);
+        const float sx = warp_sum(w * nx), sy = warp_sum(w * ny), sz = warp_sum(w * nz);
+        if (lane == 0) {
+          s_act[(F + 0) * ACT_LD + row0] = sx;
+          s_act[(F + 1) * ACT_LD + row0] = sy;
+          s_act[(F + 2) * ACT_LD + row0] = sz;
+        }
+      } else {
+        gather_rows(feat, F, K, kn.idx, lane, s_act, row0);
+        if (lane < K) {
+          s_act[(F + 0) * ACT_LD + row0 + lane] = nx;
+          s_act[(F + 1) * ACT_LD + row0 + lane] = ny;
+          s_act[(F + 2) * ACT_LD + row0 + lane] = nz;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ===================== phase B: decoder forward (thread per row) =====================
+    float* col = s_act + tid;
+    float h[H];
+    {
+      int n_in = D;
+      for (int l = 0; l < L; ++l) {
+        matvec_col<H>(smem + p.lay.dec.wt[l], smem + p.lay.dec.b[l], col, n_in, h);
+        s_mask[l * TILE + tid] = activate<H>(h, leaky);
+        if (l < L - 1) store_col<H>(col, h, H);
+        n_in = H;
+      }
+    }
+    float dval[4];  // d value / d pre-activation output, per channel (OC <= 4)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < OC) {
+        const float* wo = smem + p.lay.dec.wout + c * H;
+        float o = smem[p.lay.dec.bout + c];
+#pragma unroll
+        for (int j = 0; j < H; ++j) o = fmaf(wo[j], h[j], o);
+        float v;
+        if (p.dec.sigmoid_out) {
+          v = 1.f / (1.f + expf(-o));
+          dval[c] = v * (1.f - v);
+        } else {
+          v = o * p.dec.out_scale;
+          dval[c] = p.dec.out_scale;
+        }
+        s_out[tid * OC + c] = v;
+      }
+    }
+
+    // ============ per output channel: backward to the decoder input, then phase C ============
+    const int n_pass = need_grad ? OC : 1;
+    for (int c = 0; c < n_pass; ++c) {
+      if (need_grad) {
+        float g[H];
+        {
+          const float* wo = smem + p.lay.dec.wout + c * H;
+#pragma unroll
+          for (int j = 0; j < H; ++j) g[j] = wo[j];
+          apply_mask<H>(g, s_mask[(L - 1) * TILE + tid], leaky);
+        }
+        for (int l = L - 1; l >= 1; --l) {
+          store_col<H>(col, g, H);
+          matvec_col<H>(smem + p.lay.dec.w[l], nullptr, col, H, g);
+          apply_mask<H>(g, s_mask[(l - 1) * TILE + tid], leaky);
+        }
+        store_col<H>(col, g, H);
+        float gx[DP];
+        matvec_col<DP>(smem + p.lay.dec.w[0], nullptr, col, H, gx);
+        const float dv = c == 0 ? dval[0] : (c == 1 ? dval[1] : (c == 2 ? dval[2] : dval[3]));
+#pragma unroll
+        for (int d = 0; d < DP; ++d)
+          if (d < D) col[d * ACT_LD] = gx[d] * dv;
+      }
+      __syncthreads();
+
+      // ===================== phase C: chain rule through IDW + outputs =====================
+      if (wf) {
+        for (int ql = warp; ql < QPT; ql += TILE / 32) {
+          const long long qi = q0 + ql;
+          if (qi >= p.n) continue;
+          const float val = s_out[ql * OC + c];
+          float gq0 = 0.f, gq1 = 0.f, gq2 = 0.f;
+          if (need_grad) {
+            const int nn = s_nn[ql];
+            const int lk = lane < K ? s_idx[ql * K + lane] : -1;
+            const float d2 = lane < K ? s_d2[ql * K + lane] : INVALID_D2;
+            const bool valid = lk >= 0;
+            float u, inv_s;
+            const float w = idw_weight(d2, valid, nn, K, lane, u, inv_s);
+            const float qx = s_q[3 * ql], qy = s_q[3 * ql + 1], qz = s_q[3 * ql + 2];
+            const float gn0 = s_act[(F + 0) * ACT_LD + ql], gn1 = s_act[(F + 1) * ACT_LD + ql],
+                        gn2 = s_act[(F + 2) * ACT_LD + ql];
+            float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
+            if (valid) {
+              const float* pp = m.nb_points + 3 * (size_t)lk;
+              dx = qx - __ldg(pp);
+              dy = qy - __ldg(pp + 1);
+              dz = qz - __ldg(pp + 2);
+              nx = dx;
+              ny = dy;
+              nz = dz;
+              r0 = gn0;
+              r1 = gn1;
+              r2 = gn2;
+              if (m.after_pgo) {
+                const float* qq = m.nb_orient + 4 * (size_t)lk;
+                const float a = __ldg(qq), b = __ldg(qq + 1), cc = __ldg(qq + 2), dd = __ldg(qq + 3);
+                quat_rotate_passive(a, b, cc, dd, dx, dy, dz, nx, ny, nz);
+                quat_rotate_active(a, b, cc, dd, gn0, gn1, gn2, r0, r1, r2);
+              }
+            }
+            // a_k = <g_xbar, v_k>, v_k = [f_k ; n_k]
+            float a_k = 0.f;
+            {
+              float gxl[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = lane + 32 * jj;
+                gxl[jj] = j < F ? s_act[j * ACT_LD + ql] : 0.f;
+              }
+              for (int k = 0; k < K; ++k) {
+                const int lkb = __shfl_sync(FULL, lk, k);
+                float part = 0.f;
+                if (lkb >= 0) {
+                  const float* fr = feat + (size_t)lkb * F;
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const int j = lane + 32 * jj;
+                    if (j < F) part = fmaf(gxl[jj], __ldg(fr + j), part);
+                  }
+                }
+                part = warp_sum(part);
+                if (lane == k) a_k = part;
+              }
+              a_k += gn0 * nx + gn1 * ny + gn2 * nz;
+            }
+            const float abar = warp_sum(w * a_k);
+            // d w_k / d q = w_k (c_k - sum_j w_j c_j), c_k = -2 u_k (q - p_k)
+            const float coef = w * (a_k - abar) * (-2.f * u);
+            gq0 = warp_sum(fmaf(coef, dx, w * r0));
+            gq1 = warp_sum(fmaf(coef, dy, w * r1));
+            gq2 = warp_sum(fmaf(coef, dz, w * r2));
+          }
+          if (lane == 0) {
+            if (!p.is_color) {
+              if (p.out.sdf) p.out.sdf[qi] = val;
+              if (p.out.sdf_std) p.out.sdf_std[qi] = 0.f;
+              if (need_grad && p.out.grad) {
+                p.out.grad[3 * qi + 0] = gq0;
+                p.out.grad[3 * qi + 1] = gq1;
+                p.out.grad[3 * qi + 2] = gq2;
+              }
+            } else {
+              if (p.out.color) p.out.color[qi * OC + c] = val;
+              if (need_grad && p.out.color_grad) {
+                p.out.color_grad[(qi * OC + c) * 3 + 0] = gq0;
+                p.out.color_grad[(qi * OC + c) * 3 + 1] = gq1;
+                p.out.color_grad[(qi * OC + c) * 3 + 2] = gq2;
+              }
+            }
+          }
+        }
+        if (!need_grad && OC > 1 && p.is_color) {  // remaining colour channels without gradients
+          for (int ql = tid; ql < QPT; ql += TILE) {
+            const long long qi = q0 + ql;
+            if (qi < p.n && p.out.color)
+              for (int cc = 1; cc < OC; ++cc) p.out.color[qi * OC + cc] = s_out[ql * OC + cc];
+          }
+        }
+      } else {
+        // decode-every-neighbour: thread per query combines its K rows (tracker.py:317-323)
+        if (tid < QPT && q0 + tid < p.n) {
+          const int ql = tid;
+          const long long qi = q0 + ql;
+          const int nn = s_nn[ql];
+          const float qx = s_q[3 * ql], qy = s_q[3 * ql + 1], qz = s_q[3 * ql + 2];
+          float usum = 0.f;
+          for (int k = 0; k < K; ++k) {
+            const bool v = s_idx[ql * K + k] >= 0;
+            usum += nn == 0 ? IDW_EPS : (v ? __fdiv_rn(1.0f, s_d2[ql * K + k] + IDW_EPS) : 0.f);
+          }
+          const int n_ch = (need_grad || !p.is_color) ? 1 : OC;
+          for (int ch = 0; ch < n_ch; ++ch) {
+            const int cc = need_grad ? c : ch;
+            float mean = 0.f;
+            for (int k = 0; k < K; ++k) {
+              const bool v = s_idx[ql * K + k] >= 0;
+              const float uk = nn == 0 ? IDW_EPS : (v ? __fdiv_rn(1.0f, s_d2[ql * K + k] + IDW_EPS) : 0.f);
+              const float wk = v ? __fdiv_rn(uk, usum) : 0.f;
+              mean = fmaf(wk, s_out[(ql * K + k) * OC + cc], mean);
+            }
+            float var = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            for (int k = 0; k < K; ++k) {
+              const int lk = s_idx[ql * K + k];
+              if (lk < 0) continue;
+              const float uk = nn == 0 ? 0.f : __fdiv_rn(1.0f, s_d2[ql * K + k] + IDW_EPS);
+              const float wk = __fdiv_rn(nn == 0 ? IDW_EPS : uk, usum);
+              const float sk = s_out[(ql * K + k) * OC + cc];
+              const float dm = sk - mean;
+              var = fmaf(wk * dm, dm, var);
+              if (need_grad) {
+                const int row = ql * K + k;
+                float r0 = s_act[(F + 0) * ACT_LD + row], r1 = s_act[(F + 1) * ACT_LD + row],
+                      r2 = s_act[(F + 2) * ACT_LD + row];
+                const float* pp = m.nb_points + 3 * (size_t)lk;
+                const float dx = qx - __ldg(pp), dy = qy - __ldg(pp + 1), dz = qz - __ldg(pp + 2);
+                if (m.after_pgo) {
+                  const float* qq = m.nb_orient + 4 * (size_t)lk;
+                  quat_rotate_active(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), r0, r1, r2, r0, r1, r2);
+                }
+                const float coef = wk * dm * (-2.f * uk);
+                g0 += fmaf(coef, dx, wk * r0);
+                g1 += fmaf(coef, dy, wk * r1);
+                g2 += fmaf(coef, dz, wk * r2);
+              }
+            }
+            if (!p.is_color) {
+              if (p.out.sdf) p.out.sdf[qi] = mean;
+              if (p.out.sdf_std) p.out.sdf_std[qi] = sqrtf(var);
+              if (need_grad && p.out.grad) {
+                p.out.grad[3 * qi + 0] = g0;
+                p.out.grad[3 * qi + 1] = g1;
+                p.out.grad[3 * qi + 2] = g2;
+              }
+            } else {
+              if (p.out.color) p.out.color[qi * OC + cc] = mean;
+              if (need_grad && p.out.color_grad) {
+                p.out.color_grad[(qi * OC + cc) * 3 + 0] = g0;
+                p.out.color_grad[(qi * OC + cc) * 3 + 1] = g1;
+                p.out.color_grad[(qi * OC + cc) * 3 + 2] = g2;
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// search-only kernels (warp per query, no decoder)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE) knn_kernel(const __grid_constant__ pinb200_map_view m,
+                                                   const float* __restrict__ query_xyz, long long n, int K,
+                                                   int32_t* knn_idx, float* knn_d2, float* knn_w, int32_t* nn_count) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem);
+  fill_probe_deltas(m, s_delta);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  for (long long qi = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); qi < n; qi += (long long)gridDim.x * wpb) {
+    const float qx = __ldg(query_xyz + 3 * qi), qy = __ldg(query_xyz + 3 * qi + 1), qz = __ldg(query_xyz + 3 * qi + 2);
+    const Knn kn = knn_search_warp(m, s_delta, qx, qy, qz, K, lane);
+    float u, inv_s;
+    const float w = idw_weight(kn.d2, kn.idx >= 0, kn.count, K, lane, u, inv_s);
+    if (lane < K) {
+      if (knn_idx) knn_idx[qi * K + lane] = kn.idx;
+      if (knn_d2) knn_d2[qi * K + lane] = kn.d2;
+      if (knn_w) knn_w[qi * K + lane] = w;
+    }
+    if (lane == 0 && nn_count) nn_count[qi] = kn.count;
+  }
+}
+
+// all-probe radius search: dist2 [N,C], global ids [N,C] (model/neural_points.py:950-1009)
+__global__ void __launch_bounds__(TILE) radius_kernel(const __grid_constant__ pinb200_map_view m,
+                                                      const float* __restrict__ query_xyz, long long n, float* dist2,
+                                                      int32_t* idx, float* max_cert) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem);
+  fill_probe_deltas(m, s_delta);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  const int C = m.n_probe;
+  for (long long qi = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); qi < n; qi += (long long)gridDim.x * wpb) {
+    const float qx = __ldg(query_xyz + 3 * qi), qy = __ldg(query_xyz + 3 * qi + 1), qz = __ldg(query_xyz + 3 * qi + 2);
+    const uint32_t r0 = base_slot(m, qx, qy, qz);
+    const float td_cur = m.time_filter ? __ldg(m.travel_dist + m.cur_ts) : 0.f;
+    float best = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float d2;
+      int li, gi;
+      probe_cell(m, r0, s_delta[c], qx, qy, qz, td_cur, d2, li, gi);
+      if (dist2) dist2[qi * C + c] = d2;
+      if (idx) idx[qi * C + c] = gi;
+      if (max_cert && gi >= 0) best = fmaxf(best, m.certainty[gi]);  // query_certainty (:1025-1028)
+    }
+    if (max_cert) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
+      if (lane == 0) max_cert[qi] = best;
+    }
+  }
+}
+
+// query_feature's materialised feature vectors from saved kNN (compat path)
+__global__ void __launch_bounds__(TILE) gather_kernel(const __grid_constant__ pinb200_map_view m,
+                                                      const float* __restrict__ feat,
+                                                      const float* __restrict__ query_xyz,
+                                                      const int32_t* __restrict__ knn_idx,
+                                                      const float* __restrict__ knn_w, long long n, int K, int wf,
+                                                      float* out) {
+  const int F = m.feature_dim, D = F + 3;
+  const long long total = wf ? n * D : n * K * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const long long r = e / D;
+    const long long qi = wf ? r : r / K;
+    float acc = 0.f;
+    const int k_lo = wf ? 0 : (int)(r % K), k_hi = wf ? K : k_lo + 1;
+    for (int k = k_lo; k < k_hi; ++k) {
+      const int lk = knn_idx[qi * K + k];
+      if (lk < 0) continue;
+      float v;
+      if (d < F) {
+        v = __ldg(feat + (size_t)lk * F + d);
+      } else {
+        float nx = query_xyz[3 * qi] - m.nb_points[3 * (size_t)lk];
+        float ny = query_xyz[3 * qi + 1] - m.nb_points[3 * (size_t)lk + 1];
+        float nz = query_xyz[3 * qi + 2] - m.nb_points[3 * (size_t)lk + 2];
+        if (m.after_pgo) {
+          const float* qq = m.nb_orient + 4 * (size_t)lk;
+          quat_rotate_passive(qq[0], qq[1], qq[2], qq[3], nx, ny, nz, nx, ny, nz);
+        }
+        v = d == F ? nx : (d == F + 1 ? ny : nz);
+      }
+      acc = wf ? fmaf(knn_w[qi * K + k], v, acc) : v;
+    }
+    out[e] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int validate_map(const pinb200_map_view* m, bool need_feat) {
+  if (!m || !m->slot_table || !m->points || !m->probe_dx || m->n_probe <= 0) {
+    set_error("map view: null table/points/probe offsets");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (m->buffer_size <= 0 || m->buffer_size >= (1LL << 31)) {
+    set_error("map view: buffer_size %lld out of range (0, 2^31)", (long long)m->buffer_size);
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (m->time_filter && (!m->ts_create || !m->travel_dist)) {
+    set_error("map view: time_filter needs ts_create and travel_dist");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (need_feat) {
+    if (!m->nb_points || !m->geo_feat || !m->certainty) {
+      set_error("map view: null neighbour arrays");
+      return PINB200_ERR_BAD_ARG;
+    }
+    const int F = m->feature_dim;
+    const bool okF = (F >= 32 && F % 32 == 0 && F <= 128) || F == 4 || F == 8 || F == 16;
+    if (!okF) {
+      set_error("feature_dim %d unsupported (4, 8, 16, 32, 64, 96, 128)", F);
+      return PINB200_ERR_UNSUPPORTED;
+    }
+    if (m->after_pgo && !m->nb_orient) {
+      set_error("map view: after_pgo needs nb_orient");
+      return PINB200_ERR_BAD_ARG;
+    }
+  }
+  return PINB200_OK;
+}
+
+static QueryLayout plan_layout(const QueryParams& p, int DP) {
+  QueryLayout l{};
+  const int H = p.dec.hidden_dim, K = p.opts.nn_k;
+  int o = 0;
+  l.delta = o;
+  o += align4(p.map.n_probe);
+  l.dec = plan_decoder_smem(p.dec, DP, p.opts.need_grad != 0, o);
+  o = l.dec.end;
+  const int act_rows = (DP > H ? DP : H);
+  l.act = o;
+  o += align4(act_rows * ACT_LD);
+  l.knn_idx = o;
+  o += TILE * K;
+  l.knn_d2 = o;
+  o += TILE * K;
+  l.q = o;
+  o += TILE * 3;
+  l.out = o;
+  o += align4(TILE * p.dec.out_dim);
+  l.nn = o;
+  o += TILE;
+  o = (o + 1) & ~1;  // 8-byte align the 64-bit masks
+  l.mask = o;
+  o += 2 * TILE * p.dec.n_hidden;
+  l.total = o;
+  return l;
+}
+
+template <int H, int DP>
+static int launch_query(QueryParams& p, cudaStream_t stream) {
+  p.lay = plan_layout(p, DP);
+  const size_t smem_bytes = (size_t)p.lay.total * sizeof(float);
+  if (smem_bytes > 227 * 1024) {
+    set_error("query kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
+    return PINB200_ERR_UNSUPPORTED;
+  }
+  auto kern = query_kernel<H, DP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return PINB200_ERR_CUDA;
+  }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem_bytes);
+  if (occ < 1) occ = 1;
+  const int grid = (int)std::min<long long>(p.n_tiles, (long long)sm_count() * occ);
+  kern<<<grid, TILE, smem_bytes, stream>>>(p);
+  return check_launch("query_kernel");
+}
+
+static int dispatch_query(QueryParams& p, cudaStream_t stream) {
+  const int D = p.dec.in_dim;
+  if (p.dec.hidden_dim != 64) {
+    set_error("decoder hidden_dim %d unsupported (64)", p.dec.hidden_dim);
+    return PINB200_ERR_UNSUPPORTED;
+  }
+  if (D <= 12) return launch_query<64, 12>(p, stream);
+  if (D <= 20) return launch_query<64, 20>(p, stream);
+  if (D <= 36) return launch_query<64, 36>(p, stream);
+  if (D <= 68) return launch_query<64, 68>(p, stream);
+  set_error("decoder in_dim %d unsupported (<= 68)", D);
+  return PINB200_ERR_UNSUPPORTED;
+}
+
+static int validate_decoder(const pinb200_decoder_view* d, int F) {
+  if (!d || !d->w_out || d->n_hidden < 1 || d->n_hidden > PINB200_MAX_HIDDEN_LAYERS) {
+    set_error("decoder view: bad n_hidden / null w_out");
+    return PINB200_ERR_BAD_ARG;
+  }
+  for (int l = 0; l < d->n_hidden; ++l)
+    if (!d->w[l]) {
+      set_error("decoder view: null weight of layer %d", l);
+      return PINB200_ERR_BAD_ARG;
+    }
+  if (d->in_dim != F + 3) {
+    set_error("decoder in_dim %d != feature_dim+3 = %d (positional encoding is not supported)", d->in_dim, F + 3);
+    return PINB200_ERR_UNSUPPORTED;
+  }
+  if (d->out_dim < 1 || d->out_dim > 4) {
+    set_error("decoder out_dim %d unsupported (1..4)", d->out_dim);
+    return PINB200_ERR_UNSUPPORTED;
+  }
+  return PINB200_OK;
+}
+
+}  // namespace pinb
+
+using namespace pinb;
+
+extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_decoder_view* sdf_dec,
+                                 const pinb200_decoder_view* color_dec, const float* query_xyz,
+                                 const int32_t* query_ts, int64_t n, const pinb200_query_opts* opts,
+                                 const pinb200_query_out* out, void* stream) {
+  int rc = validate_map(map, true);
+  if (rc) return rc;
+  if (!opts || !out || (!query_xyz && n > 0)) {
+    set_error("query_sdf: null opts/out/query");
+    return PINB200_ERR_BAD_ARG;
+  }
+  rc = validate_decoder(sdf_dec, map->feature_dim);
+  if (rc) return rc;
+  const int K = opts->nn_k;
+  if (K < 1 || K > PINB200_MAX_K || K > map->n_probe) {
+    set_error("nn_k %d out of range (1..%d, <= n_probe %d)", K, PINB200_MAX_K, map->n_probe);
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  if (color_dec) {
+    rc = validate_decoder(color_dec, map->feature_dim);
+    if (rc) return rc;
+    if (!map->color_feat || !out->knn_idx || !out->knn_dist2 || !out->nn_count) {
+      set_error("colour head needs map->color_feat and out->knn_idx/knn_dist2/nn_count as scratch");
+      return PINB200_ERR_BAD_ARG;
+    }
+  }
+  QueryParams p{};
+  p.map = *map;
+  p.dec = *sdf_dec;
+  p.opts = *opts;
+  p.out = *out;
+  p.query_xyz = query_xyz;
+  p.query_ts = query_ts;
+  p.feat = map->geo_feat;
+  p.n = n;
+  p.qpt = opts->weighted_first ? TILE : TILE / K;
+  p.n_tiles = (int)((n + p.qpt - 1) / p.qpt);
+  rc = dispatch_query(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (color_dec) {  // second launch: decode the colour features with the kNN the first launch saved
+    QueryParams c = p;
+    c.dec = *color_dec;
+    c.feat = map->color_feat;
+    c.use_saved_knn = 1;
+    c.is_color = 1;
+    c.opts.training_mode = 0;
+    c.opts.need_grad = (opts->need_grad && out->color_grad) ? 1 : 0;
+    rc = dispatch_query(c, (cudaStream_t)stream);
+  }
+  return rc;
+}
+
+extern "C" int pinb200_knn_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, int32_t nn_k,
+                                  int32_t* knn_idx, float* knn_dist2, float* knn_weight, int32_t* nn_count,
+                                  void* stream) {
+  int rc = validate_map(map, false);
+  if (rc) return rc;
+  if (nn_k < 1 || nn_k > PINB200_MAX_K || nn_k > map->n_probe) {
+    set_error("nn_k %d out of range", nn_k);
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  const int grid = (int)std::min<long long>((n + 3) / 4, (long long)sm_count() * 8);
+  knn_kernel<<<grid, TILE, align4(map->n_probe) * sizeof(float), (cudaStream_t)stream>>>(
+      *map, query_xyz, n, nn_k, knn_idx, knn_dist2, knn_weight, nn_count);
+  return check_launch("knn_kernel");
+}
+
+extern "C" int pinb200_radius_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, float* dist2,
+                                     int32_t* idx, void* stream) {
+  int rc = validate_map(map, false);
+  if (rc) return rc;
+  if (n <= 0) return PINB200_OK;
+  const int grid = (int)std::min<long long>((n + 3) / 4, (long long)sm_count() * 8);
+  radius_kernel<<<grid, TILE, align4(map->n_probe) * sizeof(float), (cudaStream_t)stream>>>(*map, query_xyz, n, dist2,
+                                                                                            idx, nullptr);
+  return check_launch("radius_kernel");
+}
+
+extern "C" int pinb200_query_certainty(const pinb200_map_view* map, const float* query_xyz, int64_t n,
+                                       float* out_certainty, void* stream) {
+  int rc = validate_map(map, false);
+  if (rc) return rc;
+  if (map->global2local || map->time_filter || !map->certainty) {
+    set_error("query_certainty works on the global arrays: global2local must be NULL, time_filter 0");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  const int grid = (int)std::min<long long>((n + 3) / 4, (long long)sm_count() * 8);
+  radius_kernel<<<grid, TILE, align4(map->n_probe) * sizeof(float), (cudaStream_t)stream>>>(*map, query_xyz, n, nullptr,
+                                                                                            nullptr, out_certainty);
+  return check_launch("radius_kernel(certainty)");
+}
+
+extern "C" int pinb200_gather_features(const pinb200_map_view* map, const float* feat, const float* query_xyz,
+                                       const int32_t* knn_idx, const float* knn_weight, int64_t n, int32_t nn_k,
+                                       int32_t weighted_first, float* out, void* stream) {
+  if (!map || !feat || !knn_idx || !knn_weight || !out || !map->nb_points) {
+    set_error("gather_features: null argument");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  const long long total = (weighted_first ? n : n * nn_k) * (map->feature_dim + 3);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, feat, query_xyz, knn_idx, knn_weight, n, nn_k,
+                                                        weighted_first, out);
+  return check_launch("gather_kernel");
+}

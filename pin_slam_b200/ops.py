@@ -1,0 +1,256 @@
+"""Tensor-facing wrappers of the C ABI: build the plain-C views from CUDA tensors
+and launch on torch's current stream.  No arithmetic happens here."""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DecoderView, MapView, QueryOpts, QueryOut
+
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("pin_slam_b200: the hot path runs on CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("pin_slam_b200: tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"pin_slam_b200: expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class MapHandle:
+    """A pinb200_map_view plus references that keep its tensors alive."""
+
+    def __init__(self, *, slot_table, buffer_size, points, ts_create, travel_dist, global2local, nb_points,
+                 nb_orient, geo_feat, color_feat, certainty, ts_update, probe_dx, resolution, max_valid_dist2,
+                 time_filter, cur_ts, diff_travel_dist_local, after_pgo):
+        self.keep = dict(slot_table=slot_table, points=points, ts_create=ts_create, travel_dist=travel_dist,
+                         global2local=global2local, nb_points=nb_points, nb_orient=nb_orient, geo_feat=geo_feat,
+                         color_feat=color_feat, certainty=certainty, ts_update=ts_update, probe_dx=probe_dx)
+        v = MapView()
+        v.slot_table = _ptr(slot_table, torch.int32)
+        v.buffer_size = int(buffer_size)
+        v.points = _ptr(points, torch.float32)
+        v.ts_create = _ptr(ts_create, torch.int32)
+        v.n_global = points.shape[0]
+        v.travel_dist = _ptr(travel_dist, torch.float32)
+        v.n_travel = 0 if travel_dist is None else travel_dist.shape[0]
+        v.global2local = _ptr(global2local, torch.int32)
+        v.nb_points = _ptr(nb_points, torch.float32)
+        v.nb_orient = _ptr(nb_orient, torch.float32)
+        v.geo_feat = _ptr(geo_feat, torch.float32)
+        v.color_feat = _ptr(color_feat, torch.float32)
+        v.certainty = _ptr(certainty, torch.float32)
+        v.ts_update = _ptr(ts_update, torch.int32)
+        v.n_nb = 0 if nb_points is None else nb_points.shape[0]
+        v.feature_dim = 0 if geo_feat is None else geo_feat.shape[1]
+        v.probe_dx = _ptr(probe_dx, torch.int32)
+        v.n_probe = probe_dx.shape[0]
+        v.resolution = float(resolution)
+        v.max_valid_dist2 = float(max_valid_dist2)
+        v.time_filter = int(bool(time_filter))
+        v.cur_ts = int(cur_ts)
+        v.diff_travel_dist_local = float(diff_travel_dist_local)
+        v.after_pgo = int(bool(after_pgo))
+        if time_filter and (travel_dist is None or cur_ts >= travel_dist.shape[0]):
+            raise RuntimeError("time filter needs travel_dist[cur_ts]")
+        self.view = v
+        self.device = points.device
+
+    @property
+    def n_nb(self):
+        return self.view.n_nb
+
+    @property
+    def n_probe(self):
+        return self.view.n_probe
+
+
+class DecoderHandle:
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], w_out, b_out,
+                 out_scale=1.0, leaky=False, sigmoid_out=False):
+        self.keep = (list(weights), list(biases), w_out, b_out)
+        v = DecoderView()
+        if not 1 <= len(weights) <= _lib.MAX_HIDDEN:
+            raise RuntimeError("decoder: 1..4 hidden layers supported")
+        for i, (w, b) in enumerate(zip(weights, biases)):
+            v.w[i] = _ptr(w, torch.float32)
+            v.b[i] = _ptr(b, torch.float32)
+        v.w_out = _ptr(w_out, torch.float32)
+        v.b_out = _ptr(b_out, torch.float32)
+        v.n_hidden = len(weights)
+        v.hidden_dim = weights[0].shape[0]
+        v.in_dim = weights[0].shape[1]
+        v.out_dim = w_out.shape[0]
+        v.out_scale = float(out_scale)
+        v.leaky_relu = int(bool(leaky))
+        v.sigmoid_out = int(bool(sigmoid_out))
+        self.view = v
+
+    def param_count(self):
+        return int(_lib.load().pinb200_decoder_param_count(C.byref(self.view)))
+
+
+def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int, weighted_first: bool,
+              training_mode: bool = False, need_grad: bool = True, query_ts: Optional[torch.Tensor] = None,
+              color_dec: Optional[DecoderHandle] = None, color_grad: bool = False,
+              transform: Optional[torch.Tensor] = None, save_knn: bool = False, want_xyz: bool = False,
+              out: Optional[dict] = None):
+    """K1.  Returns a dict of freshly allocated (or caller-provided `out`) CUDA tensors."""
+    lib = _lib.load()
+    n = xyz.shape[0]
+    dev = xyz.device
+    o = {} if out is None else out
+
+    def buf(name, shape, dtype=torch.float32):
+        t = o.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            o[name] = t
+        return t
+
+    qo = QueryOut()
+    qo.sdf = _ptr(buf("sdf", (n,)))
+    qo.sdf_std = _ptr(buf("sdf_std", (n,)))
+    qo.nn_count = _ptr(buf("nn_count", (n,), torch.int32))
+    qo.certainty = _ptr(buf("certainty", (n,)))
+    if need_grad:
+        qo.grad = _ptr(buf("grad", (n, 3)))
+    if save_knn or color_dec is not None:
+        qo.knn_idx = _ptr(buf("knn_idx", (n, nn_k), torch.int32))
+        qo.knn_dist2 = _ptr(buf("knn_dist2", (n, nn_k)))
+        qo.knn_weight = _ptr(buf("knn_weight", (n, nn_k)))
+    if want_xyz:
+        qo.xyz = _ptr(buf("xyz", (n, 3)))
+    if color_dec is not None:
+        cc = color_dec.view.out_dim
+        qo.color = _ptr(buf("color", (n, cc)))
+        if color_grad:
+            qo.color_grad = _ptr(buf("color_grad", (n, cc, 3)))
+    opts = QueryOpts(int(nn_k), int(bool(weighted_first)), int(bool(training_mode)), int(bool(need_grad)),
+                     _ptr(transform, torch.float64))
+    rc = lib.pinb200_query_sdf(C.byref(mh.view), C.byref(dec.view),
+                               C.byref(color_dec.view) if color_dec is not None else None,
+                               _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), n, C.byref(opts), C.byref(qo),
+                               _stream())
+    _lib.check(rc, "pinb200_query_sdf")
+    _count(2 if color_dec is not None else 1)
+    return o
+
+
+def knn_search(mh: MapHandle, xyz: torch.Tensor, nn_k: int):
+    lib = _lib.load()
+    n, dev = xyz.shape[0], xyz.device
+    idx = torch.empty((n, nn_k), dtype=torch.int32, device=dev)
+    d2 = torch.empty((n, nn_k), dtype=torch.float32, device=dev)
+    w = torch.empty((n, nn_k), dtype=torch.float32, device=dev)
+    cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+    rc = lib.pinb200_knn_search(C.byref(mh.view), _ptr(xyz, torch.float32), n, nn_k, _ptr(idx), _ptr(d2), _ptr(w),
+                                _ptr(cnt), _stream())
+    _lib.check(rc, "pinb200_knn_search")
+    _count()
+    return idx, d2, w, cnt
+
+
+def radius_search(mh: MapHandle, xyz: torch.Tensor):
+    lib = _lib.load()
+    n, dev, c = xyz.shape[0], xyz.device, mh.n_probe
+    d2 = torch.empty((n, c), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, c), dtype=torch.int32, device=dev)
+    rc = lib.pinb200_radius_search(C.byref(mh.view), _ptr(xyz, torch.float32), n, _ptr(d2), _ptr(idx), _stream())
+    _lib.check(rc, "pinb200_radius_search")
+    _count()
+    return d2, idx
+
+
+def query_certainty(mh: MapHandle, xyz: torch.Tensor):
+    lib = _lib.load()
+    out = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)
+    rc = lib.pinb200_query_certainty(C.byref(mh.view), _ptr(xyz, torch.float32), xyz.shape[0], _ptr(out), _stream())
+    _lib.check(rc, "pinb200_query_certainty")
+    _count()
+    return out
+
+
+def gather_features(mh: MapHandle, feat: torch.Tensor, xyz, knn_idx, knn_weight, weighted_first: bool):
+    lib = _lib.load()
+    n, k = knn_idx.shape
+    d = feat.shape[1] + 3
+    out = torch.empty((n, d) if weighted_first else (n, k, d), dtype=torch.float32, device=xyz.device)
+    rc = lib.pinb200_gather_features(C.byref(mh.view), _ptr(feat, torch.float32), _ptr(xyz, torch.float32),
+                                     _ptr(knn_idx, torch.int32), _ptr(knn_weight, torch.float32), n, k,
+                                     int(bool(weighted_first)), _ptr(out), _stream())
+    _lib.check(rc, "pinb200_gather_features")
+    _count()
+    return out
+
+
+def train_backward(mh: MapHandle, dec: DecoderHandle, feat, xyz, knn_idx, knn_weight, dloss_dout, weighted_first,
+                   grad_feat, grad_dec):
+    lib = _lib.load()
+    n, k = knn_idx.shape
+    rc = lib.pinb200_train_backward(C.byref(mh.view), C.byref(dec.view), _ptr(feat, torch.float32),
+                                    _ptr(xyz, torch.float32), _ptr(knn_idx, torch.int32),
+                                    _ptr(knn_weight, torch.float32), _ptr(dloss_dout, torch.float32), n, k,
+                                    int(bool(weighted_first)), _ptr(grad_feat, torch.float32),
+                                    _ptr(grad_dec, torch.float32), _stream())
+    _lib.check(rc, "pinb200_train_backward")
+    _count()
+
+
+def mapping_loss(sdf, sdf_label, weight, n_main, n_eik, sigma, loss_weight_on, weight_e, eik_eps, dloss, losses):
+    lib = _lib.load()
+    rc = lib.pinb200_mapping_loss(_ptr(sdf, torch.float32), _ptr(sdf_label, torch.float32),
+                                  _ptr(weight, torch.float32), n_main, n_eik, float(sigma), int(bool(loss_weight_on)),
+                                  float(weight_e), float(eik_eps), _ptr(dloss, torch.float32),
+                                  _ptr(losses, torch.float32), _stream())
+    _lib.check(rc, "pinb200_mapping_loss")
+    _count()
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    lib = _lib.load()
+    rc = lib.pinb200_adam_step(_ptr(param, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
+                               _ptr(exp_avg_sq, torch.float32), param.numel(), float(lr), float(beta1), float(beta2),
+                               float(eps), float(weight_decay), int(step), _stream())
+    _lib.check(rc, "pinb200_adam_step")
+    _count()
+
+
+def gn_step(xyz, sdf, grad, sdf_std, nn_count, *, min_nn, min_grad_norm, max_grad_norm, max_sdf_std, gm_dist,
+            gm_grad, lm_lambda, sdf_label=None, normals=None, t_inout=None, sums=None, result=None):
+    """K4.  Returns (result[32] f64 device tensor, sums[64] f64 device tensor)."""
+    lib = _lib.load()
+    dev = xyz.device
+    if sums is None:
+        sums = torch.empty(64, dtype=torch.float64, device=dev)
+    if result is None:
+        result = torch.empty(32, dtype=torch.float64, device=dev)
+    rc = lib.pinb200_gn_step(_ptr(xyz, torch.float32), _ptr(sdf, torch.float32), _ptr(grad, torch.float32),
+                             _ptr(sdf_std, torch.float32), _ptr(nn_count, torch.int32),
+                             _ptr(sdf_label, torch.float32), _ptr(normals, torch.float32), xyz.shape[0], int(min_nn),
+                             float(min_grad_norm), float(max_grad_norm), float(max_sdf_std),
+                             float(gm_dist or 0.0), float(gm_grad or 0.0), float(lm_lambda),
+                             _ptr(sums, torch.float64), _ptr(result, torch.float64), _ptr(t_inout, torch.float64),
+                             _stream())
+    _lib.check(rc, "pinb200_gn_step")
+    _count(2)
+    return result, sums

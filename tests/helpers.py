@@ -114,3 +114,56 @@ def queries_near(m, n, seed, sigma=0.15):
     g = torch.Generator().manual_seed(seed)
     sel = torch.randint(0, m.neural_points.shape[0], (n,), generator=g)
     return (m.neural_points[sel] + sigma * torch.randn(n, 3, generator=g)).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# CUDA-side helpers (only used by -m gpu tests, smoke and bench)
+# ---------------------------------------------------------------------------
+def map_handle_from_oracle(m, query_locally=True, device="cuda", color=True):
+    """Upload an OracleMap's tensors and wrap them in a pin_slam_b200.ops.MapHandle."""
+    from pin_slam_b200 import ops
+
+    dev = torch.device(device)
+    up = lambda x, dt=None: None if x is None else (x if dt is None else x.to(dt)).contiguous().to(dev)  # noqa: E731
+    local = query_locally
+    return ops.MapHandle(
+        slot_table=up(m.buffer_pt_index, torch.int32),
+        buffer_size=m.buffer_size,
+        points=up(m.neural_points),
+        ts_create=up(m.point_ts_create, torch.int32),
+        travel_dist=up(m.travel_dist),
+        global2local=up(m.global2local, torch.int32) if local else None,
+        nb_points=up(m.local_neural_points if local else m.neural_points),
+        nb_orient=up(m.local_point_orientations if local else m.point_orientations),
+        geo_feat=up((m.local_geo_features if local else m.geo_features).detach()),
+        color_feat=up((m.local_color_features if local else m.color_features).detach())
+        if (color and m.color_features is not None) else None,
+        certainty=up(m.local_point_certainties if local else m.point_certainties),
+        ts_update=up(m.local_point_ts_update if local else m.point_ts_update, torch.int32),
+        probe_dx=up(m.neighbor_dx, torch.int32),
+        resolution=m.resolution,
+        max_valid_dist2=m.max_valid_dist2,
+        time_filter=m.temporal_local_map_on and local,
+        cur_ts=m.cur_ts,
+        diff_travel_dist_local=m.diff_travel_dist_local,
+        after_pgo=m.after_pgo,
+    )
+
+
+def decoder_handle_from_oracle(dec, device="cuda", sigmoid_out=False):
+    from pin_slam_b200 import ops
+
+    dev = torch.device(device)
+    ws = [w.detach().contiguous().to(dev) for w, _ in dec.hidden]
+    bs = [b.detach().contiguous().to(dev) for _, b in dec.hidden]
+    return ops.DecoderHandle(ws, bs, dec.out[0].detach().contiguous().to(dev), dec.out[1].detach().contiguous().to(dev),
+                             out_scale=1.0 if sigmoid_out else dec.sdf_scale, leaky=dec.leaky, sigmoid_out=sigmoid_out)
+
+
+def flat_decoder_params(dec):
+    """[w0|b0|w1|b1|...|w_out|b_out] -- the layout pinb200_train_backward / adam use."""
+    parts = []
+    for w, b in dec.hidden:
+        parts += [w.detach().reshape(-1), b.detach().reshape(-1)]
+    parts += [dec.out[0].detach().reshape(-1), dec.out[1].detach().reshape(-1)]
+    return torch.cat(parts)

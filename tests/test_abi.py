@@ -1,0 +1,83 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol
+include/pinb200.h declares, and the ctypes mirror agrees with the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "pinb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pinb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def header_struct_fields(name):
+    src = open(os.path.join(ROOT, "include", "pinb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(\[[A-Z0-9_]+\])?$", decl)
+        fields.append(m.group(1))
+    return fields
+
+
+def test_library_exports_every_declared_symbol():
+    from pin_slam_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pinb200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.pinb200_version() == 100
+
+
+@pytest.mark.parametrize("cname,pyname", [("pinb200_map_view", "MapView"), ("pinb200_decoder_view", "DecoderView"),
+                                          ("pinb200_query_opts", "QueryOpts"), ("pinb200_query_out", "QueryOut")])
+def test_ctypes_structs_mirror_header(cname, pyname):
+    from pin_slam_b200 import _lib
+
+    py = [f[0] for f in getattr(_lib, pyname)._fields_]
+    assert py == header_struct_fields(cname)
+
+
+def test_struct_sizes_match_c_compiler(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof() with ctypes."""
+    import subprocess
+
+    from pin_slam_b200 import _lib
+
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "pinb200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                   "sizeof(pinb200_map_view),sizeof(pinb200_decoder_view),sizeof(pinb200_query_opts),"
+                   "sizeof(pinb200_query_out));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).split()
+    sizes = [int(x) for x in out]
+    assert sizes == [ctypes.sizeof(_lib.MapView), ctypes.sizeof(_lib.DecoderView), ctypes.sizeof(_lib.QueryOpts),
+                     ctypes.sizeof(_lib.QueryOut)]
+
+
+def test_no_cpu_fallback():
+    """The product path must refuse CPU tensors instead of silently computing on the host."""
+    import torch
+
+    from pin_slam_b200 import ops
+
+    with pytest.raises(RuntimeError):
+        ops._ptr(torch.zeros(3))

@@ -1,0 +1,400 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI) against the CPU
+oracle on the same seeded inputs, and against the golden fixtures recorded from
+the unmodified reference.
+
+Tolerances:
+  ids / counts / cell hashing : exact
+  SDF                         : |d| <= 1e-5 * max(|ref|, sdf_scale)
+  d sdf / d x                 : 1e-4 relative to max(|ref|, typical gradient scale)
+  feature / decoder grads     : 1e-4 relative (float atomics reorder the sums)
+  post-Adam parameters        : 1e-5 abs, a small fraction of near-zero-gradient outliers allowed
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pin_oracle as po
+from tests.helpers import (decoder_from_fixture, decoder_handle_from_oracle, flat_decoder_params, load_npz,
+                           map_from_fixture, map_handle_from_oracle, queries_near, synthetic_map, t)
+
+pytestmark = pytest.mark.gpu
+
+QUERY_FIXTURES = ["query_kitti_nwf", "query_kitti_wf", "query_cfg2_wf", "query_cfg2_nwf_pgo", "query_replica_wf_color"]
+TRAIN_FIXTURES = ["train_kitti_nwf", "train_cfg2_wf"]
+
+
+def ops():
+    from pin_slam_b200 import ops as _ops
+
+    return _ops
+
+
+def assert_sdf_close(got, ref, scale, tol=1e-5):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    bound = tol * np.maximum(np.abs(ref), scale)
+    bad = np.abs(got - ref) > bound
+    assert not bad.any(), f"{bad.sum()} / {bad.size} sdf values differ; max err {np.abs(got - ref).max():.3e}"
+
+
+def assert_rel_close(got, ref, tol, floor):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    bound = tol * np.maximum(np.abs(ref), floor)
+    err = np.abs(got - ref)
+    assert (err <= bound).all(), f"max err {err.max():.3e} (bound {bound.min():.3e}); {int((err > bound).sum())} bad"
+
+
+# --------------------------------------------------------------------------------------
+# search
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_radius_search_matches_reference_bit_exact(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    q = t(fx["q"]).cuda()
+    mh = map_handle_from_oracle(m, True)
+    d2, idx = ops().radius_search(mh, q)
+    assert np.array_equal(idx.cpu().numpy(), fx["rs.idx"])
+    assert np.array_equal(d2.cpu().numpy(), fx["rs.dist2"])
+    mg = map_handle_from_oracle(m, False)
+    _, idxg = ops().radius_search(mg, q)
+    assert np.array_equal(idxg.cpu().numpy(), fx["rs_nofilter.idx"])
+    qc = ops().query_certainty(mg, q)
+    assert np.array_equal(qc.cpu().numpy(), fx["query_certainty"])
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+@pytest.mark.parametrize("local", [True, False])
+def test_knn_and_features_match_reference(name, local):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    q = t(fx["q"]).cuda()
+    mh = map_handle_from_oracle(m, local)
+    idx, d2, w, cnt = ops().knn_search(mh, q, k)
+    tag = "qf_local" if local else "qf_global"
+    assert np.array_equal(cnt.cpu().numpy(), fx[tag + ".nn_counts"])
+    # oracle kNN ids for the same query (sorted by distance)
+    out = po.query_feature(m, t(fx["q"]).clone(), None, k, wf, training_mode=False, query_locally=local,
+                           return_idx=True)
+    ref_idx, ref_d2 = out[5].numpy(), out[6].numpy()
+    assert np.array_equal(d2.cpu().numpy(), ref_d2)
+    # ids must agree wherever the distance is not tied with its neighbour in the list
+    got_idx = idx.cpu().numpy()
+    tie = np.zeros_like(ref_d2, dtype=bool)
+    tie[:, 1:] |= ref_d2[:, 1:] == ref_d2[:, :-1]
+    tie[:, :-1] |= ref_d2[:, :-1] == ref_d2[:, 1:]
+    assert np.array_equal(got_idx[~tie], ref_idx[~tie])
+    np.testing.assert_allclose(w.cpu().numpy(), fx[tag + ".weight"][..., 0], rtol=2e-6, atol=1e-9)
+    feat = mh.keep["geo_feat"]
+    g = ops().gather_features(mh, feat, q, idx, w, wf)
+    np.testing.assert_allclose(g.cpu().numpy(), fx[tag + ".geo"], rtol=1e-5, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------
+# K1 fused query vs the reference's Tracker.query_source_points
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_fused_query_matches_reference(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    color = "map.color_features" in fx
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    ch = decoder_handle_from_oracle(decoder_from_fixture(fx, "color_mlp"), sigmoid_out=True) if color else None
+    q = t(fx["q"]).cuda()
+    out = ops().query_sdf(mh, dh, q, nn_k=k, weighted_first=wf, need_grad=True, color_dec=ch, color_grad=color)
+    torch.cuda.synchronize()
+    assert_sdf_close(out["sdf"].cpu(), fx["trk.sdf"], dec.sdf_scale)
+    gscale = float(np.abs(fx["trk.grad"]).mean()) + 1e-12
+    assert_rel_close(out["grad"].cpu(), fx["trk.grad"], 1e-4, gscale)
+    assert_rel_close(out["sdf_std"].cpu(), fx["trk.sdf_std"], 1e-4, dec.sdf_scale)
+    np.testing.assert_allclose(out["certainty"].cpu().numpy(), fx["trk.certainty"], rtol=1e-5, atol=1e-6)
+    mask = (out["nn_count"] >= int(fx["cfg.track_mask_query_nn_k"])).cpu().numpy()
+    assert np.array_equal(mask, fx["trk.mask"])
+    if color:
+        np.testing.assert_allclose(out["color"].cpu().numpy(), fx["trk.color"], rtol=1e-5, atol=1e-6)
+        cscale = float(np.abs(fx["trk.color_grad"]).mean()) + 1e-12
+        assert_rel_close(out["color_grad"].cpu(), fx["trk.color_grad"], 1e-4, cscale)
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_training_mode_side_effects(name):
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    ops().query_sdf(mh, dh, t(fx["q"]).cuda(), nn_k=k, weighted_first=wf, need_grad=False, training_mode=True,
+                    query_ts=t(fx["train_fx.ts"]).cuda())
+    np.testing.assert_allclose(mh.keep["certainty"].cpu().numpy(), fx["train_fx.certainties_after"], rtol=1e-5,
+                               atol=1e-5)
+    assert np.array_equal(mh.keep["ts_update"].cpu().numpy(), fx["train_fx.ts_update_after"])
+
+
+@pytest.mark.parametrize("F,K,L,wf,pgo,C", [(8, 6, 1, False, False, (2, 0.2)), (8, 6, 1, True, False, (2, 0.2)),
+                                            (32, 8, 2, True, False, (2, 0.2)), (32, 8, 2, False, True, (2, 0.2)),
+                                            (16, 4, 3, True, True, (1, 0.0)), (64, 8, 2, True, False, (2, 0.5)),
+                                            (8, 6, 1, False, False, (3, 0.2))])
+def test_fused_query_vs_oracle_synthetic(F, K, L, wf, pgo, C):
+    """Seeded synthetic maps at sizes the oracle finishes in seconds; local map with an age filter."""
+    m = synthetic_map(n_surface=60000, seed=F + K, resolution=0.4, buffer_size=200003, feature_dim=F,
+                      after_pgo=pgo, local_radius=14.0, diff_td=3.0, num_nei_cells=C[0], search_alpha=C[1])
+    dec = po.make_decoder(F + 3, 64, L, 1, 0.044, seed=3)
+    q = queries_near(m, 20000, seed=5)
+    q[:16] = torch.tensor([300.0, -200.0, 50.0])  # no neighbours at all
+    ref = po.query_sdf(m, dec, q, K, wf)
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    out = ops().query_sdf(mh, dh, q.cuda(), nn_k=K, weighted_first=wf, need_grad=True)
+    assert np.array_equal(out["nn_count"].cpu().numpy(), ref["nn_count"].numpy())
+    assert_sdf_close(out["sdf"].cpu(), ref["sdf"], dec.sdf_scale)
+    gscale = float(ref["grad"].abs().mean()) + 1e-12
+    assert_rel_close(out["grad"].cpu(), ref["grad"], 1e-4, gscale)
+    assert_rel_close(out["sdf_std"].cpu(), ref["sdf_std"], 1e-4, dec.sdf_scale)
+    # sdf-only launch must give the same values
+    out2 = ops().query_sdf(mh, dh, q.cuda(), nn_k=K, weighted_first=wf, need_grad=False)
+    assert torch.equal(out2["sdf"], out["sdf"])
+
+
+def test_fused_transform_matches_pretransformed():
+    m = synthetic_map(n_surface=30000, seed=1, buffer_size=100003, feature_dim=8)
+    dec = po.make_decoder(11, 64, 1, 1, 0.044, seed=1)
+    q = queries_near(m, 5000, seed=2)
+    T = torch.eye(4, dtype=torch.float64)
+    T[:3, :3] = po.expmap(torch.tensor([0.01, -0.02, 0.03], dtype=torch.float64))
+    T[:3, 3] = torch.tensor([0.1, -0.05, 0.02], dtype=torch.float64)
+    qt = po.transform_points(q, T)
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    a = ops().query_sdf(mh, dh, q.cuda(), nn_k=6, weighted_first=False, transform=T.cuda(), want_xyz=True)
+    np.testing.assert_allclose(a["xyz"].cpu().numpy(), qt.numpy(), rtol=0, atol=4e-6)
+    b = ops().query_sdf(mh, dh, a["xyz"].clone(), nn_k=6, weighted_first=False)
+    assert torch.equal(a["sdf"], b["sdf"]) and torch.equal(a["grad"], b["grad"])
+
+
+def test_empty_and_tiny_inputs():
+    m = synthetic_map(n_surface=5000, seed=2, buffer_size=50021, feature_dim=8)
+    dec = po.make_decoder(11, 64, 1, 1, 0.044, seed=1)
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    out = ops().query_sdf(mh, dh, torch.empty(0, 3, device="cuda"), nn_k=6, weighted_first=True)
+    assert out["sdf"].shape == (0,)
+    q = queries_near(m, 1, seed=3)
+    ref = po.query_sdf(m, dec, q, 6, True)
+    out = ops().query_sdf(mh, dh, q.cuda(), nn_k=6, weighted_first=True)
+    assert_sdf_close(out["sdf"].cpu(), ref["sdf"], dec.sdf_scale)
+    with pytest.raises(RuntimeError):
+        ops().query_sdf(mh, dh, q.cuda(), nn_k=40, weighted_first=True)  # K > n_probe / MAX_K
+
+
+# --------------------------------------------------------------------------------------
+# K4 registration step
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in QUERY_FIXTURES if "color" not in n])
+def test_gn_step_matches_reference(name):
+    fx = load_npz(name)
+    q = t(fx["q"])
+    mn, mx, max_std, gmd, gmg, lam = [float(v) for v in fx["reg.params"]]
+    nn = torch.where(t(fx["trk.mask"]), 100, 0).to(torch.int32)
+    ref = po.registration_step(q, t(fx["trk.sdf"]), t(fx["trk.grad"]), t(fx["trk.sdf_std"]), nn,
+                               torch.zeros(q.shape[0]), 1, mn, mx, max_std, gmd, gmg, lam)
+    T0 = torch.eye(4, dtype=torch.float64, device="cuda")
+    res, sums = ops().gn_step(q.cuda(), t(fx["trk.sdf"]).cuda(), t(fx["trk.grad"]).cuda(),
+                              t(fx["trk.sdf_std"]).cuda(), nn.cuda(), min_nn=1, min_grad_norm=mn, max_grad_norm=mx,
+                              max_sdf_std=max_std, gm_dist=gmd, gm_grad=gmg, lm_lambda=lam, t_inout=T0)
+    res = res.cpu().numpy()
+    assert int(res[16]) == int(fx["reg.valid_count"]) == ref["valid_count"]
+    np.testing.assert_allclose(res[17], float(fx["reg.residual_cm"]), rtol=1e-5)
+    # normal equations first (accumulation order differs), then the pose update
+    s = sums.cpu().numpy()
+    sc = res[16] / (2.0 * s[42])
+    np.testing.assert_allclose(s[:36].reshape(6, 6) * sc, ref["N"].double().numpy(), rtol=1e-4,
+                               atol=1e-5 * float(ref["N"].abs().max()))
+    np.testing.assert_allclose(s[36:42] * sc, ref["g"].double().numpy(), rtol=1e-4,
+                               atol=1e-5 * float(ref["g"].abs().max()))
+    np.testing.assert_allclose(res[:16].reshape(4, 4), fx["reg.T"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(T0.cpu().numpy(), res[:16].reshape(4, 4), rtol=0, atol=1e-12)
+
+
+def test_gn_step_too_few_points_gives_identity():
+    n = 50
+    z = torch.zeros(n, device="cuda")
+    res, _ = ops().gn_step(torch.rand(n, 3, device="cuda"), z, torch.zeros(n, 3, device="cuda"), z,
+                           torch.zeros(n, dtype=torch.int32, device="cuda"), min_nn=6, min_grad_norm=0.5,
+                           max_grad_norm=2.0, max_sdf_std=0.25, gm_dist=0.3, gm_grad=0.1, lm_lambda=1e-4)
+    r = res.cpu().numpy()
+    assert np.array_equal(r[:16].reshape(4, 4), np.eye(4)) and r[16] == 0
+
+
+# --------------------------------------------------------------------------------------
+# training: loss heads, backward (K2), Adam (K3)
+# --------------------------------------------------------------------------------------
+def _oracle_train_grads(fx, it=0):
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    _, sdf_scale, weight_e, eps_num, *_ = [float(v) for v in fx["cfg.floats"]]
+    m.local_geo_features.requires_grad_(True)
+    dec.requires_grad_(True)
+    m0 = m.clone()
+    loss, parts = po.mapping_loss(m, dec, t(fx[f"batch{it}.coord"]), t(fx[f"batch{it}.sdf_label"]),
+                                  t(fx[f"batch{it}.ts"]), t(fx[f"batch{it}.weight"]), k, wf, sdf_scale,
+                                  bool(fx["cfg.loss_weight_on"]), weight_e, int(fx["cfg.gradient_decimation"]), eps_num)
+    loss.backward()
+    gdec = torch.cat([p.grad.reshape(-1) for p in dec.tensors()])
+    return m0, m, dec, loss, parts, m.local_geo_features.grad, gdec
+
+
+def _cuda_train_iteration(mh, dh, fx, it, k, wf, sdf_scale, weight_e, eps_num, loss_weight_on, dec_n, gfeat, gdec):
+    coord = t(fx[f"batch{it}.coord"]).cuda()
+    dec_step = int(fx["cfg.gradient_decimation"])
+    sub = coord[::dec_step]
+    n, ne = coord.shape[0], sub.shape[0]
+    e = torch.zeros(3, 3, device="cuda")
+    e[0, 0] = e[1, 1] = e[2, 2] = eps_num
+    shifted = torch.cat([sub + e[0], sub - e[0], sub + e[1], sub - e[1], sub + e[2], sub - e[2]], 0)
+    ts = t(fx[f"batch{it}.ts"]).cuda()
+    # main rows carry the training side effects, the numerical-gradient rows do not (mapper.py:941)
+    o1 = ops().query_sdf(mh, dh, coord, nn_k=k, weighted_first=wf, need_grad=False, training_mode=True, query_ts=ts,
+                         save_knn=True)
+    o2 = ops().query_sdf(mh, dh, shifted, nn_k=k, weighted_first=wf, need_grad=False, save_knn=True)
+    sdf = torch.cat([o1["sdf"], o2["sdf"]])
+    xyz = torch.cat([coord, shifted])
+    idx = torch.cat([o1["knn_idx"], o2["knn_idx"]])
+    w = torch.cat([o1["knn_weight"], o2["knn_weight"]])
+    dl = torch.empty_like(sdf)
+    losses = torch.zeros(2, device="cuda")
+    ops().mapping_loss(sdf, t(fx[f"batch{it}.sdf_label"]).cuda(), t(fx[f"batch{it}.weight"]).cuda(), n, ne, sdf_scale,
+                       loss_weight_on, weight_e, eps_num, dl, losses)
+    ops().train_backward(mh, dh, mh.keep["geo_feat"], xyz, idx, w, dl, wf, gfeat, gdec)
+    return sdf, losses
+
+
+@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def test_train_backward_matches_autograd(name):
+    fx = load_npz(name)
+    m0, m, dec, loss, parts, gfeat_ref, gdec_ref = _oracle_train_grads(fx)
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    _, sdf_scale, weight_e, eps_num, *_ = [float(v) for v in fx["cfg.floats"]]
+    mh = map_handle_from_oracle(m0, True)
+    dec0 = decoder_from_fixture(fx, "sdf_mlp")
+    dh = decoder_handle_from_oracle(dec0)
+    gfeat = torch.zeros_like(mh.keep["geo_feat"])
+    gdec = torch.zeros(dh.param_count(), device="cuda")
+    sdf, losses = _cuda_train_iteration(mh, dh, fx, 0, k, wf, sdf_scale, weight_e, eps_num,
+                                        bool(fx["cfg.loss_weight_on"]), dh.param_count(), gfeat, gdec)
+    torch.cuda.synchronize()
+    n = fx["batch0.coord"].shape[0]
+    assert_sdf_close(sdf[:n].cpu(), parts["sdf_pred"], dec0.sdf_scale)
+    np.testing.assert_allclose(losses.cpu().numpy(), [float(parts["bce"]), float(parts["eikonal"])], rtol=2e-5)
+    assert_rel_close(gfeat.cpu(), gfeat_ref, 1e-4, float(gfeat_ref.abs().max()) * 1e-2)
+    assert_rel_close(gdec.cpu(), gdec_ref, 1e-4, float(gdec_ref.abs().max()) * 1e-2)
+    # training side effects of the forward
+    np.testing.assert_allclose(mh.keep["certainty"].cpu().numpy(), m.local_point_certainties.numpy(), rtol=1e-5,
+                               atol=1e-5)
+    assert np.array_equal(mh.keep["ts_update"].cpu().numpy(), m.local_point_ts_update.numpy())
+
+
+def test_adam_matches_torch():
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(5000, generator=g)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    pc, m, v = p.cuda(), torch.zeros(5000, device="cuda"), torch.zeros(5000, device="cuda")
+    for step in range(1, 6):
+        grad = torch.randn(5000, generator=g) * 1e-3
+        grad[::7] = 0.0
+        ref.grad = grad.clone()
+        opt.step()
+        gc = grad.cuda()
+        ops().adam_step(pc, gc, m, v, 0.01, 0.9, 0.99, 1e-15, 0.0, step)
+        assert float(gc.abs().max()) == 0.0  # zero_grad folded in
+    np.testing.assert_allclose(pc.cpu().numpy(), ref.detach().numpy(), rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def test_three_mapping_iterations_match_reference(name):
+    """Mapper.mapping for 3 iterations: fused forward + loss + K2 + K3 vs the reference's post-step state."""
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    k = int(fx["cfg.query_nn_k"])
+    wf = bool(fx["cfg.weighted_first"])
+    _, sdf_scale, weight_e, eps_num, lr, adam_eps, wd, *_ = [float(v) for v in fx["cfg.floats"]]
+    mh = map_handle_from_oracle(m, True)
+    feat = mh.keep["geo_feat"]
+    flat = flat_decoder_params(dec).cuda()
+    # decoder handle whose weights are views into the flat parameter vector (Adam updates them in place)
+    views, off = [], 0
+    ws, bs = [], []
+    for w, b in dec.hidden:
+        ws.append(flat[off:off + w.numel()].view_as(w)); off += w.numel()
+        bs.append(flat[off:off + b.numel()].view_as(b)); off += b.numel()
+    wo = flat[off:off + dec.out[0].numel()].view_as(dec.out[0]); off += dec.out[0].numel()
+    bo = flat[off:off + dec.out[1].numel()].view_as(dec.out[1])
+    dh = ops().DecoderHandle(ws, bs, wo, bo, out_scale=dec.sdf_scale)
+    gfeat, gdec = torch.zeros_like(feat), torch.zeros_like(flat)
+    mf, vf = torch.zeros_like(feat), torch.zeros_like(feat)
+    md, vd = torch.zeros_like(flat), torch.zeros_like(flat)
+    for it in range(int(fx["n_iters"])):
+        _cuda_train_iteration(mh, dh, fx, it, k, wf, sdf_scale, weight_e, eps_num, bool(fx["cfg.loss_weight_on"]),
+                              flat.numel(), gfeat, gdec)
+        ops().adam_step(flat, gdec, md, vd, lr, 0.9, 0.99, adam_eps, 0.0, it + 1)
+        ops().adam_step(feat, gfeat, mf, vf, lr, 0.9, 0.99, adam_eps, wd, it + 1)
+    torch.cuda.synchronize()
+
+    def close_frac(a, b, atol=1e-5, max_bad_frac=5e-3, max_abs=4e-2):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        bad = np.abs(a - b) > atol + 1e-5 * np.abs(b)
+        assert bad.mean() <= max_bad_frac, f"{bad.sum()} / {bad.size} differ, max {np.abs(a - b).max():.2e}"
+        assert np.abs(a - b).max() <= max_abs
+
+    close_frac(feat.cpu().numpy(), fx["after.local_geo_features"])
+    ref_flat = np.concatenate([fx[f"after.sdf_mlp.layers.{i}.{p}"].reshape(-1) for i in range(len(dec.hidden))
+                               for p in ("weight", "bias")] + [fx["after.sdf_mlp.lout.weight"].reshape(-1),
+                                                               fx["after.sdf_mlp.lout.bias"].reshape(-1)])
+    close_frac(flat.cpu().numpy(), ref_flat)
+    np.testing.assert_allclose(mh.keep["certainty"].cpu().numpy(), fx["after.local_point_certainties"], rtol=1e-4,
+                               atol=1e-4)
+    assert np.array_equal(mh.keep["ts_update"].cpu().numpy(), fx["after.local_point_ts_update"])
+
+
+# --------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE config 2: 200k queries, K=8, F=32, 2x64 decoder)
+# --------------------------------------------------------------------------------------
+def test_full_size_properties():
+    m = synthetic_map(n_surface=1500000, seed=0, resolution=0.4, buffer_size=int(5e7), feature_dim=32, extent=160.0)
+    dec = po.make_decoder(35, 64, 2, 1, 0.055, seed=0)
+    q = queries_near(m, 200000, seed=1, sigma=0.1)
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    qc = q.cuda()
+    a = ops().query_sdf(mh, dh, qc, nn_k=8, weighted_first=True, need_grad=True, save_knn=True)
+    # (1) determinism / idempotence of the inference path
+    b = ops().query_sdf(mh, dh, qc, nn_k=8, weighted_first=True, need_grad=True)
+    assert torch.equal(a["sdf"], b["sdf"]) and torch.equal(a["grad"], b["grad"])
+    # (2) permutation equivariance: position inside a tile / CTA must not matter
+    perm = torch.randperm(qc.shape[0], device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    c = ops().query_sdf(mh, dh, qc[perm].contiguous(), nn_k=8, weighted_first=True, need_grad=True)
+    assert torch.equal(c["sdf"], a["sdf"][perm]) and torch.equal(c["grad"], a["grad"][perm])
+    # (3) kNN lists are sorted, weights are a partition of unity wherever a neighbour exists
+    d2 = a["knn_dist2"]
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    has = a["nn_count"] > 0
+    ws = a["knn_weight"].sum(1)
+    assert torch.allclose(ws[has], torch.ones_like(ws[has]), atol=1e-5) and float(ws[~has].abs().max(initial=0)) == 0
+    assert int((a["knn_idx"] >= 0).sum(1).sub(torch.clamp(a["nn_count"], max=8)).abs().max()) == 0
+    # (4) a random 4k subset against the oracle
+    sel = torch.randperm(q.shape[0], generator=torch.Generator().manual_seed(3))[:4096]
+    ref = po.query_sdf(m, dec, q[sel], 8, True)
+    assert_sdf_close(a["sdf"][sel.cuda()].cpu(), ref["sdf"], dec.sdf_scale)
+    assert_rel_close(a["grad"][sel.cuda()].cpu(), ref["grad"], 1e-4, float(ref["grad"].abs().mean()))
+    assert np.array_equal(a["nn_count"][sel.cuda()].cpu().numpy(), ref["nn_count"].numpy())
