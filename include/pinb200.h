@@ -107,6 +107,7 @@ typedef struct pinb200_query_out {
   int32_t* knn_idx;    /* [N,K] ids in the queried index space, -1 invalid, ascending distance */
   float* knn_dist2;    /* [N,K] squared distances (9e3 for invalid, :583) */
   float* knn_weight;   /* [N,K] normalised IDW weights (:667-683) */
+  int32_t* knn_gidx;   /* [N,K] ids of the same neighbours in the GLOBAL arrays (== knn_idx when global2local is NULL) */
   float* xyz;          /* [N,3] the (transformed) query points actually used */
 } pinb200_query_out;
 
@@ -129,8 +130,8 @@ int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_decoder_view* s
 /* Search only (no decoder): top-K ids / distances / weights / nn_count.
  * model/neural_points.py:562-589,665-683. */
 int pinb200_knn_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, int32_t nn_k,
-                       int32_t* knn_idx, float* knn_dist2, float* knn_weight, int32_t* nn_count,
-                       void* stream);
+                       int32_t* knn_idx, int32_t* knn_gidx, float* knn_dist2, float* knn_weight,
+                       int32_t* nn_count, void* stream);
 
 /* All-probe form of the radius search: dist2 [N,C] and GLOBAL ids [N,C] exactly
  * as NeuralPoints.radius_neighborhood_search returns them (:950-1009). */

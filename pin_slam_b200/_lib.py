@@ -44,7 +44,7 @@ class QueryOpts(C.Structure):
 class QueryOut(C.Structure):
     _fields_ = [("sdf", c_f32p), ("grad", c_f32p), ("sdf_std", c_f32p), ("nn_count", c_i32p),
                 ("certainty", c_f32p), ("color", c_f32p), ("color_grad", c_f32p), ("knn_idx", c_i32p),
-                ("knn_dist2", c_f32p), ("knn_weight", c_f32p), ("xyz", c_f32p)]
+                ("knn_dist2", c_f32p), ("knn_weight", c_f32p), ("knn_gidx", c_i32p), ("xyz", c_f32p)]
 
 
 # name -> (restype, argtypes); every symbol include/pinb200.h declares
@@ -53,7 +53,7 @@ SIGNATURES = {
     "pinb200_last_error": (C.c_char_p, []),
     "pinb200_query_sdf": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,
                                     c_i32p, C.c_int64, C.POINTER(QueryOpts), C.POINTER(QueryOut), C.c_void_p]),
-    "pinb200_knn_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, C.c_int32, c_i32p, c_f32p, c_f32p,
+    "pinb200_knn_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, C.c_int32, c_i32p, c_i32p, c_f32p, c_f32p,
                                      c_i32p, C.c_void_p]),
     "pinb200_radius_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, c_f32p, c_i32p, C.c_void_p]),
     "pinb200_query_certainty": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, c_f32p, C.c_void_p]),

@@ -1,0 +1,107 @@
+"""Minimal configuration object carrying the attributes the hot path reads from the
+reference's `utils.config.Config` (utils/config.py:13-312), with the same names and
+defaults.  The drop-in classes are duck-typed: they accept the reference Config
+unchanged; this class exists so the hot path can be driven without the reference
+checkout (tests, bench, smoke on the GPU box)."""
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class HotPathConfig:
+    device: str = "cuda"
+    dtype: torch.dtype = torch.float32
+    tran_dtype: torch.dtype = torch.float64
+    silence: bool = True
+    # neural points (config.py:92-104)
+    voxel_size_m: float = 0.3
+    weighted_first: bool = True
+    layer_norm_on: bool = False
+    num_nei_cells: int = 2
+    query_nn_k: int = 6
+    use_mid_ts: bool = False
+    search_alpha: float = 0.2
+    buffer_size: int = int(5e7)
+    feature_dim: int = 8
+    feature_std: float = 0.0
+    color_on: bool = False
+    color_channel: int = 0
+    # local map (config.py:112-115, 559-560)
+    diff_ts_local: float = 400.0
+    local_map_travel_dist_ratio: float = 5.0
+    local_map_radius: float = 50.0
+    max_range: float = 60.0
+    # decoder (config.py:138-158)
+    mlp_bias_on: bool = True
+    mlp_leaky_relu: bool = False
+    geo_mlp_level: int = 1
+    geo_mlp_hidden_dim: int = 64
+    color_mlp_level: int = 1
+    color_mlp_hidden_dim: int = 64
+    use_gaussian_pe: bool = False
+    pos_encoding_band: int = 0
+    pos_input_dim: int = 3
+    # loss (config.py:161-184)
+    main_loss_type: str = "bce"
+    sigma_sigmoid_m: float = 0.1
+    logistic_gaussian_ratio: float = 0.55
+    loss_weight_on: bool = False
+    numerical_grad: bool = True
+    gradient_decimation: int = 10
+    num_grad_step_ratio: float = 0.2
+    ekional_loss_on: bool = True
+    ekional_add_to: str = "all"
+    weight_e: float = 0.5
+    weight_i: float = 1.0
+    surface_sample_range_m: float = 0.25
+    # optimiser (config.py:188-199)
+    iters: int = 12
+    bs: int = 16384
+    lr: float = 0.01
+    weight_decay: float = 0.0
+    adam_eps: float = 1e-15
+    opt_adam: bool = True
+    bs_new_sample: int = 2048
+    # tracker (config.py:213-233)
+    track_on: bool = True
+    photometric_loss_on: bool = False
+    photometric_loss_weight: float = 0.01
+    consist_wieght_on: bool = True
+    reg_min_grad_norm: float = 0.5
+    reg_max_grad_norm: float = 2.0
+    track_mask_query_nn_k: int = 6
+    max_sdf_ratio: float = 5.0
+    max_sdf_std_ratio: float = 1.0
+    reg_dist_div_grad_norm: bool = False
+    reg_GM_dist_m: float = 0.3
+    reg_GM_grad: float = 0.1
+    reg_lm_lambda: float = 1e-4
+    reg_iter_n: int = 50
+    reg_term_thre_deg: float = 0.01
+    reg_term_thre_m: float = 0.001
+    eigenvalue_check: bool = True
+    eigenvalue_ratio_thre: float = 0.005
+    final_residual_ratio_thre: float = 0.6
+    semantic_on: bool = False
+
+    @property
+    def infer_bs(self):
+        return self.bs * 32
+
+    @classmethod
+    def kitti(cls, **kw):
+        """config/lidar_slam/run_kitti.yaml of the reference."""
+        d = dict(voxel_size_m=0.4, weighted_first=False, feature_dim=8, query_nn_k=6, track_mask_query_nn_k=6,
+                 sigma_sigmoid_m=0.08, loss_weight_on=True, weight_e=0.5, max_range=80.0, local_map_radius=82.0,
+                 surface_sample_range_m=0.25, reg_GM_dist_m=0.2, reg_GM_grad=0.1, reg_iter_n=100, bs_new_sample=1000)
+        d.update(kw)
+        return cls(**d)
+
+    @classmethod
+    def cfg2(cls, **kw):
+        """BASELINE.json configs[1]: 32-d features, K=8, 2-layer decoder."""
+        d = dict(voxel_size_m=0.4, weighted_first=True, feature_dim=32, query_nn_k=8, track_mask_query_nn_k=8,
+                 geo_mlp_level=2)
+        d.update(kw)
+        return cls(**d)

@@ -60,6 +60,7 @@ __device__ __forceinline__ void quat_rotate_active(float qw, float qx, float qy,
 struct Knn {
   float d2;   // squared distance, INVALID_D2 if idx < 0
   int idx;    // id in the queried index space, -1 invalid
+  int gidx;   // id of the same neighbour in the GLOBAL arrays (what the distance was measured to)
   int count;  // nn_counts: valid probes before top-K (warp-uniform)
 };
 
@@ -120,6 +121,7 @@ __device__ __forceinline__ Knn knn_search_warp(const pinb200_map_view& m, const 
   Knn r;
   r.d2 = INVALID_D2;
   r.idx = -1;
+  r.gidx = -1;
   r.count = 0;
   const uint32_t r0 = base_slot(m, qx, qy, qz);
   const float td_cur = m.time_filter ? __ldg(m.travel_dist + m.cur_ts) : 0.f;
@@ -128,7 +130,7 @@ __device__ __forceinline__ Knn knn_search_warp(const pinb200_map_view& m, const 
     const int c = base + lane;
     bool valid = false;
     float d2 = 0.f;
-    int li = -1, gi;
+    int li = -1, gi = -1;
     if (c < m.n_probe) valid = probe_cell(m, r0, s_delta[c], qx, qy, qz, td_cur, d2, li, gi);
     r.count += __popc(__ballot_sync(FULL, valid));
     uint32_t cand = valid ? __float_as_uint(d2) : INF_BITS;  // d2 >= 0: uint order == float order
@@ -140,23 +142,28 @@ __device__ __forceinline__ Knn knn_search_warp(const pinb200_map_view& m, const 
       if (!(mnf < worst)) break;
       const int src = __ffs(__ballot_sync(FULL, cand == mn)) - 1;
       const int cidx = __shfl_sync(FULL, li, src);
+      const int cgi = __shfl_sync(FULL, gi, src);
       if (lane == src) cand = INF_BITS;
       const int pos = __popc(__ballot_sync(FULL, (lane < K) && (r.d2 <= mnf)));
       const float up_d2 = __shfl_up_sync(FULL, r.d2, 1);
       const int up_idx = __shfl_up_sync(FULL, r.idx, 1);
+      const int up_gi = __shfl_up_sync(FULL, r.gidx, 1);
       if (lane > pos && lane < K) {
         r.d2 = up_d2;
         r.idx = up_idx;
+        r.gidx = up_gi;
       }
       if (lane == pos) {
         r.d2 = mnf;
         r.idx = cidx;
+        r.gidx = cgi;
       }
     }
   }
   if (lane >= K) {
     r.d2 = INVALID_D2;
     r.idx = -1;
+    r.gidx = -1;
   }
   return r;
 }

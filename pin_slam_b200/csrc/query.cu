@@ -23,7 +23,7 @@ namespace pinb {
 
 struct QueryLayout {  // float offsets into dynamic smem
   DecSmem dec;
-  int delta, act, knn_idx, knn_d2, q, out, nn, mask, total;
+  int delta, act, knn_idx, knn_gidx, knn_d2, q, out, nn, mask, total;
 };
 
 struct QueryParams {
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem + p.lay.delta);
   float* s_act = smem + p.lay.act;
   int* s_idx = reinterpret_cast<int*>(smem + p.lay.knn_idx);
+  int* s_gidx = reinterpret_cast<int*>(smem + p.lay.knn_gidx);
   float* s_d2 = smem + p.lay.knn_d2;
   float* s_q = smem + p.lay.q;
   float* s_out = smem + p.lay.out;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
         for (int e = lane; e < D * nrows; e += 32) s_act[(e / nrows) * ACT_LD + row0 + (e % nrows)] = 0.f;
         if (lane < K) {
           s_idx[ql * K + lane] = -1;
+          s_gidx[ql * K + lane] = -1;
           s_d2[ql * K + lane] = INVALID_D2;
         }
         if (lane == 0) s_nn[ql] = 0;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
       Knn kn;
       if (p.use_saved_knn) {
         kn.idx = lane < K ? __ldg(p.out.knn_idx + qi * K + lane) : -1;
+        kn.gidx = lane < K ? __ldg(p.out.knn_gidx + qi * K + lane) : -1;
         kn.d2 = lane < K ? __ldg(p.out.knn_dist2 + qi * K + lane) : INVALID_D2;
         kn.count = __ldg(p.out.nn_count + qi);
       } else {
@@ -195,12 +198,14 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
         }
         if (lane < K && !p.use_saved_knn) {
           if (p.out.knn_idx) p.out.knn_idx[qi * K + lane] = kn.idx;
+          if (p.out.knn_gidx) p.out.knn_gidx[qi * K + lane] = kn.gidx;
           if (p.out.knn_dist2) p.out.knn_dist2[qi * K + lane] = kn.d2;
           if (p.out.knn_weight) p.out.knn_weight[qi * K + lane] = w;
         }
       }
       if (lane < K) {
         s_idx[ql * K + lane] = kn.idx;
+        s_gidx[ql * K + lane] = kn.gidx;
         s_d2[ql * K + lane] = kn.d2;
       }
       if (lane == 0) {
@@ -305,20 +310,25 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
                         gn2 = s_act[(F + 2) * ACT_LD + ql];
             float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
             if (valid) {
+              // n_k is measured to the neighbour in the queried index space, the IDW distance to the
+              // global point the hash returned (they only differ through the reference's global2local
+              // fill value, see DESIGN.md "reference quirks")
               const float* pp = m.nb_points + 3 * (size_t)lk;
-              dx = qx - __ldg(pp);
-              dy = qy - __ldg(pp + 1);
-              dz = qz - __ldg(pp + 2);
-              nx = dx;
-              ny = dy;
-              nz = dz;
+              nx = qx - __ldg(pp);
+              ny = qy - __ldg(pp + 1);
+              nz = qz - __ldg(pp + 2);
+              const float* pg = m.points + 3 * (size_t)s_gidx[ql * K + lane];
+              dx = qx - __ldg(pg);
+              dy = qy - __ldg(pg + 1);
+              dz = qz - __ldg(pg + 2);
+              const float ux = nx, uy = ny, uz = nz;
               r0 = gn0;
               r1 = gn1;
               r2 = gn2;
               if (m.after_pgo) {
                 const float* qq = m.nb_orient + 4 * (size_t)lk;
                 const float a = __ldg(qq), b = __ldg(qq + 1), cc = __ldg(qq + 2), dd = __ldg(qq + 3);
-                quat_rotate_passive(a, b, cc, dd, dx, dy, dz, nx, ny, nz);
+                quat_rotate_passive(a, b, cc, dd, ux, uy, uz, nx, ny, nz);
                 quat_rotate_active(a, b, cc, dd, gn0, gn1, gn2, r0, r1, r2);
               }
             }
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
                 const int row = ql * K + k;
                 float r0 = s_act[(F + 0) * ACT_LD + row], r1 = s_act[(F + 1) * ACT_LD + row],
                       r2 = s_act[(F + 2) * ACT_LD + row];
-                const float* pp = m.nb_points + 3 * (size_t)lk;
+                const float* pp = m.points + 3 * (size_t)s_gidx[ql * K + k];  // the point dist2 was measured to
                 const float dx = qx - __ldg(pp), dy = qy - __ldg(pp + 1), dz = qz - __ldg(pp + 2);
                 if (m.after_pgo) {
                   const float* qq = m.nb_orient + 4 * (size_t)lk;
@@ -456,7 +466,8 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE) knn_kernel(const __grid_constant__ pinb200_map_view m,
                                                    const float* __restrict__ query_xyz, long long n, int K,
-                                                   int32_t* knn_idx, float* knn_d2, float* knn_w, int32_t* nn_count) {
+                                                   int32_t* knn_idx, int32_t* knn_gidx, float* knn_d2, float* knn_w,
+                                                   int32_t* nn_count) {
   extern __shared__ __align__(16) float smem[];
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem);
   fill_probe_deltas(m, s_delta);
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(TILE) knn_kernel(const __grid_constant__ pinb2
     const float w = idw_weight(kn.d2, kn.idx >= 0, kn.count, K, lane, u, inv_s);
     if (lane < K) {
       if (knn_idx) knn_idx[qi * K + lane] = kn.idx;
+      if (knn_gidx) knn_gidx[qi * K + lane] = kn.gidx;
       if (knn_d2) knn_d2[qi * K + lane] = kn.d2;
       if (knn_w) knn_w[qi * K + lane] = w;
     }
@@ -510,7 +522,7 @@ __global__ void __launch_bounds__(TILE) radius_kernel(const __grid_constant__ pi
 }
 
 // query_feature's materialised feature vectors from saved kNN (compat path)
-__global__ void __launch_bounds__(TILE) gather_kernel(const __grid_constant__ pinb200_map_view m,
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ pinb200_map_view m,
                                                       const float* __restrict__ feat,
                                                       const float* __restrict__ query_xyz,
                                                       const int32_t* __restrict__ knn_idx,
@@ -593,6 +605,8 @@ static QueryLayout plan_layout(const QueryParams& p, int DP) {
   l.act = o;
   o += align4(act_rows * ACT_LD);
   l.knn_idx = o;
+  o += TILE * K;
+  l.knn_gidx = o;
   o += TILE * K;
   l.knn_d2 = o;
   o += TILE * K;
@@ -691,8 +705,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   if (color_dec) {
     rc = validate_decoder(color_dec, map->feature_dim);
     if (rc) return rc;
-    if (!map->color_feat || !out->knn_idx || !out->knn_dist2 || !out->nn_count) {
-      set_error("colour head needs map->color_feat and out->knn_idx/knn_dist2/nn_count as scratch");
+    if (!map->color_feat || !out->knn_idx || !out->knn_gidx || !out->knn_dist2 || !out->nn_count) {
+      set_error("colour head needs map->color_feat and out->knn_idx/knn_gidx/knn_dist2/nn_count as scratch");
       return PINB200_ERR_BAD_ARG;
     }
   }
@@ -723,8 +737,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
 }
 
 extern "C" int pinb200_knn_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, int32_t nn_k,
-                                  int32_t* knn_idx, float* knn_dist2, float* knn_weight, int32_t* nn_count,
-                                  void* stream) {
+                                  int32_t* knn_idx, int32_t* knn_gidx, float* knn_dist2, float* knn_weight,
+                                  int32_t* nn_count, void* stream) {
   int rc = validate_map(map, false);
   if (rc) return rc;
   if (nn_k < 1 || nn_k > PINB200_MAX_K || nn_k > map->n_probe) {
@@ -734,7 +748,7 @@ extern "C" int pinb200_knn_search(const pinb200_map_view* map, const float* quer
   if (n <= 0) return PINB200_OK;
   const int grid = (int)std::min<long long>((n + 3) / 4, (long long)sm_count() * 8);
   knn_kernel<<<grid, TILE, align4(map->n_probe) * sizeof(float), (cudaStream_t)stream>>>(
-      *map, query_xyz, n, nn_k, knn_idx, knn_dist2, knn_weight, nn_count);
+      *map, query_xyz, n, nn_k, knn_idx, knn_gidx, knn_dist2, knn_weight, nn_count);
   return check_launch("knn_kernel");
 }
 

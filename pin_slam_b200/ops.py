@@ -138,6 +138,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
         qo.knn_idx = _ptr(buf("knn_idx", (n, nn_k), torch.int32))
         qo.knn_dist2 = _ptr(buf("knn_dist2", (n, nn_k)))
         qo.knn_weight = _ptr(buf("knn_weight", (n, nn_k)))
+        qo.knn_gidx = _ptr(buf("knn_gidx", (n, nn_k), torch.int32))
     if want_xyz:
         qo.xyz = _ptr(buf("xyz", (n, 3)))
     if color_dec is not None:
@@ -156,17 +157,20 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
     return o
 
 
-def knn_search(mh: MapHandle, xyz: torch.Tensor, nn_k: int):
+def knn_search(mh: MapHandle, xyz: torch.Tensor, nn_k: int, want_gidx: bool = False):
     lib = _lib.load()
     n, dev = xyz.shape[0], xyz.device
     idx = torch.empty((n, nn_k), dtype=torch.int32, device=dev)
+    gidx = torch.empty((n, nn_k), dtype=torch.int32, device=dev) if want_gidx else None
     d2 = torch.empty((n, nn_k), dtype=torch.float32, device=dev)
     w = torch.empty((n, nn_k), dtype=torch.float32, device=dev)
     cnt = torch.empty((n,), dtype=torch.int32, device=dev)
-    rc = lib.pinb200_knn_search(C.byref(mh.view), _ptr(xyz, torch.float32), n, nn_k, _ptr(idx), _ptr(d2), _ptr(w),
-                                _ptr(cnt), _stream())
+    rc = lib.pinb200_knn_search(C.byref(mh.view), _ptr(xyz, torch.float32), n, nn_k, _ptr(idx), _ptr(gidx), _ptr(d2),
+                                _ptr(w), _ptr(cnt), _stream())
     _lib.check(rc, "pinb200_knn_search")
     _count()
+    if want_gidx:
+        return idx, d2, w, cnt, gidx
     return idx, d2, w, cnt
 
 

@@ -1,0 +1,122 @@
+"""Seeded synthetic inputs of the benchmark workloads (there is no network for datasets).
+
+  * `room_surface_points`  -- points on the surfaces of a closed analytic scene (ground, four
+    walls, a few boxes that break the corridor symmetry), used to grow a neural point map;
+  * `lidar_scan`           -- a 64 x 1024 KITTI-shaped scan of that scene by analytic ray casting
+    (64 elevations in [+2, -24.8] deg, 1024 azimuths, 1 cm range noise), sensor height 1.73 m;
+  * `build_map`            -- grows a `NeuralPoints` map from surface points through its own
+    `update()` (the reference's map-growth entry point).
+"""
+import math
+
+import torch
+
+BOXES = [  # (cx, cy, half_x, half_y, height)
+    (8.0, 6.0, 2.0, 1.5, 2.5), (-12.0, -9.0, 1.5, 3.0, 3.0), (20.0, -14.0, 3.0, 2.0, 2.0), (-25.0, 15.0, 2.5, 2.5, 4.0),
+    (3.0, -20.0, 1.0, 4.0, 1.5), (30.0, 22.0, 2.0, 2.0, 3.5),
+]
+
+
+def room_surface_points(n, seed, extent=80.0, wall_h=6.0, device="cpu", noise=0.01):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda k: torch.rand(k, generator=g)  # noqa: E731
+    half = extent / 2
+    u = lambda k: r(k) * extent - half  # noqa: E731
+    area = [extent * extent] + [extent * wall_h] * 4 + [4 * (2 * b[2] + 2 * b[3]) * b[4] + 4 * b[2] * b[3] for b in BOXES]
+    tot = sum(area)
+    cnt = [max(1, int(n * a / tot)) for a in area]
+    parts = [torch.stack([u(cnt[0]), u(cnt[0]), torch.zeros(cnt[0])], 1)]
+    for i, (ax, val) in enumerate([(1, half), (1, -half), (0, half), (0, -half)]):
+        k = cnt[1 + i]
+        a, z = u(k), r(k) * wall_h
+        fixed = torch.full((k,), val)
+        parts.append(torch.stack([a, fixed, z], 1) if ax == 1 else torch.stack([fixed, a, z], 1))
+    for j, (cx, cy, hx, hy, h) in enumerate(BOXES):
+        k = cnt[5 + j]
+        side = torch.randint(0, 5, (k,), generator=g)
+        x = cx + (r(k) * 2 - 1) * hx
+        y = cy + (r(k) * 2 - 1) * hy
+        z = r(k) * h
+        x = torch.where(side == 0, torch.full_like(x, cx - hx), torch.where(side == 1, torch.full_like(x, cx + hx), x))
+        y = torch.where(side == 2, torch.full_like(y, cy - hy), torch.where(side == 3, torch.full_like(y, cy + hy), y))
+        z = torch.where(side == 4, torch.full_like(z, h), z)
+        parts.append(torch.stack([x, y, z], 1))
+    p = torch.cat(parts, 0)
+    p = p + noise * torch.randn(p.shape, generator=g)
+    return p.to(device)
+
+
+def _ray_box(o, d, lo, hi):
+    """Slab test, rays [N,3] against one axis-aligned box; returns entry t (inf if missed)."""
+    inv = 1.0 / torch.where(d.abs() < 1e-9, torch.full_like(d, 1e-9), d)
+    t0 = (lo - o) * inv
+    t1 = (hi - o) * inv
+    tmin = torch.minimum(t0, t1).max(dim=1)[0]
+    tmax = torch.maximum(t0, t1).min(dim=1)[0]
+    hit = (tmax >= tmin) & (tmax > 0)
+    t = torch.where(tmin > 0, tmin, tmax)
+    return torch.where(hit, t, torch.full_like(t, float("inf")))
+
+
+def lidar_scan(pose: torch.Tensor, seed: int, extent=80.0, wall_h=6.0, beams=64, azimuths=1024, noise=0.01,
+               max_range=80.0, device="cpu"):
+    """Sensor-frame points [<=beams*azimuths, 3] of one scan taken at `pose` (4x4, sensor->world)."""
+    g = torch.Generator().manual_seed(seed)
+    el = torch.deg2rad(torch.linspace(2.0, -24.8, beams))
+    az = torch.linspace(-math.pi, math.pi, azimuths + 1)[:-1]
+    ee, aa = torch.meshgrid(el, az, indexing="ij")
+    d_s = torch.stack([torch.cos(ee) * torch.cos(aa), torch.cos(ee) * torch.sin(aa), torch.sin(ee)], -1).reshape(-1, 3)
+    rot, org = pose[:3, :3].float(), pose[:3, 3].float()
+    d_w = d_s @ rot.T
+    o = org.expand_as(d_w)
+    half = extent / 2
+    # inside of the room: distance to the exit of the big box = the wall/ground hit
+    inv = 1.0 / torch.where(d_w.abs() < 1e-9, torch.full_like(d_w, 1e-9), d_w)
+    lo = torch.tensor([-half, -half, 0.0])
+    hi = torch.tensor([half, half, wall_h + 100.0])  # no ceiling: rays that go up leave the scene
+    t_exit = torch.maximum((lo - o) * inv, (hi - o) * inv).min(dim=1)[0]
+    hit_z = o[:, 2] + t_exit * d_w[:, 2]
+    t = torch.where(hit_z <= wall_h + 1e-3, t_exit, torch.full_like(t_exit, float("inf")))
+    for cx, cy, hx, hy, h in BOXES:
+        t = torch.minimum(t, _ray_box(o, d_w, torch.tensor([cx - hx, cy - hy, 0.0]), torch.tensor([cx + hx, cy + hy, h])))
+    ok = torch.isfinite(t) & (t < max_range) & (t > 1.0)
+    rng = t + noise * torch.randn(t.shape, generator=g)
+    return (d_s * rng.unsqueeze(1))[ok].to(device)
+
+
+def trajectory_pose(frame: int, step=0.8, yaw_per_frame=0.004, height=1.73):
+    yaw = yaw_per_frame * frame
+    c, s = math.cos(yaw), math.sin(yaw)
+    T = torch.eye(4, dtype=torch.float64)
+    T[0, 0], T[0, 1], T[1, 0], T[1, 1] = c, -s, s, c
+    T[0, 3] = -20.0 + step * frame
+    T[1, 3] = 0.5 * math.sin(0.05 * frame)
+    T[2, 3] = height
+    return T
+
+
+def build_map(config, n_surface=3_000_000, seed=0, extent=80.0, feature_seed=1234):
+    """A NeuralPoints map grown from synthetic surface points through NeuralPoints.update()."""
+    from .model import NeuralPoints
+
+    dev = torch.device(config.device)
+    npm = NeuralPoints(config)
+    npm.travel_dist = torch.zeros(4, device=dev)
+    pts = room_surface_points(n_surface, seed, extent=extent, device=dev)
+    gen_state = torch.cuda.get_rng_state(dev) if dev.type == "cuda" else torch.get_rng_state()
+    torch.manual_seed(feature_seed)
+    npm.update(pts, torch.tensor([0.0, 0.0, 1.0], device=dev), torch.eye(3, device=dev), 0)
+    if dev.type == "cuda":
+        torch.cuda.set_rng_state(gen_state, dev)
+    else:
+        torch.set_rng_state(gen_state)
+    return npm
+
+
+def surface_queries(npm, n, seed, sigma=0.1):
+    """n query points: neural point positions + N(0, sigma^2) offsets."""
+    dev = npm.neural_points.device
+    g = torch.Generator().manual_seed(seed)
+    sel = torch.randint(0, npm.count(), (n,), generator=g).to(dev)
+    off = (sigma * torch.randn(n, 3, generator=g)).to(dev)
+    return (npm.neural_points[sel] + off).contiguous()
