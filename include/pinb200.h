@@ -92,6 +92,9 @@ typedef struct pinb200_query_opts {
   int32_t weighted_first;   /* config.weighted_first */
   int32_t training_mode;    /* certainty / ts scatter side effects (:685-710) */
   int32_t need_grad;        /* also produce d sdf / d query (replaces tools.py:247 autograd.grad) */
+  int64_t training_rows;    /* side effects only for the first training_rows queries (0 = all); the numerical-
+                               gradient rows of a training batch follow the samples and are inference-mode
+                               (mapper.py:941) */
   const double* transform;  /* optional device ptr, 4x4 row-major fp64: q = T*p evaluated in fp32 (tools.py:534-553) */
 } pinb200_query_opts;
 
@@ -171,10 +174,11 @@ int pinb200_train_backward(const pinb200_map_view* map, const pinb200_decoder_vi
  * BCE-with-logits on the first n_main rows, Eikonal on the 6*n_eik numerical-
  * gradient rows laid out [x+ | x- | y+ | y- | z+ | z-] after them
  * (mapper.py:1002-1014).  Writes d loss / d sdf for every row (of the total loss
- * bce + weight_e * eikonal) and losses[0]=bce, [1]=eikonal (unweighted). */
+ * bce + weight_e * eikonal, times grad_scale = 1/world_size when the batch is sharded over GPUs and the
+ * gradients are summed by an all-reduce) and losses[0]=bce, [1]=eikonal (unweighted). */
 int pinb200_mapping_loss(const float* sdf, const float* sdf_label, const float* weight, int64_t n_main,
                          int64_t n_eik, float sigma, int32_t loss_weight_on, float weight_e,
-                         float eik_eps, float* dloss_dsdf, float* losses, void* stream);
+                         float eik_eps, float grad_scale, float* dloss_dsdf, float* losses, void* stream);
 
 /* K3 -- Adam step, arithmetic of torch.optim.Adam (betas .9/.99, no amsgrad)
  * as set up by utils/tools.py:153-203; `step` is the 1-based step count.

@@ -38,7 +38,7 @@ class DecoderView(C.Structure):
 
 class QueryOpts(C.Structure):
     _fields_ = [("nn_k", C.c_int32), ("weighted_first", C.c_int32), ("training_mode", C.c_int32),
-                ("need_grad", C.c_int32), ("transform", c_f64p)]
+                ("need_grad", C.c_int32), ("training_rows", C.c_int64), ("transform", c_f64p)]
 
 
 class QueryOut(C.Structure):
@@ -63,7 +63,7 @@ SIGNATURES = {
     "pinb200_train_backward": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), c_f32p, c_f32p, c_i32p, c_f32p,
                                          c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
     "pinb200_mapping_loss": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_float, C.c_int32,
-                                       C.c_float, C.c_float, c_f32p, c_f32p, C.c_void_p]),
+                                       C.c_float, C.c_float, C.c_float, c_f32p, c_f32p, C.c_void_p]),
     "pinb200_adam_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                     C.c_double, C.c_double, C.c_int32, C.c_void_p]),
     "pinb200_gn_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int32,

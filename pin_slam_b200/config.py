@@ -84,6 +84,35 @@ class HotPathConfig:
     eigenvalue_ratio_thre: float = 0.005
     final_residual_ratio_thre: float = 0.6
     semantic_on: bool = False
+    # sampler / pool / map management (config.py:105-136)
+    surface_sample_n: int = 3
+    free_sample_begin_ratio: float = 0.3
+    free_sample_end_dist_m: float = 1.0
+    free_front_n: int = 2
+    free_behind_n: int = 1
+    dist_weight_on: bool = True
+    dist_weight_scale: float = 0.8
+    behind_dropoff_on: bool = False
+    from_sample_points: bool = True
+    from_all_samples: bool = False
+    map_surface_ratio: float = 0.5
+    prune_map_on: bool = False
+    max_prune_certainty: float = 3.0
+    prune_freq_frame: int = 100
+    window_radius: float = 50.0
+    pool_capacity: int = int(1e7)
+    new_certainty_thre: float = 1.0
+    pool_filter_freq: int = 10
+    adaptive_iters: bool = False
+    new_sample_ratio_less: float = 0.02
+    new_sample_ratio_more: float = 0.15
+    new_sample_ratio_restart: float = 0.3
+    freeze_after_frame: int = 40
+    dynamic_filter_on: bool = False
+    dynamic_certainty_thre: float = 1.0
+    dynamic_sdf_ratio_thre: float = 0.5
+    dynamic_min_grad_norm_thre: float = 0.25
+    pgo_on: bool = False
 
     @property
     def infer_bs(self):
@@ -94,7 +123,9 @@ class HotPathConfig:
         """config/lidar_slam/run_kitti.yaml of the reference."""
         d = dict(voxel_size_m=0.4, weighted_first=False, feature_dim=8, query_nn_k=6, track_mask_query_nn_k=6,
                  sigma_sigmoid_m=0.08, loss_weight_on=True, weight_e=0.5, max_range=80.0, local_map_radius=82.0,
-                 surface_sample_range_m=0.25, reg_GM_dist_m=0.2, reg_GM_grad=0.1, reg_iter_n=100, bs_new_sample=1000)
+                 surface_sample_range_m=0.25, reg_GM_dist_m=0.2, reg_GM_grad=0.1, reg_iter_n=100, bs_new_sample=1000,
+                 surface_sample_n=4, free_front_n=2, free_behind_n=1, window_radius=80.0, pool_capacity=int(2e7),
+                 pool_filter_freq=1)
         d.update(kw)
         return cls(**d)
 

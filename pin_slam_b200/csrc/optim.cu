@@ -33,7 +33,7 @@ __global__ void adam_kernel(float* __restrict__ param, float* __restrict__ grad,
 // utils/mapper.py:728-780, utils/loss.py:45-63, utils/mapper.py:1002-1014.
 __global__ void mapping_loss_kernel(const float* __restrict__ sdf, const float* __restrict__ label,
                                     const float* __restrict__ weight, long long n_main, long long n_eik, float sigma,
-                                    int weighted, float weight_e, float eik_eps, float* __restrict__ dl,
+                                    int weighted, float weight_e, float eik_eps, float gscale, float* __restrict__ dl,
                                     float* __restrict__ losses) {
   float bce = 0.f, eik = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -46,7 +46,7 @@ __global__ void mapping_loss_kernel(const float* __restrict__ sdf, const float* 
     // (1-t)*z + log1p(exp(-|z|)) + max(-z,0)
     bce += w * ((1.f - t) * z + log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f));
     const float sg = 1.f / (1.f + expf(-z));
-    dl[i] = w * (sg - t) * inv_n / sigma;
+    dl[i] = gscale * w * (sg - t) * inv_n / sigma;
   }
   if (n_eik > 0) {
     const float* s = sdf + n_main;
@@ -59,7 +59,7 @@ __global__ void mapping_loss_kernel(const float* __restrict__ sdf, const float* 
       const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
       const float e = nrm - 1.f;
       eik += e * e;
-      const float c = nrm > 0.f ? weight_e * 2.f * e / ((float)n_eik * nrm) * inv2e : 0.f;
+      const float c = nrm > 0.f ? gscale * weight_e * 2.f * e / ((float)n_eik * nrm) * inv2e : 0.f;
       d[j] = c * gx;
       d[n_eik + j] = -c * gx;
       d[2 * n_eik + j] = c * gy;
@@ -102,7 +102,7 @@ extern "C" int pinb200_adam_step(float* param, float* grad, float* exp_avg, floa
 
 extern "C" int pinb200_mapping_loss(const float* sdf, const float* sdf_label, const float* weight, int64_t n_main,
                                     int64_t n_eik, float sigma, int32_t loss_weight_on, float weight_e, float eik_eps,
-                                    float* dloss_dsdf, float* losses, void* stream) {
+                                    float grad_scale, float* dloss_dsdf, float* losses, void* stream) {
   if (!sdf || !sdf_label || !dloss_dsdf || n_main <= 0 || (loss_weight_on && !weight)) {
     set_error("mapping_loss: null argument / empty batch");
     return PINB200_ERR_BAD_ARG;
@@ -117,6 +117,6 @@ extern "C" int pinb200_mapping_loss(const float* sdf, const float* sdf_label, co
   const long long work = std::max<long long>(n_main, n_eik);
   const int grid = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 4);
   mapping_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sdf, sdf_label, weight, n_main, n_eik, sigma,
-                                                              loss_weight_on, weight_e, eik_eps, dloss_dsdf, losses);
+                                                              loss_weight_on, weight_e, eik_eps, grad_scale, dloss_dsdf, losses);
   return check_launch("mapping_loss_kernel");
 }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
       if (!p.is_color) {
         // queried certainty (:713-718) uses the values gathered before this query's own scatter
         const float qc = warp_sum(cert * w);
-        if (p.opts.training_mode && valid) {  // (:685-710); invalid entries add 0 / max with 0 in the reference
+        if (p.opts.training_mode && valid && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {  // (:685-710); invalid entries add 0 / max with 0 in the reference
           atomicAdd(m.certainty + kn.idx, w);
           if (m.ts_update && p.query_ts) atomicMax(m.ts_update + kn.idx, __ldg(p.query_ts + qi));
         }

@@ -75,7 +75,31 @@ class Decoder(nn.Module):
             self._handle = {"h": h, "key": key}
         return h
 
+    def flat_parameters(self) -> torch.Tensor:
+        """All parameters as ONE contiguous vector [w0|b0|w1|b1|...|w_out|b_out] (the layout K2/K3 use).
+        On first use the nn.Linear parameters are re-pointed to views of this vector, so the fused Adam
+        step updates the modules in place and state_dict()/checkpoints keep working."""
+        ps = [p for l in self.layers for p in (l.weight, l.bias) if p is not None]
+        ps += [p for p in (self.lout.weight, self.lout.bias) if p is not None]
+        flat = getattr(self, "_flat", None)
+        ok = flat is not None and flat.device == ps[0].device
+        if ok:
+            off = 0
+            for p in ps:
+                ok = ok and p.data_ptr() == flat.data_ptr() + 4 * off
+                off += p.numel()
+        if not ok:
+            flat = torch.cat([p.detach().reshape(-1) for p in ps]).contiguous()
+            off = 0
+            for p in ps:
+                p.data = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._flat = flat
+            self._handle = {}
+        return flat
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_handle"] = {}
+        state.pop("_flat", None)
         return state

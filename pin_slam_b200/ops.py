@@ -113,7 +113,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
               training_mode: bool = False, need_grad: bool = True, query_ts: Optional[torch.Tensor] = None,
               color_dec: Optional[DecoderHandle] = None, color_grad: bool = False,
               transform: Optional[torch.Tensor] = None, save_knn: bool = False, want_xyz: bool = False,
-              out: Optional[dict] = None):
+              training_rows: int = 0, out: Optional[dict] = None):
     """K1.  Returns a dict of freshly allocated (or caller-provided `out`) CUDA tensors."""
     lib = _lib.load()
     n = xyz.shape[0]
@@ -147,7 +147,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
         if color_grad:
             qo.color_grad = _ptr(buf("color_grad", (n, cc, 3)))
     opts = QueryOpts(int(nn_k), int(bool(weighted_first)), int(bool(training_mode)), int(bool(need_grad)),
-                     _ptr(transform, torch.float64))
+                     int(training_rows), _ptr(transform, torch.float64))
     rc = lib.pinb200_query_sdf(C.byref(mh.view), C.byref(dec.view),
                                C.byref(color_dec.view) if color_dec is not None else None,
                                _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), n, C.byref(opts), C.byref(qo),
@@ -220,11 +220,12 @@ def train_backward(mh: MapHandle, dec: DecoderHandle, feat, xyz, knn_idx, knn_we
     _count()
 
 
-def mapping_loss(sdf, sdf_label, weight, n_main, n_eik, sigma, loss_weight_on, weight_e, eik_eps, dloss, losses):
+def mapping_loss(sdf, sdf_label, weight, n_main, n_eik, sigma, loss_weight_on, weight_e, eik_eps, dloss, losses,
+                 grad_scale: float = 1.0):
     lib = _lib.load()
     rc = lib.pinb200_mapping_loss(_ptr(sdf, torch.float32), _ptr(sdf_label, torch.float32),
                                   _ptr(weight, torch.float32), n_main, n_eik, float(sigma), int(bool(loss_weight_on)),
-                                  float(weight_e), float(eik_eps), _ptr(dloss, torch.float32),
+                                  float(weight_e), float(eik_eps), float(grad_scale), _ptr(dloss, torch.float32),
                                   _ptr(losses, torch.float32), _stream())
     _lib.check(rc, "pinb200_mapping_loss")
     _count()

@@ -1,0 +1,358 @@
+"""Online map training on the fused kernels.
+
+API-compatible with the reference `Mapper` (utils/mapper.py:33 of PRBonn/PIN_SLAM): same
+constructor, pool attributes, `process_frame`, `get_batch`, `mapping`, `sdf`, `sdf_batch`,
+`get_numerical_gradient`, `dynamic_filter`, `determine_used_pose`, `transform_data_pool`.
+One training iteration (reference: ~590 ATen ops + ~32 host syncs, mapper.py:623-822) is
+
+    batch draw          torch.randint + pool gathers (same RNG calls as the reference)
+    K1  query_sdf       all bs + 6*ceil(bs/10) rows in ONE launch (training side effects on the
+                        first bs rows only), kNN ids / weights saved
+    loss heads          BCE-with-logits + Eikonal (numerical gradient) -> d loss / d sdf per row
+    K2  train_backward  decoder activations recomputed, feature-gradient scatter + decoder grads
+    K3  adam_step x2    neural-point features, decoder parameters (fresh Adam state per call,
+                        like the reference's per-frame setup_optimizer)
+
+With torch.distributed initialised (one process per GPU, NCCL over NVLink) every rank trains on its
+own sub-batch of its pool shard and the gradients / certainty increments are summed with ONE
+all-reduce per iteration (plus a max-reduce of the timestamps); map, decoder and Adam state stay
+replicated and bit-identical across ranks.
+"""
+import math
+
+import torch
+
+from .. import ops
+
+
+class DataSampler:
+    """Per-ray training samples (reference: utils/data_sampler.py:18-260): the measured end point,
+    `surface_sample_n` Gaussian samples around it, `free_front_n` uniform samples in front and
+    `free_behind_n` behind; label = signed distance along the ray (positive in front)."""
+
+    def __init__(self, config):
+        self.config = config
+        self.dev = config.device
+
+    def sample(self, points, normals, sem_labels, colors):
+        c = self.config
+        dev = points.device
+        n = points.shape[0]
+        ns, nf, nb = c.surface_sample_n, c.free_front_n, c.free_behind_n
+        total = 1 + ns + nf + nb
+        sigma = c.surface_sample_range_m
+        dist = torch.linalg.norm(points, dim=1, keepdim=True)  # [n,1]
+        # same RNG draws, in the same order, as the reference sampler
+        disp_surf = torch.randn(n * ns, 1, device=dev) * sigma
+        d_f = dist.repeat(nf, 1)
+        front_hi = 1.0 - 2.0 * sigma / d_f
+        ratio_front = torch.rand(n * nf, 1, device=dev) * (front_hi - c.free_sample_begin_ratio) + c.free_sample_begin_ratio
+        d_b = dist.repeat(nb, 1)
+        behind_lo = 1.0 + 2.0 * sigma / d_b
+        ratio_behind = torch.rand(n * nb, 1, device=dev) * (c.free_sample_end_dist_m / d_b + 1.0 - behind_lo) + behind_lo
+        ratio = torch.cat((torch.ones_like(dist), disp_surf / dist.repeat(ns, 1) + 1.0, ratio_front, ratio_behind), 0)
+        disp = torch.cat((torch.zeros_like(dist), disp_surf, (ratio_front - 1.0) * d_f, (ratio_behind - 1.0) * d_b), 0)
+        d_all = dist.repeat(total, 1)
+        coord = points.repeat(total, 1) * ratio
+        weight = torch.ones_like(d_all)
+        n_surf = n * (ns + 1)
+        if c.dist_weight_on:
+            weight[:n_surf] = 1 + c.dist_weight_scale * 0.5 - (d_all[:n_surf] / c.max_range) * c.dist_weight_scale
+        if c.behind_dropoff_on:
+            lo, hi = 0.2 * c.free_sample_end_dist_m, c.free_sample_end_dist_m
+            weight = weight * (torch.clamp((hi - disp) / (hi - lo), 0.0, 1.0) * 0.8 + 0.2)
+        weight[n_surf:] *= -1.0  # sign marks free-space samples
+        # ray-major order: all samples of ray 0, then ray 1, ...
+        by_ray = lambda t_, w: t_.reshape(total, n, w).transpose(0, 1).reshape(-1, w)  # noqa: E731
+        coord = by_ray(coord, 3)
+        label = -by_ray(disp, 1).squeeze(1)
+        weight = by_ray(weight, 1).squeeze(1)
+        normal_label = None if normals is None else by_ray(normals.repeat(total, 1), 3)
+        color_label = None
+        if colors is not None:
+            cc = colors.shape[1]
+            color_all = torch.cat((colors, colors.repeat(ns, 1), torch.zeros(n * (nf + nb), cc, device=dev)), 0)
+            color_label = by_ray(color_all, cc)
+        return coord, label, normal_label, None, color_label, weight
+
+
+def _transform(points, pose):
+    p = pose.to(points)
+    return points @ p[:3, :3].T + p[:3, 3]
+
+
+class Mapper:
+    def __init__(self, config, dataset, neural_points, decoders: dict):
+        self.config = config
+        self.silence = config.silence
+        self.dataset = dataset
+        self.neural_points = neural_points
+        self.sdf_mlp = decoders["sdf"]
+        self.sem_mlp = decoders.get("semantic")
+        self.color_mlp = decoders.get("color")
+        self.device = config.device
+        self.dtype = config.dtype
+        self.used_poses = None
+        self.require_gradient = False
+        self.total_iter = 0
+        self.sdf_scale = config.logistic_gaussian_ratio * config.sigma_sigmoid_m
+        self.sampler = DataSampler(config)
+        self.ray_sample_count = 1 + config.surface_sample_n + config.free_behind_n + config.free_front_n
+        self.new_idx = None
+        self.ba_done_flag = False
+        self.adaptive_iter_offset = 0
+        self.static_mask = None
+        self.cur_sample_count = 0
+        self.pool_sample_count = 0
+        self.last_losses = None
+        self._work = {}
+        self.init_pool()
+
+    # ------------------------------------------------------------------ pool
+    def init_pool(self):
+        dev, dt = self.device, self.dtype
+        self.coord_pool = torch.empty((0, 3), device=dev, dtype=dt)
+        self.global_coord_pool = torch.empty((0, 3), device=dev, dtype=dt)
+        self.sdf_label_pool = torch.empty((0,), device=dev, dtype=dt)
+        self.color_pool = torch.empty((0, self.config.color_channel), device=dev, dtype=dt)
+        self.sem_label_pool = None
+        self.normal_label_pool = None
+        self.weight_pool = torch.empty((0,), device=dev, dtype=dt)
+        self.time_pool = torch.empty((0,), device=dev, dtype=torch.int32)
+
+    def free_pool(self):
+        self.coord_pool = self.weight_pool = self.sdf_label_pool = self.time_pool = None
+        self.sem_label_pool = self.color_pool = self.normal_label_pool = None
+
+    def determine_used_pose(self):
+        cur = self.dataset.processed_frame
+        src = None
+        if getattr(self.config, "pgo_on", False):
+            src = self.dataset.pgo_poses
+        elif self.config.track_on:
+            src = self.dataset.odom_poses
+        elif self.dataset.gt_pose_provided:
+            src = self.dataset.gt_poses
+        if src is not None:
+            self.used_poses = torch.as_tensor(src[: cur + 1], device=self.device, dtype=torch.float64)
+
+    def transform_data_pool(self, pose_diff_torch):
+        tf = pose_diff_torch[self.time_pool.long()].to(self.global_coord_pool)
+        self.global_coord_pool = (tf[:, :3, :3] @ self.global_coord_pool.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+
+    # ------------------------------------------------------------------ per-frame preparation
+    def dynamic_filter(self, points_torch, type_2_on: bool = True):
+        """Static mask of a frame from the map's SDF and stability (reference: mapper.py:99-137)."""
+        cfg = self.config
+        o = self.neural_points.query_sdf(points_torch.contiguous(), self.sdf_mlp, need_grad=type_2_on)
+        uncertain = o["certainty"] < cfg.dynamic_certainty_thre
+        static = uncertain | (o["sdf"] < cfg.dynamic_sdf_ratio_thre * cfg.voxel_size_m)
+        if type_2_on:
+            static = static & ((o["grad"].norm(dim=-1) > cfg.dynamic_min_grad_norm_thre) | uncertain)
+        return static
+
+    def process_frame(self, point_cloud_torch, frame_label_torch, cur_pose_torch, frame_id: int,
+                      filter_dynamic: bool = False):
+        """Sample the frame, grow the map, append to the replay pool (reference: mapper.py:162-449)."""
+        cfg = self.config
+        origin = cur_pose_torch[:3, 3]
+        orient = cur_pose_torch[:3, :3]
+        pts = point_cloud_torch[:, :3]
+        self.static_mask = torch.ones(pts.shape[0], dtype=torch.bool, device=self.device)
+        if filter_dynamic:
+            self.neural_points.reset_local_map(origin, orient, frame_id)
+            self.static_mask = self.dynamic_filter(_transform(pts, cur_pose_torch))
+            pts = pts[self.static_mask]
+        colors = None
+        if cfg.color_on:
+            colors = point_cloud_torch[:, 3:]
+            if filter_dynamic:
+                colors = colors[self.static_mask]
+        self.dataset.static_mask = self.static_mask
+
+        coord, label, normal_label, _, color_label, weight = self.sampler.sample(pts, None, None, colors)
+        stamps = torch.full((coord.shape[0],), frame_id, dtype=torch.int32, device=self.device)
+        self.cur_sample_count = label.shape[0]
+        self.pool_sample_count = self.sdf_label_pool.shape[0]
+
+        if cfg.from_sample_points:
+            if cfg.from_all_samples:
+                grow_pts = coord
+            else:
+                near = torch.abs(label) < cfg.surface_sample_range_m * cfg.map_surface_ratio
+                grow_pts = _transform(coord[near], cur_pose_torch)
+        else:
+            grow_pts = _transform(pts, cur_pose_torch)
+        if cfg.prune_map_on and ((frame_id + 1) % cfg.prune_freq_frame == 0):
+            if self.neural_points.prune_map(cfg.max_prune_certainty):
+                self.neural_points.recreate_hash(None, None, True, True, frame_id)
+        self.cur_new_point_ratio = self.neural_points.update(grow_pts, origin, orient, frame_id)
+        self.neural_points.record_memory(verbose=(not self.silence))
+
+        self.coord_pool = torch.cat((self.coord_pool, coord), 0)
+        self.weight_pool = torch.cat((self.weight_pool, weight), 0)
+        self.sdf_label_pool = torch.cat((self.sdf_label_pool, label), 0)
+        self.time_pool = torch.cat((self.time_pool, stamps), 0)
+        self.color_pool = torch.cat((self.color_pool, color_label), 0) if color_label is not None else None
+        self.determine_used_pose()
+        if self.ba_done_flag:
+            tf = self.used_poses[self.time_pool.long()].to(self.coord_pool)
+            self.global_coord_pool = (tf[:, :3, :3] @ self.coord_pool.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+            self.ba_done_flag = False
+        else:
+            self.global_coord_pool = torch.cat((self.global_coord_pool, _transform(coord, cur_pose_torch)), 0)
+
+        if (frame_id + 1) % cfg.pool_filter_freq == 0:
+            keep = ((self.global_coord_pool - origin) ** 2).sum(-1) < cfg.window_radius**2
+            alive = torch.nonzero(keep).squeeze(-1)
+            if alive.shape[0] > cfg.pool_capacity:
+                drop = torch.randint(0, alive.shape[0], (alive.shape[0] - cfg.pool_capacity,), device=self.device)
+                keep[alive[drop]] = False
+            self.coord_pool = self.coord_pool[keep]
+            self.global_coord_pool = self.global_coord_pool[keep]
+            self.sdf_label_pool = self.sdf_label_pool[keep]
+            self.weight_pool = self.weight_pool[keep]
+            self.time_pool = self.time_pool[keep]
+            if self.color_pool is not None:
+                self.color_pool = self.color_pool[keep]
+            self.cur_sample_count = int(keep[-self.cur_sample_count:].sum().item())
+            self.pool_sample_count = int(keep.sum().item())
+        else:
+            self.cur_sample_count = coord.shape[0]
+            self.pool_sample_count = self.coord_pool.shape[0]
+
+        if cfg.bs_new_sample > 0:
+            fresh = self.global_coord_pool[-self.cur_sample_count:]
+            fresh_label = self.sdf_label_pool[-self.cur_sample_count:]
+            self.neural_points.set_search_neighborhood(num_nei_cells=1, search_alpha=0.0)
+            certainty = self.neural_points.query_certainty(fresh.contiguous())
+            self.neural_points.set_search_neighborhood(num_nei_cells=cfg.num_nei_cells, search_alpha=cfg.search_alpha)
+            self.new_idx = torch.where((certainty < cfg.new_certainty_thre) &
+                                       (torch.abs(fresh_label) < cfg.surface_sample_range_m * 3.0))[0]
+            self.new_idx += self.pool_sample_count - self.cur_sample_count
+            self.adaptive_iter_offset = 0
+            if cfg.adaptive_iters:
+                ratio = self.new_idx.shape[0] / max(1, self.cur_sample_count)
+                if ratio < cfg.new_sample_ratio_less:
+                    self.adaptive_iter_offset = -5
+                elif ratio > cfg.new_sample_ratio_more:
+                    self.adaptive_iter_offset = 5
+                    if frame_id > cfg.freeze_after_frame and ratio > cfg.new_sample_ratio_restart:
+                        self.adaptive_iter_offset = 10
+
+    # ------------------------------------------------------------------ batches
+    def get_batch(self, global_coord=False, bs=None):
+        """Same torch.randint calls as the reference (mapper.py:452-503) so the RNG stream is shared."""
+        cfg = self.config
+        bs = cfg.bs if bs is None else bs
+        lose = getattr(self.dataset, "lose_track", False) or getattr(self.dataset, "stop_status", False)
+        if cfg.bs_new_sample > 0 and self.new_idx is not None and not lose and self.new_idx.shape[0] > 0:
+            n_new = min(self.new_idx.shape[0], cfg.bs_new_sample)
+            hist = torch.randint(0, self.pool_sample_count, (bs - n_new,), device=self.device)
+            pick = torch.randint(0, self.new_idx.shape[0], (n_new,), device=self.device)
+            index = torch.cat((hist, self.new_idx[pick]), dim=0)
+        else:
+            index = torch.randint(0, self.pool_sample_count, (bs,), device=self.device)
+        coord = (self.global_coord_pool if global_coord else self.coord_pool)[index, :]
+        color = self.color_pool[index] if self.color_pool is not None else None
+        return coord, self.sdf_label_pool[index], self.time_pool[index], None, None, color, self.weight_pool[index]
+
+    # ------------------------------------------------------------------ queries
+    def sdf(self, x, get_std=False, min_nn_count=1, accumulate_stability=False):
+        o = self.neural_points.query_sdf(x.contiguous(), self.sdf_mlp, need_grad=False,
+                                         training_mode=accumulate_stability)
+        return o["sdf"], (o["sdf_std"] if (get_std and not self.config.weighted_first) else None), \
+            o["nn_count"] >= min_nn_count
+
+    def sdf_batch(self, x, bs, get_std=False, min_nn_count=1, accumulate_stability=False):
+        return self.sdf(x, get_std, min_nn_count, accumulate_stability)  # one launch covers any batch size
+
+    def get_numerical_gradient(self, x, sdf_x=None, eps=0.02, two_side=True):
+        e = torch.eye(3, device=x.device, dtype=x.dtype) * eps
+        n = x.shape[0]
+        if two_side:
+            s = self.sdf(torch.cat([x + e[0], x - e[0], x + e[1], x - e[1], x + e[2], x - e[2]], 0))[0]
+            return torch.stack([(s[0:n] - s[n:2 * n]), (s[2 * n:3 * n] - s[3 * n:4 * n]),
+                                (s[4 * n:5 * n] - s[5 * n:])], 1) / (2 * eps)
+        s = self.sdf(torch.cat([x + e[0], x + e[1], x + e[2]], 0))[0]
+        return torch.stack([s[0:n] - sdf_x, s[n:2 * n] - sdf_x, s[2 * n:] - sdf_x], 1) / eps
+
+    # ------------------------------------------------------------------ training
+    def _decoder_trainable(self):
+        return any(p.requires_grad for p in self.sdf_mlp.parameters())
+
+    def mapping(self, iter_count):
+        """Reference: utils/mapper.py:600-844."""
+        cfg = self.config
+        if cfg.color_on and cfg.weight_i > 0:
+            raise NotImplementedError("colour-head training is not implemented in the B200 path yet")
+        if not (cfg.main_loss_type == "bce" and cfg.numerical_grad and cfg.opt_adam):
+            raise NotImplementedError("B200 mapper supports the reference defaults: bce loss, numerical Eikonal, Adam")
+        iter_count = max(1, iter_count + self.adaptive_iter_offset)
+        npm = self.neural_points
+        feat = npm.local_geo_features.data
+        dev = feat.device
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        world = torch.distributed.get_world_size() if dist_on else 1
+        train_dec = self._decoder_trainable()
+        flat = self.sdf_mlp.flat_parameters()  # decoder weights live in (and are views of) this vector
+        n_dec = flat.numel()
+        m_rows = npm.local_count()
+        # one contiguous reduction buffer: [feature grads | decoder grads | certainty increments]
+        red = torch.zeros(feat.numel() + n_dec + m_rows, device=dev, dtype=torch.float32)
+        gfeat = red[: feat.numel()].view_as(feat)
+        gdec = red[feat.numel(): feat.numel() + n_dec]
+        dcert = red[feat.numel() + n_dec:]
+        mf, vf = torch.zeros_like(feat), torch.zeros_like(feat)
+        md, vd = torch.zeros_like(flat), torch.zeros_like(flat)
+        losses = torch.zeros(2, device=dev)
+        dec_step = cfg.gradient_decimation
+        eik_on = cfg.ekional_loss_on and cfg.weight_e > 0
+        eps_num = cfg.voxel_size_m * cfg.num_grad_step_ratio
+        shifts = torch.zeros(6, 1, 3, device=dev)
+        for a in range(3):
+            shifts[2 * a, 0, a] = eps_num
+            shifts[2 * a + 1, 0, a] = -eps_num
+        out = self._work
+        for it in range(iter_count):
+            coord, label, ts, _, _, _, weight = self.get_batch(global_coord=not self.ba_done_flag)
+            if self.ba_done_flag:
+                tf = self.used_poses[ts.long()].to(coord)
+                coord = (tf[:, :3, :3] @ coord.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+            n = coord.shape[0]
+            if eik_on:
+                sub = coord[::dec_step]
+                ne = sub.shape[0]
+                rows = torch.cat((coord, (sub.unsqueeze(0) + shifts).reshape(-1, 3)), 0)
+            else:
+                ne = 0
+                rows = coord.contiguous()
+            if dist_on:
+                cert_before = npm.local_point_certainties.clone()
+            o = ops.query_sdf(npm.map_handle(True), self.sdf_mlp.handle(), rows, nn_k=cfg.query_nn_k,
+                              weighted_first=cfg.weighted_first, training_mode=True, training_rows=n, need_grad=False,
+                              query_ts=ts.contiguous(), save_knn=True, out=out)
+            dl = out.get("dl")
+            if dl is None or dl.shape[0] != rows.shape[0]:
+                dl = out["dl"] = torch.empty(rows.shape[0], device=dev)
+            ops.mapping_loss(o["sdf"], label.contiguous(), weight.contiguous(), n, ne, self.sdf_scale,
+                             cfg.loss_weight_on, cfg.weight_e if eik_on else 0.0, eps_num, dl, losses,
+                             grad_scale=1.0 / world)
+            ops.train_backward(npm.map_handle(True), self.sdf_mlp.handle(), feat, rows, o["knn_idx"], o["knn_weight"],
+                               dl, cfg.weighted_first, gfeat, gdec)
+            if dist_on:
+                torch.sub(npm.local_point_certainties, cert_before, out=dcert)
+                torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.SUM)
+                torch.add(cert_before, dcert, out=npm.local_point_certainties)
+                torch.distributed.all_reduce(npm.local_point_ts_update, op=torch.distributed.ReduceOp.MAX)
+            if train_dec:
+                ops.adam_step(flat, gdec, md, vd, cfg.lr, 0.9, 0.99, cfg.adam_eps, 0.0, it + 1)
+            else:
+                gdec.zero_()
+            ops.adam_step(feat, gfeat, mf, vf, cfg.lr, 0.9, 0.99, cfg.adam_eps, cfg.weight_decay, it + 1)
+            self.total_iter += 1
+        self.last_losses = losses
+        npm.assign_local_to_global()
+
+    def bundle_adjustment(self, iter_count, window_size: int = 50, use_lie_group: bool = False):
+        raise NotImplementedError("local bundle adjustment (pypose) is outside the B200 hot path (SURVEY.md section 2 #4)")
