@@ -32,7 +32,7 @@ extern "C" {
 
 #define PINB200_VERSION 100 /* round 1 */
 #define PINB200_MAX_HIDDEN_LAYERS 4
-#define PINB200_MAX_K 16
+#define PINB200_MAX_K 8 /* neighbours kept in registers by the fused search; the reference uses 6 (default) / 8 */
 
 #define PINB200_OK 0
 #define PINB200_ERR_BAD_ARG (-1)

@@ -90,6 +90,16 @@ class OracleMap:
             kw[k] = v.clone() if torch.is_tensor(v) else v
         return OracleMap(**kw)
 
+    def double(self):
+        """fp64 copy: the reference honours config.dtype everywhere on the path, so the same algorithm in
+        fp64 is the ground truth that separates a kernel's error from the fp32 reference's own rounding
+        (SURVEY.md section 8c)."""
+        kw = {}
+        for k, v in self.__dict__.items():
+            kw[k] = v.double() if (torch.is_tensor(v) and v.dtype == torch.float32) else (
+                v.clone() if torch.is_tensor(v) else v)
+        return OracleMap(**kw)
+
 
 def probe_offsets(num_nei_cells: int, search_alpha: float, device="cpu") -> torch.Tensor:
     """Integer cell offsets inside the sphere |dx|^2 < (n+alpha)^2.
@@ -393,6 +403,11 @@ class DecoderParams:
             self.leaky,
         )
 
+    def double(self):
+        return DecoderParams([(w.detach().double(), b.detach().double()) for w, b in self.hidden],
+                             (self.out[0].detach().double(), self.out[1].detach().double()), self.sdf_scale,
+                             self.leaky)
+
     def to(self, device):
         return DecoderParams(
             [(w.to(device), b.to(device)) for w, b in self.hidden],
@@ -481,7 +496,7 @@ def query_sdf(
         query_color_feature=color_dec is not None,
     )
     sdf = decoder_sdf(dec, geo)
-    sdf_std = torch.zeros(coord.shape[0], device=coord.device)
+    sdf_std = torch.zeros(coord.shape[0], device=coord.device, dtype=coord.dtype)
     if not weighted_first:
         mean = torch.sum(sdf * w, dim=1)  # [N,1]
         var = torch.sum(w * (sdf - mean.unsqueeze(-1)) ** 2, dim=1)
@@ -502,7 +517,7 @@ def query_sdf(
             c = torch.sum(c * w, dim=1)
         out["color"] = c.detach()
         if color_grad:
-            cg = torch.zeros(coord.shape[0], c.shape[1], 3, device=coord.device)
+            cg = torch.zeros(coord.shape[0], c.shape[1], 3, device=coord.device, dtype=coord.dtype)
             for i in range(c.shape[1]):
                 cg[:, i, :] = get_gradient(coord, c[:, i]).detach()
             out["color_grad"] = cg

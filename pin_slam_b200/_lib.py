@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpinb200.so")
 
 MAX_HIDDEN = 4
-MAX_K = 16
+MAX_K = 8
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p

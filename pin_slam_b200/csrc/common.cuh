@@ -187,4 +187,139 @@ __device__ __forceinline__ float idw_weight(float d2, bool valid, int nn_count, 
   return w;
 }
 
+// ---------------------------------------------------------------------------
+// Thread-per-query search: the K (<= KREG) nearest candidates live in registers
+// as a sorted list; the C probes are issued in batches of PROBE_BATCH independent
+// loads per dependency level (table -> point/ts/g2l -> travel distance) so that one
+// thread keeps ~8 loads in flight and a 128-thread CTA ~1000.
+// ---------------------------------------------------------------------------
+constexpr int KREG = 8;
+constexpr int PROBE_BATCH = 8;
+
+struct KnnRegs {
+  float d2[KREG];
+  int idx[KREG];
+  int gidx[KREG];
+};
+
+__device__ __forceinline__ void knn_regs_init(KnnRegs& L) {
+#pragma unroll
+  for (int i = 0; i < KREG; ++i) {
+    L.d2[i] = INVALID_D2;
+    L.idx[i] = -1;
+    L.gidx[i] = -1;
+  }
+}
+
+// stable insertion (after equal distances => earlier probe first, like the warp version)
+__device__ __forceinline__ void knn_regs_insert(KnnRegs& L, float d2, int li, int gi) {
+  int pos = 0;
+#pragma unroll
+  for (int i = 0; i < KREG; ++i) pos += (L.d2[i] <= d2) ? 1 : 0;
+#pragma unroll
+  for (int i = KREG - 1; i >= 0; --i) {
+    if (i > pos) {
+      if (i > 0) {
+        L.d2[i] = L.d2[i - 1];
+        L.idx[i] = L.idx[i - 1];
+        L.gidx[i] = L.gidx[i - 1];
+      }
+    } else if (i == pos) {
+      L.d2[i] = d2;
+      L.idx[i] = li;
+      L.gidx[i] = gi;
+    }
+  }
+}
+
+__device__ __forceinline__ int knn_search_thread(const pinb200_map_view& m, const uint32_t* s_delta, float qx, float qy,
+                                                 float qz, KnnRegs& L) {
+  knn_regs_init(L);
+  int count = 0;
+  const uint32_t r0 = base_slot(m, qx, qy, qz);
+  const bool tf = m.time_filter != 0;
+  const float td_cur = tf ? __ldg(m.travel_dist + m.cur_ts) : 0.f;
+  const uint32_t B = (uint32_t)m.buffer_size;
+  const int C = m.n_probe;
+  for (int c0 = 0; c0 < C; c0 += PROBE_BATCH) {
+    int gi[PROBE_BATCH];
+#pragma unroll
+    for (int j = 0; j < PROBE_BATCH; ++j) {
+      gi[j] = -1;
+      if (c0 + j < C) {
+        uint32_t slot = r0 + s_delta[c0 + j];
+        if (slot >= B) slot -= B;
+        gi[j] = __ldg(m.slot_table + slot);
+      }
+    }
+    float px[PROBE_BATCH], py[PROBE_BATCH], pz[PROBE_BATCH];
+    int ts[PROBE_BATCH], li[PROBE_BATCH];
+#pragma unroll
+    for (int j = 0; j < PROBE_BATCH; ++j) {
+      px[j] = py[j] = pz[j] = 0.f;
+      ts[j] = 0;
+      li[j] = -1;
+      if (gi[j] >= 0) {
+        const float* pp = m.points + 3 * (size_t)gi[j];
+        px[j] = __ldg(pp);
+        py[j] = __ldg(pp + 1);
+        pz[j] = __ldg(pp + 2);
+        if (tf) ts[j] = __ldg(m.ts_create + gi[j]);
+        li[j] = m.global2local ? __ldg(m.global2local + gi[j]) : gi[j];
+      }
+    }
+    float td[PROBE_BATCH];
+#pragma unroll
+    for (int j = 0; j < PROBE_BATCH; ++j) td[j] = (tf && gi[j] >= 0) ? __ldg(m.travel_dist + ts[j]) : td_cur;
+#pragma unroll
+    for (int j = 0; j < PROBE_BATCH; ++j) {
+      if (gi[j] < 0) continue;
+      const bool young = !tf || (fabsf(td_cur - td[j]) < m.diff_travel_dist_local);
+      const float dx = __fsub_rn(px[j], qx), dy = __fsub_rn(py[j], qy), dz = __fsub_rn(pz[j], qz);
+      const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (young && !(dd > m.max_valid_dist2) && li[j] >= 0) {
+        ++count;
+        if (dd < L.d2[KREG - 1]) knn_regs_insert(L, dd, li[j], gi[j]);
+      }
+    }
+  }
+  return count;
+}
+
+// Sum K (<= 8) per-lane values over the 32 lanes with 9 shuffles (vs 5 per value):
+// after the call, lane l holds the warp total of value k = 4*bit4(l) + 2*bit3(l) + bit2(l).
+__device__ __forceinline__ float warp_reduce8(float (&p)[8], int lane) {
+  float a[4];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? p[i] : p[4 + i];
+      const float keep = hi ? p[4 + i] : p[i];
+      a[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+  }
+  float b[2];
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? a[i] : a[2 + i];
+      const float keep = hi ? a[2 + i] : a[i];
+      b[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+  }
+  float c;
+  {
+    const bool hi = (lane & 4) != 0;
+    const float send = hi ? b[0] : b[1];
+    const float keep = hi ? b[1] : b[0];
+    c = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  c += __shfl_xor_sync(FULL, c, 2);
+  c += __shfl_xor_sync(FULL, c, 1);
+  return c;
+}
+__device__ __forceinline__ int warp_reduce8_owner(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
 }  // namespace pinb

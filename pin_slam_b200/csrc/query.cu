@@ -23,7 +23,7 @@ namespace pinb {
 
 struct QueryLayout {  // float offsets into dynamic smem
   DecSmem dec;
-  int delta, act, knn_idx, knn_gidx, knn_d2, q, out, nn, mask, total;
+  int delta, act, knn_idx, knn_gidx, knn_d2, knn_w, knn_a, q, out, nn, mask, total;
 };
 
 struct QueryParams {
@@ -43,52 +43,228 @@ struct QueryParams {
 };
 
 // ---------------------------------------------------------------------------
-// phase A helpers
+// warp-per-query feature movement, G queries per iteration so that each warp keeps
+// G * ceil(K*F/32) independent 128-byte row loads in flight
 // ---------------------------------------------------------------------------
+constexpr int GQ = 4;     // queries gathered concurrently by one warp
+constexpr int RB = 8;     // row-loads per query issued back to back
 
-// IDW-average the K neighbour feature rows into act[0..F) of `row` (weighted_first).
-__device__ __forceinline__ void gather_weighted(const float* __restrict__ feat, int F, int K, int my_idx, float my_w,
-                                                int lane, float* s_act, int row) {
+// element e = r*32 + lane of query's [K x F] neighbour-feature block -> (k, j)
+__device__ __forceinline__ void elem_kj(int r, int lane, int F, int& k, int& j) {
+  const int e = r * 32 + lane;
+  k = e / F;
+  j = e - k * F;
+}
+
+// weighted_first: act[j][row] = sum_k w_k f_k[j]  for the GQ queries ql0 + 4*g (g < GQ)
+__device__ __forceinline__ void gather_weighted_group(const float* __restrict__ feat, int F, int K, const int* s_idx,
+                                                      const float* s_w, int lane, float* s_act, int ql0, int qpt) {
+  const int R = (K * F + 31) >> 5;
   if (F >= 32) {
-    const int nj = F >> 5;  // F is a multiple of 32 (checked on the host), <= 128
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < K; ++k) {
-      const int lk = __shfl_sync(FULL, my_idx, k);
-      const float wk = __shfl_sync(FULL, my_w, k);
-      if (lk >= 0) {
-        const float* fr = feat + (size_t)lk * F + lane;
+    const int nj = F >> 5;
+    float acc[GQ][4];
+#pragma unroll
+    for (int g = 0; g < GQ; ++g)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[g][jj] = 0.f;
+    for (int r0 = 0; r0 < R; r0 += RB) {
+      float v[GQ][RB], w[GQ][RB];
+#pragma unroll
+      for (int g = 0; g < GQ; ++g) {
+        const int ql = ql0 + 4 * g;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u;
+          v[g][u] = 0.f;
+          w[g][u] = 0.f;
+          if (r < R && ql < qpt) {
+            const int k = r / nj, jj = r - k * nj;
+            const int lk = s_idx[ql * K + k];
+            w[g][u] = s_w[ql * K + k];
+            v[g][u] = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + 32 * jj + lane);
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GQ; ++g)
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u;
+          const int jj = r % nj;  // nj in {1,2,3,4}
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t == jj) acc[g][t] = fmaf(w[g][u], v[g][u], acc[g][t]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < GQ; ++g) {
+      const int ql = ql0 + 4 * g;
+      if (ql < qpt)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-          if (jj < nj) acc[jj] = fmaf(wk, __ldg(fr + 32 * jj), acc[jj]);
+          if (jj < nj) s_act[(32 * jj + lane) * ACT_LD + ql] = acc[g][jj];
+    }
+  } else {
+    float acc[GQ];
+#pragma unroll
+    for (int g = 0; g < GQ; ++g) acc[g] = 0.f;
+    for (int r0 = 0; r0 < R; r0 += RB) {
+      float v[GQ][RB], w[GQ][RB];
+#pragma unroll
+      for (int g = 0; g < GQ; ++g) {
+        const int ql = ql0 + 4 * g;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u;
+          int k, j;
+          elem_kj(r, lane, F, k, j);
+          v[g][u] = 0.f;
+          w[g][u] = 0.f;
+          if (r < R && k < K && ql < qpt) {
+            const int lk = s_idx[ql * K + k];
+            w[g][u] = s_w[ql * K + k];
+            v[g][u] = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + j);
+          }
+        }
       }
+#pragma unroll
+      for (int g = 0; g < GQ; ++g)
+#pragma unroll
+        for (int u = 0; u < RB; ++u) acc[g] = fmaf(w[g][u], v[g][u], acc[g]);
     }
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (jj < nj) s_act[(32 * jj + lane) * ACT_LD + row] = acc[jj];
-  } else {
-    // F in {4,8,16}: 32/F neighbours per warp load
-    const int g = 32 / F, ksub = lane / F, j = lane - ksub * F;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < K; k0 += g) {
-      const int k = k0 + ksub;
-      const int lk = __shfl_sync(FULL, my_idx, k < K ? k : 0);
-      const float wk = __shfl_sync(FULL, my_w, k < K ? k : 0);
-      if (k < K && lk >= 0) acc = fmaf(wk, __ldg(feat + (size_t)lk * F + j), acc);
+    for (int g = 0; g < GQ; ++g) {
+      float a = acc[g];
+      for (int off = F; off < 32; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
+      const int ql = ql0 + 4 * g;
+      if (lane < F && ql < qpt) s_act[lane * ACT_LD + ql] = a;
     }
-    for (int off = F; off < 32; off <<= 1) acc += __shfl_xor_sync(FULL, acc, off);
-    if (lane < F) s_act[lane * ACT_LD + row] = acc;
   }
 }
 
-// Copy the K neighbour feature rows into act[0..F) of rows row0..row0+K (decode every neighbour).
-__device__ __forceinline__ void gather_rows(const float* __restrict__ feat, int F, int K, int my_idx, int lane,
-                                            float* s_act, int row0) {
-  const int items = K * F;
-  for (int it0 = 0; it0 < items; it0 += 32) {
-    const int it = it0 + lane;
-    const int k = it / F, j = it - k * F;
-    const int lk = __shfl_sync(FULL, my_idx, k < K ? k : 0);
-    if (it < items) s_act[j * ACT_LD + row0 + k] = lk >= 0 ? __ldg(feat + (size_t)lk * F + j) : 0.f;
+// decode-every-neighbour: act[j][ql*K + k] = f_k[j] (0 if invalid)
+__device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat, int F, int K, const int* s_idx,
+                                                  int lane, float* s_act, int ql0, int qpt, int sq0) {
+  const int R = (K * F + 31) >> 5;
+  for (int r0 = 0; r0 < R; r0 += RB) {
+    float v[GQ][RB];
+#pragma unroll
+    for (int g = 0; g < GQ; ++g) {
+      const int ql = ql0 + 4 * g;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        int k, j;
+        elem_kj(r0 + u, lane, F, k, j);
+        v[g][u] = 0.f;
+        if (r0 + u < R && k < K && ql < qpt) {
+          const int lk = s_idx[(sq0 + ql) * K + k];
+          const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + j);
+          v[g][u] = lk < 0 ? 0.f : x;
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < GQ; ++g) {
+      const int ql = ql0 + 4 * g;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        int k, j;
+        elem_kj(r0 + u, lane, F, k, j);
+        if (r0 + u < R && k < K && ql < qpt) s_act[j * ACT_LD + ql * K + k] = v[g][u];
+      }
+    }
+  }
+}
+
+// a_k = <g_xbar[0..F), f_k> for the GQ queries ql0 + 4*g  ->  s_a[ql*K + k]
+__device__ __forceinline__ void feature_dots_group(const float* __restrict__ feat, int F, int K, const int* s_idx,
+                                                   int lane, const float* s_act, float* s_a, int ql0, int qpt) {
+  const int R = (K * F + 31) >> 5;
+  if (F >= 32) {
+    const int nj = F >> 5;
+    float part[GQ][8];
+#pragma unroll
+    for (int g = 0; g < GQ; ++g)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part[g][k] = 0.f;
+    float gx[GQ][4];
+#pragma unroll
+    for (int g = 0; g < GQ; ++g)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int ql = ql0 + 4 * g;
+        gx[g][jj] = (jj < nj && ql < qpt) ? s_act[(32 * jj + lane) * ACT_LD + ql] : 0.f;
+      }
+    for (int r0 = 0; r0 < R; r0 += RB) {
+      float v[GQ][RB];
+#pragma unroll
+      for (int g = 0; g < GQ; ++g) {
+        const int ql = ql0 + 4 * g;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u;
+          v[g][u] = 0.f;
+          if (r < R && ql < qpt) {
+            const int k = r / nj, jj = r - k * nj;
+            const int lk = s_idx[ql * K + k];
+            const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + 32 * jj + lane);
+            v[g][u] = lk < 0 ? 0.f : x;
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GQ; ++g)
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u;
+          const int k = r / nj, jj = r - k * nj;
+          float gxv = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t == jj) gxv = gx[g][t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t == k) part[g][t] = fmaf(gxv, v[g][u], part[g][t]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < GQ; ++g) {
+      const float tot = warp_reduce8(part[g], lane);
+      const int ql = ql0 + 4 * g;
+      const int k = warp_reduce8_owner(lane);
+      if ((lane & 3) == 0 && k < K && ql < qpt) s_a[ql * K + k] = tot;
+    }
+  } else {
+    for (int r0 = 0; r0 < R; r0 += RB) {
+      float v[GQ][RB];
+#pragma unroll
+      for (int g = 0; g < GQ; ++g) {
+        const int ql = ql0 + 4 * g;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          int k, j;
+          elem_kj(r0 + u, lane, F, k, j);
+          v[g][u] = 0.f;
+          if (r0 + u < R && k < K && ql < qpt) {
+            const int lk = s_idx[ql * K + k];
+            const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + j);
+            v[g][u] = lk < 0 ? 0.f : x * s_act[j * ACT_LD + ql];
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GQ; ++g) {
+        const int ql = ql0 + 4 * g;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          float a = v[g][u];
+          for (int off = 1; off < F; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
+          int k, j;
+          elem_kj(r0 + u, lane, F, k, j);
+          if (r0 + u < R && j == 0 && k < K && ql < qpt) s_a[ql * K + k] = a;
+        }
+      }
+    }
   }
 }
 
@@ -96,7 +272,7 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ feat, int 
 // the fused kernel
 // ---------------------------------------------------------------------------
 template <int H, int DP>
-__global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ QueryParams p) {
+__global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ QueryParams p) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pinb200_map_view& m = p.map;
@@ -112,6 +288,8 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
   int* s_idx = reinterpret_cast<int*>(smem + p.lay.knn_idx);
   int* s_gidx = reinterpret_cast<int*>(smem + p.lay.knn_gidx);
   float* s_d2 = smem + p.lay.knn_d2;
+  float* s_w = smem + p.lay.knn_w;
+  float* s_a = smem + p.lay.knn_a;
   float* s_q = smem + p.lay.q;
   float* s_out = smem + p.lay.out;
   int* s_nn = reinterpret_cast<int*>(smem + p.lay.nn);
@@ -121,250 +299,280 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
   if (!p.use_saved_knn) fill_probe_deltas(m, s_delta);
   __syncthreads();
 
-  const int QPT = p.qpt;
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const long long q0 = (long long)tile * QPT;
+  const int QPT = wf ? TILE : TILE / K;                 // queries per 128-row decoder tile
+  const int n_rt = wf ? 1 : (TILE + QPT - 1) / QPT;     // row tiles per 128-query super tile
+  for (int st = blockIdx.x; st < p.n_tiles; st += gridDim.x) {
+    const long long q0s = (long long)st * TILE;
 
-    // ===================== phase A: search + gather (warp per query) =====================
-    for (int ql = warp; ql < QPT; ql += TILE / 32) {
-      const long long qi = q0 + ql;
-      const int row0 = wf ? ql : ql * K;
-      const int nrows = wf ? 1 : K;
-      if (qi >= p.n) {  // tail padding: keep phase B finite
-        for (int e = lane; e < D * nrows; e += 32) s_act[(e / nrows) * ACT_LD + row0 + (e % nrows)] = 0.f;
-        if (lane < K) {
-          s_idx[ql * K + lane] = -1;
-          s_gidx[ql * K + lane] = -1;
-          s_d2[ql * K + lane] = INVALID_D2;
+    // ============ phase A1: thread per query -- search, IDW weights, side effects ============
+    {
+      const long long qi = q0s + tid;
+      const bool live = qi < p.n;
+      KnnRegs Lk;
+      knn_regs_init(Lk);
+      int cnt = 0;
+      float qx = 0.f, qy = 0.f, qz = 0.f;
+      if (live) {
+        qx = __ldg(p.query_xyz + 3 * qi + 0);
+        qy = __ldg(p.query_xyz + 3 * qi + 1);
+        qz = __ldg(p.query_xyz + 3 * qi + 2);
+        if (p.opts.transform) {  // q = T p in fp32 (utils/tools.py:534-553)
+          const double* T = p.opts.transform;
+          const float x = fmaf(qz, (float)T[2], fmaf(qy, (float)T[1], qx * (float)T[0])) + (float)T[3];
+          const float y = fmaf(qz, (float)T[6], fmaf(qy, (float)T[5], qx * (float)T[4])) + (float)T[7];
+          const float z = fmaf(qz, (float)T[10], fmaf(qy, (float)T[9], qx * (float)T[8])) + (float)T[11];
+          qx = x;
+          qy = y;
+          qz = z;
         }
-        if (lane == 0) s_nn[ql] = 0;
-        continue;
-      }
-      float qx = __ldg(p.query_xyz + 3 * qi + 0), qy = __ldg(p.query_xyz + 3 * qi + 1),
-            qz = __ldg(p.query_xyz + 3 * qi + 2);
-      if (p.opts.transform) {  // q = T p in fp32 (utils/tools.py:534-553)
-        const double* T = p.opts.transform;
-        const float t00 = (float)T[0], t01 = (float)T[1], t02 = (float)T[2], t03 = (float)T[3];
-        const float t10 = (float)T[4], t11 = (float)T[5], t12 = (float)T[6], t13 = (float)T[7];
-        const float t20 = (float)T[8], t21 = (float)T[9], t22 = (float)T[10], t23 = (float)T[11];
-        const float x = fmaf(qz, t02, fmaf(qy, t01, qx * t00)) + t03;
-        const float y = fmaf(qz, t12, fmaf(qy, t11, qx * t10)) + t13;
-        const float z = fmaf(qz, t22, fmaf(qy, t21, qx * t20)) + t23;
-        qx = x;
-        qy = y;
-        qz = z;
-      }
-      Knn kn;
-      if (p.use_saved_knn) {
-        kn.idx = lane < K ? __ldg(p.out.knn_idx + qi * K + lane) : -1;
-        kn.gidx = lane < K ? __ldg(p.out.knn_gidx + qi * K + lane) : -1;
-        kn.d2 = lane < K ? __ldg(p.out.knn_dist2 + qi * K + lane) : INVALID_D2;
-        kn.count = __ldg(p.out.nn_count + qi);
-      } else {
-        kn = knn_search_warp(m, s_delta, qx, qy, qz, K, lane);
-      }
-      const bool valid = kn.idx >= 0;
-      float u, inv_s;
-      const float w = idw_weight(kn.d2, valid, kn.count, K, lane, u, inv_s);
-
-      // neighbour vector n_k = q - p_k (rotated into the point frame after PGO), zero if invalid (:632-651)
-      float nx = 0.f, ny = 0.f, nz = 0.f, cert = 0.f;
-      if (valid) {
-        const float* pp = m.nb_points + 3 * (size_t)kn.idx;
-        nx = __fsub_rn(qx, __ldg(pp + 0));
-        ny = __fsub_rn(qy, __ldg(pp + 1));
-        nz = __fsub_rn(qz, __ldg(pp + 2));
-        if (m.after_pgo) {
-          const float* qq = m.nb_orient + 4 * (size_t)kn.idx;
-          quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
+        if (p.use_saved_knn) {
+#pragma unroll
+          for (int k = 0; k < KREG; ++k)
+            if (k < K) {
+              Lk.idx[k] = __ldg(p.out.knn_idx + qi * K + k);
+              Lk.gidx[k] = __ldg(p.out.knn_gidx + qi * K + k);
+              Lk.d2[k] = __ldg(p.out.knn_dist2 + qi * K + k);
+            }
+          cnt = __ldg(p.out.nn_count + qi);
+        } else {
+          cnt = knn_search_thread(m, s_delta, qx, qy, qz, Lk);
         }
-        cert = m.certainty[kn.idx];
       }
-      if (!p.is_color) {
-        // queried certainty (:713-718) uses the values gathered before this query's own scatter
-        const float qc = warp_sum(cert * w);
-        if (p.opts.training_mode && valid && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {  // (:685-710); invalid entries add 0 / max with 0 in the reference
-          atomicAdd(m.certainty + kn.idx, w);
-          if (m.ts_update && p.query_ts) atomicMax(m.ts_update + kn.idx, __ldg(p.query_ts + qi));
+      // normalised inverse-distance weights, summed in neighbour order (model/neural_points.py:665-683)
+      float u[KREG], w[KREG], usum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KREG; ++k) {
+        const bool v = k < K && Lk.idx[k] >= 0;
+        u[k] = k < K ? (cnt == 0 ? IDW_EPS : (v ? __fdiv_rn(1.0f, Lk.d2[k] + IDW_EPS) : 0.f)) : 0.f;
+        usum += u[k];
+      }
+#pragma unroll
+      for (int k = 0; k < KREG; ++k) w[k] = (k < K && Lk.idx[k] >= 0) ? __fdiv_rn(u[k], usum) : 0.f;
+#pragma unroll
+      for (int k = 0; k < KREG; ++k)
+        if (k < K) {
+          s_idx[tid * K + k] = Lk.idx[k];
+          s_gidx[tid * K + k] = Lk.gidx[k];
+          s_d2[tid * K + k] = Lk.d2[k];
+          s_w[tid * K + k] = w[k];
         }
-        if (lane == 0) {
-          if (p.out.certainty) p.out.certainty[qi] = qc;
-          if (p.out.nn_count && !p.use_saved_knn) p.out.nn_count[qi] = kn.count;
-          if (p.out.xyz) {
-            p.out.xyz[3 * qi + 0] = qx;
-            p.out.xyz[3 * qi + 1] = qy;
-            p.out.xyz[3 * qi + 2] = qz;
+      s_nn[tid] = cnt;
+      s_q[3 * tid + 0] = qx;
+      s_q[3 * tid + 1] = qy;
+      s_q[3 * tid + 2] = qz;
+      // neighbour vectors n_k = q - p_k (rotated into the point frame after PGO), certainty (:631-651)
+      float sx = 0.f, sy = 0.f, sz = 0.f, qc = 0.f;
+      {
+        float px[KREG], py[KREG], pz[KREG], ce[KREG];
+#pragma unroll
+        for (int k = 0; k < KREG; ++k) {
+          px[k] = py[k] = pz[k] = ce[k] = 0.f;
+          if (k < K && Lk.idx[k] >= 0) {
+            const float* pp = m.nb_points + 3 * (size_t)Lk.idx[k];
+            px[k] = __ldg(pp);
+            py[k] = __ldg(pp + 1);
+            pz[k] = __ldg(pp + 2);
+            if (!p.is_color) ce[k] = m.certainty[Lk.idx[k]];
           }
         }
-        if (lane < K && !p.use_saved_knn) {
-          if (p.out.knn_idx) p.out.knn_idx[qi * K + lane] = kn.idx;
-          if (p.out.knn_gidx) p.out.knn_gidx[qi * K + lane] = kn.gidx;
-          if (p.out.knn_dist2) p.out.knn_dist2[qi * K + lane] = kn.d2;
-          if (p.out.knn_weight) p.out.knn_weight[qi * K + lane] = w;
+#pragma unroll
+        for (int k = 0; k < KREG; ++k) {
+          if (k < K && Lk.idx[k] >= 0) {
+            float nx = __fsub_rn(qx, px[k]), ny = __fsub_rn(qy, py[k]), nz = __fsub_rn(qz, pz[k]);
+            if (m.after_pgo) {
+              const float* qq = m.nb_orient + 4 * (size_t)Lk.idx[k];
+              quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
+            }
+            sx = fmaf(w[k], nx, sx);
+            sy = fmaf(w[k], ny, sy);
+            sz = fmaf(w[k], nz, sz);
+            qc = fmaf(w[k], ce[k], qc);
+          }
         }
       }
-      if (lane < K) {
-        s_idx[ql * K + lane] = kn.idx;
-        s_gidx[ql * K + lane] = kn.gidx;
-        s_d2[ql * K + lane] = kn.d2;
+      if (wf) {  // the position part of the IDW-averaged decoder input; the tile row is this thread's column
+        s_act[(F + 0) * ACT_LD + tid] = sx;
+        s_act[(F + 1) * ACT_LD + tid] = sy;
+        s_act[(F + 2) * ACT_LD + tid] = sz;
       }
-      if (lane == 0) {
-        s_nn[ql] = kn.count;
-        s_q[3 * ql + 0] = qx;
-        s_q[3 * ql + 1] = qy;
-        s_q[3 * ql + 2] = qz;
-      }
-      if (wf) {
-        gather_weighted(feat, F, K, kn.idx, w, lane, s_act, row0);
-        const float sx = warp_sum(w * nx), sy = warp_sum(w * ny), sz = warp_sum(w * nz);
-        if (lane == 0) {
-          s_act[(F + 0) * ACT_LD + row0] = sx;
-          s_act[(F + 1) * ACT_LD + row0] = sy;
-          s_act[(F + 2) * ACT_LD + row0] = sz;
+      if (live && !p.is_color) {
+        if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
+          // certainty scatter_add / ts amax (:685-710); invalid entries add 0 / max with 0 in the reference
+          const int ts = (m.ts_update && p.query_ts) ? __ldg(p.query_ts + qi) : 0;
+#pragma unroll
+          for (int k = 0; k < KREG; ++k)
+            if (k < K && Lk.idx[k] >= 0) {
+              atomicAdd(m.certainty + Lk.idx[k], w[k]);
+              if (m.ts_update && p.query_ts) atomicMax(m.ts_update + Lk.idx[k], ts);
+            }
         }
-      } else {
-        gather_rows(feat, F, K, kn.idx, lane, s_act, row0);
-        if (lane < K) {
-          s_act[(F + 0) * ACT_LD + row0 + lane] = nx;
-          s_act[(F + 1) * ACT_LD + row0 + lane] = ny;
-          s_act[(F + 2) * ACT_LD + row0 + lane] = nz;
+        if (p.out.certainty) p.out.certainty[qi] = qc;
+        if (!p.use_saved_knn) {
+          if (p.out.nn_count) p.out.nn_count[qi] = cnt;
+#pragma unroll
+          for (int k = 0; k < KREG; ++k)
+            if (k < K) {
+              if (p.out.knn_idx) p.out.knn_idx[qi * K + k] = Lk.idx[k];
+              if (p.out.knn_gidx) p.out.knn_gidx[qi * K + k] = Lk.gidx[k];
+              if (p.out.knn_dist2) p.out.knn_dist2[qi * K + k] = Lk.d2[k];
+              if (p.out.knn_weight) p.out.knn_weight[qi * K + k] = w[k];
+            }
+        }
+        if (p.out.xyz) {
+          p.out.xyz[3 * qi + 0] = qx;
+          p.out.xyz[3 * qi + 1] = qy;
+          p.out.xyz[3 * qi + 2] = qz;
         }
       }
     }
     __syncthreads();
 
-    // ===================== phase B: decoder forward (thread per row) =====================
-    float* col = s_act + tid;
-    float h[H];
-    {
-      int n_in = D;
-      for (int l = 0; l < L; ++l) {
-        matvec_col<H>(smem + p.lay.dec.wt[l], smem + p.lay.dec.b[l], col, n_in, h);
-        s_mask[l * TILE + tid] = activate<H>(h, leaky);
-        if (l < L - 1) store_col<H>(col, h, H);
-        n_in = H;
-      }
-    }
-    float dval[4];  // d value / d pre-activation output, per channel (OC <= 4)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c < OC) {
-        const float* wo = smem + p.lay.dec.wout + c * H;
-        float o = smem[p.lay.dec.bout + c];
-#pragma unroll
-        for (int j = 0; j < H; ++j) o = fmaf(wo[j], h[j], o);
-        float v;
-        if (p.dec.sigmoid_out) {
-          v = 1.f / (1.f + expf(-o));
-          dval[c] = v * (1.f - v);
-        } else {
-          v = o * p.dec.out_scale;
-          dval[c] = p.dec.out_scale;
-        }
-        s_out[tid * OC + c] = v;
-      }
-    }
+    for (int rt = 0; rt < n_rt; ++rt) {
+      const int sq0 = rt * QPT;                              // first query of this row tile inside the super tile
+      const int qpt = min(QPT, TILE - sq0);                  // queries in this row tile
+      const int used_rows = wf ? TILE : qpt * K;
 
-    // ============ per output channel: backward to the decoder input, then phase C ============
-    const int n_pass = need_grad ? OC : 1;
-    for (int c = 0; c < n_pass; ++c) {
-      if (need_grad) {
-        float g[H];
-        {
-          const float* wo = smem + p.lay.dec.wout + c * H;
-#pragma unroll
-          for (int j = 0; j < H; ++j) g[j] = wo[j];
-          apply_mask<H>(g, s_mask[(L - 1) * TILE + tid], leaky);
+      // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
+      if (wf) {
+        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_weighted_group(feat, F, K, s_idx, s_w, lane, s_act, ql0, qpt);
+      } else {
+        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_rows_group(feat, F, K, s_idx, lane, s_act, ql0, qpt, sq0);
+        // neighbour vectors of the (query, k) rows: thread per row
+        if (tid < used_rows) {
+          const int ql = tid / K, k = tid - ql * K, sq = sq0 + ql;
+          const int lk = s_idx[sq * K + k];
+          float nx = 0.f, ny = 0.f, nz = 0.f;
+          if (lk >= 0) {
+            const float* pp = m.nb_points + 3 * (size_t)lk;
+            nx = __fsub_rn(s_q[3 * sq + 0], __ldg(pp));
+            ny = __fsub_rn(s_q[3 * sq + 1], __ldg(pp + 1));
+            nz = __fsub_rn(s_q[3 * sq + 2], __ldg(pp + 2));
+            if (m.after_pgo) {
+              const float* qq = m.nb_orient + 4 * (size_t)lk;
+              quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
+            }
+          }
+          s_act[(F + 0) * ACT_LD + tid] = nx;
+          s_act[(F + 1) * ACT_LD + tid] = ny;
+          s_act[(F + 2) * ACT_LD + tid] = nz;
+        } else {
+          for (int d = 0; d < D; ++d) s_act[d * ACT_LD + tid] = 0.f;  // unused rows stay finite
         }
-        for (int l = L - 1; l >= 1; --l) {
-          store_col<H>(col, g, H);
-          matvec_col<H>(smem + p.lay.dec.w[l], nullptr, col, H, g);
-          apply_mask<H>(g, s_mask[(l - 1) * TILE + tid], leaky);
-        }
-        store_col<H>(col, g, H);
-        float gx[DP];
-        matvec_col<DP>(smem + p.lay.dec.w[0], nullptr, col, H, gx);
-        const float dv = c == 0 ? dval[0] : (c == 1 ? dval[1] : (c == 2 ? dval[2] : dval[3]));
-#pragma unroll
-        for (int d = 0; d < DP; ++d)
-          if (d < D) col[d * ACT_LD] = gx[d] * dv;
       }
       __syncthreads();
 
-      // ===================== phase C: chain rule through IDW + outputs =====================
-      if (wf) {
-        for (int ql = warp; ql < QPT; ql += TILE / 32) {
-          const long long qi = q0 + ql;
-          if (qi >= p.n) continue;
-          const float val = s_out[ql * OC + c];
-          float gq0 = 0.f, gq1 = 0.f, gq2 = 0.f;
-          if (need_grad) {
-            const int nn = s_nn[ql];
-            const int lk = lane < K ? s_idx[ql * K + lane] : -1;
-            const float d2 = lane < K ? s_d2[ql * K + lane] : INVALID_D2;
-            const bool valid = lk >= 0;
-            float u, inv_s;
-            const float w = idw_weight(d2, valid, nn, K, lane, u, inv_s);
-            const float qx = s_q[3 * ql], qy = s_q[3 * ql + 1], qz = s_q[3 * ql + 2];
-            const float gn0 = s_act[(F + 0) * ACT_LD + ql], gn1 = s_act[(F + 1) * ACT_LD + ql],
-                        gn2 = s_act[(F + 2) * ACT_LD + ql];
-            float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
-            if (valid) {
-              // n_k is measured to the neighbour in the queried index space, the IDW distance to the
-              // global point the hash returned (they only differ through the reference's global2local
-              // fill value, see DESIGN.md "reference quirks")
-              const float* pp = m.nb_points + 3 * (size_t)lk;
-              nx = qx - __ldg(pp);
-              ny = qy - __ldg(pp + 1);
-              nz = qz - __ldg(pp + 2);
-              const float* pg = m.points + 3 * (size_t)s_gidx[ql * K + lane];
-              dx = qx - __ldg(pg);
-              dy = qy - __ldg(pg + 1);
-              dz = qz - __ldg(pg + 2);
-              const float ux = nx, uy = ny, uz = nz;
-              r0 = gn0;
-              r1 = gn1;
-              r2 = gn2;
-              if (m.after_pgo) {
-                const float* qq = m.nb_orient + 4 * (size_t)lk;
-                const float a = __ldg(qq), b = __ldg(qq + 1), cc = __ldg(qq + 2), dd = __ldg(qq + 3);
-                quat_rotate_passive(a, b, cc, dd, ux, uy, uz, nx, ny, nz);
-                quat_rotate_active(a, b, cc, dd, gn0, gn1, gn2, r0, r1, r2);
-              }
-            }
-            // a_k = <g_xbar, v_k>, v_k = [f_k ; n_k]
-            float a_k = 0.f;
-            {
-              float gxl[4];
+      // ============ phase B: decoder forward (thread per row) ============
+      float* col = s_act + tid;
+      float h[H];
+      {
+        int n_in = D;
+        for (int l = 0; l < L; ++l) {
+          matvec_col<H>(smem + p.lay.dec.wt[l], smem + p.lay.dec.b[l], col, n_in, h);
+          s_mask[l * TILE + tid] = activate<H>(h, leaky);
+          if (l < L - 1) store_col<H>(col, h, H);
+          n_in = H;
+        }
+      }
+      float dval[4];  // d value / d pre-activation output, per channel (OC <= 4)
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = lane + 32 * jj;
-                gxl[jj] = j < F ? s_act[j * ACT_LD + ql] : 0.f;
-              }
-              for (int k = 0; k < K; ++k) {
-                const int lkb = __shfl_sync(FULL, lk, k);
-                float part = 0.f;
-                if (lkb >= 0) {
-                  const float* fr = feat + (size_t)lkb * F;
+      for (int c = 0; c < 4; ++c) {
+        dval[c] = 0.f;
+        if (c < OC) {
+          const float* wo = smem + p.lay.dec.wout + c * H;
+          float o = smem[p.lay.dec.bout + c];
 #pragma unroll
-                  for (int jj = 0; jj < 4; ++jj) {
-                    const int j = lane + 32 * jj;
-                    if (j < F) part = fmaf(gxl[jj], __ldg(fr + j), part);
-                  }
-                }
-                part = warp_sum(part);
-                if (lane == k) a_k = part;
-              }
-              a_k += gn0 * nx + gn1 * ny + gn2 * nz;
-            }
-            const float abar = warp_sum(w * a_k);
-            // d w_k / d q = w_k (c_k - sum_j w_j c_j), c_k = -2 u_k (q - p_k)
-            const float coef = w * (a_k - abar) * (-2.f * u);
-            gq0 = warp_sum(fmaf(coef, dx, w * r0));
-            gq1 = warp_sum(fmaf(coef, dy, w * r1));
-            gq2 = warp_sum(fmaf(coef, dz, w * r2));
+          for (int j = 0; j < H; ++j) o = fmaf(wo[j], h[j], o);
+          float v;
+          if (p.dec.sigmoid_out) {
+            v = 1.f / (1.f + expf(-o));
+            dval[c] = v * (1.f - v);
+          } else {
+            v = o * p.dec.out_scale;
+            dval[c] = p.dec.out_scale;
           }
-          if (lane == 0) {
+          s_out[tid * OC + c] = v;
+        }
+      }
+
+      // ======== per output channel: backward to the decoder input, then the IDW chain rule ========
+      const int n_pass = need_grad ? OC : 1;
+      for (int c = 0; c < n_pass; ++c) {
+        if (need_grad) {
+          float g[H];
+          {
+            const float* wo = smem + p.lay.dec.wout + c * H;
+#pragma unroll
+            for (int j = 0; j < H; ++j) g[j] = wo[j];
+            apply_mask<H>(g, s_mask[(L - 1) * TILE + tid], leaky);
+          }
+          for (int l = L - 1; l >= 1; --l) {
+            store_col<H>(col, g, H);
+            matvec_col<H>(smem + p.lay.dec.w[l], nullptr, col, H, g);
+            apply_mask<H>(g, s_mask[(l - 1) * TILE + tid], leaky);
+          }
+          store_col<H>(col, g, H);
+          float gx[DP];
+          matvec_col<DP>(smem + p.lay.dec.w[0], nullptr, col, H, gx);
+          const float dv = c == 0 ? dval[0] : (c == 1 ? dval[1] : (c == 2 ? dval[2] : dval[3]));
+#pragma unroll
+          for (int d = 0; d < DP; ++d)
+            if (d < D) col[d * ACT_LD] = gx[d] * dv;
+        }
+        __syncthreads();
+
+        if (wf) {
+          // ---- C1: a_k = <g_xbar, f_k> (warp per query, coalesced re-read of the K feature rows)
+          if (need_grad) {
+            for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) feature_dots_group(feat, F, K, s_idx, lane, s_act, s_a, ql0, qpt);
+            __syncthreads();
+          }
+          // ---- C2: thread per query -- chain rule through the IDW weights, outputs
+          const long long qi = q0s + tid;
+          if (qi < p.n) {
+            const float val = s_out[tid * OC + c];
+            float gq0 = 0.f, gq1 = 0.f, gq2 = 0.f;
+            if (need_grad) {
+              const int nn = s_nn[tid];
+              const float qx = s_q[3 * tid], qy = s_q[3 * tid + 1], qz = s_q[3 * tid + 2];
+              const float gn0 = col[(F + 0) * ACT_LD], gn1 = col[(F + 1) * ACT_LD], gn2 = col[(F + 2) * ACT_LD];
+              float ak[KREG], wk[KREG], ck[KREG], dx[KREG], dy[KREG], dz[KREG];
+              float abar = 0.f;
+#pragma unroll
+              for (int k = 0; k < KREG; ++k) {
+                ak[k] = wk[k] = ck[k] = dx[k] = dy[k] = dz[k] = 0.f;
+                const int lk = k < K ? s_idx[tid * K + k] : -1;
+                if (lk >= 0) {
+                  const float* pp = m.nb_points + 3 * (size_t)lk;
+                  const float ux = qx - __ldg(pp), uy = qy - __ldg(pp + 1), uz = qz - __ldg(pp + 2);
+                  const float* pg = m.points + 3 * (size_t)s_gidx[tid * K + k];  // what dist2 was measured to
+                  dx[k] = qx - __ldg(pg);
+                  dy[k] = qy - __ldg(pg + 1);
+                  dz[k] = qz - __ldg(pg + 2);
+                  float nx = ux, ny = uy, nz = uz, r0 = gn0, r1 = gn1, r2 = gn2;
+                  if (m.after_pgo) {
+                    const float* qq = m.nb_orient + 4 * (size_t)lk;
+                    const float a = __ldg(qq), b = __ldg(qq + 1), cc = __ldg(qq + 2), dd = __ldg(qq + 3);
+                    quat_rotate_passive(a, b, cc, dd, ux, uy, uz, nx, ny, nz);
+                    quat_rotate_active(a, b, cc, dd, gn0, gn1, gn2, r0, r1, r2);
+                  }
+                  wk[k] = s_w[tid * K + k];
+                  ak[k] = s_a[tid * K + k] + gn0 * nx + gn1 * ny + gn2 * nz;
+                  abar = fmaf(wk[k], ak[k], abar);
+                  ck[k] = nn > 0 ? -2.f * __fdiv_rn(1.0f, s_d2[tid * K + k] + IDW_EPS) : 0.f;
+                  gq0 = fmaf(wk[k], r0, gq0);
+                  gq1 = fmaf(wk[k], r1, gq1);
+                  gq2 = fmaf(wk[k], r2, gq2);
+                }
+              }
+              // d w_k / d q = w_k (c_k - sum_j w_j c_j),  c_k = -2 u_k (q - p_k)
+#pragma unroll
+              for (int k = 0; k < KREG; ++k) {
+                const float coef = wk[k] * (ak[k] - abar) * ck[k];
+                gq0 = fmaf(coef, dx[k], gq0);
+                gq1 = fmaf(coef, dy[k], gq1);
+                gq2 = fmaf(coef, dz[k], gq2);
+              }
+            }
             if (!p.is_color) {
               if (p.out.sdf) p.out.sdf[qi] = val;
               if (p.out.sdf_std) p.out.sdf_std[qi] = 0.f;
@@ -374,7 +582,13 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
                 p.out.grad[3 * qi + 2] = gq2;
               }
             } else {
-              if (p.out.color) p.out.color[qi * OC + c] = val;
+              if (p.out.color) {
+                if (need_grad) {
+                  p.out.color[qi * OC + c] = val;
+                } else {
+                  for (int cc = 0; cc < OC; ++cc) p.out.color[qi * OC + cc] = s_out[tid * OC + cc];
+                }
+              }
               if (need_grad && p.out.color_grad) {
                 p.out.color_grad[(qi * OC + c) * 3 + 0] = gq0;
                 p.out.color_grad[(qi * OC + c) * 3 + 1] = gq1;
@@ -382,81 +596,63 @@ __global__ void __launch_bounds__(TILE, 4) query_kernel(const __grid_constant__ 
               }
             }
           }
-        }
-        if (!need_grad && OC > 1 && p.is_color) {  // remaining colour channels without gradients
-          for (int ql = tid; ql < QPT; ql += TILE) {
-            const long long qi = q0 + ql;
-            if (qi < p.n && p.out.color)
-              for (int cc = 1; cc < OC; ++cc) p.out.color[qi * OC + cc] = s_out[ql * OC + cc];
-          }
-        }
-      } else {
-        // decode-every-neighbour: thread per query combines its K rows (tracker.py:317-323)
-        if (tid < QPT && q0 + tid < p.n) {
-          const int ql = tid;
-          const long long qi = q0 + ql;
-          const int nn = s_nn[ql];
-          const float qx = s_q[3 * ql], qy = s_q[3 * ql + 1], qz = s_q[3 * ql + 2];
-          float usum = 0.f;
-          for (int k = 0; k < K; ++k) {
-            const bool v = s_idx[ql * K + k] >= 0;
-            usum += nn == 0 ? IDW_EPS : (v ? __fdiv_rn(1.0f, s_d2[ql * K + k] + IDW_EPS) : 0.f);
-          }
-          const int n_ch = (need_grad || !p.is_color) ? 1 : OC;
-          for (int ch = 0; ch < n_ch; ++ch) {
-            const int cc = need_grad ? c : ch;
-            float mean = 0.f;
-            for (int k = 0; k < K; ++k) {
-              const bool v = s_idx[ql * K + k] >= 0;
-              const float uk = nn == 0 ? IDW_EPS : (v ? __fdiv_rn(1.0f, s_d2[ql * K + k] + IDW_EPS) : 0.f);
-              const float wk = v ? __fdiv_rn(uk, usum) : 0.f;
-              mean = fmaf(wk, s_out[(ql * K + k) * OC + cc], mean);
-            }
-            float var = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-            for (int k = 0; k < K; ++k) {
-              const int lk = s_idx[ql * K + k];
-              if (lk < 0) continue;
-              const float uk = nn == 0 ? 0.f : __fdiv_rn(1.0f, s_d2[ql * K + k] + IDW_EPS);
-              const float wk = __fdiv_rn(nn == 0 ? IDW_EPS : uk, usum);
-              const float sk = s_out[(ql * K + k) * OC + cc];
-              const float dm = sk - mean;
-              var = fmaf(wk * dm, dm, var);
-              if (need_grad) {
-                const int row = ql * K + k;
-                float r0 = s_act[(F + 0) * ACT_LD + row], r1 = s_act[(F + 1) * ACT_LD + row],
-                      r2 = s_act[(F + 2) * ACT_LD + row];
-                const float* pp = m.points + 3 * (size_t)s_gidx[ql * K + k];  // the point dist2 was measured to
-                const float dx = qx - __ldg(pp), dy = qy - __ldg(pp + 1), dz = qz - __ldg(pp + 2);
-                if (m.after_pgo) {
-                  const float* qq = m.nb_orient + 4 * (size_t)lk;
-                  quat_rotate_active(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), r0, r1, r2, r0, r1, r2);
+        } else {
+          // decode-every-neighbour: thread per query combines its K rows (tracker.py:317-323)
+          if (tid < qpt && q0s + sq0 + tid < p.n) {
+            const int ql = tid, sq = sq0 + ql;
+            const long long qi = q0s + sq;
+            const int nn = s_nn[sq];
+            const float qx = s_q[3 * sq], qy = s_q[3 * sq + 1], qz = s_q[3 * sq + 2];
+            const int n_ch = (need_grad || !p.is_color) ? 1 : OC;
+            for (int ch = 0; ch < n_ch; ++ch) {
+              const int cc = need_grad ? c : ch;
+              float mean = 0.f;
+              for (int k = 0; k < K; ++k) mean = fmaf(s_w[sq * K + k], s_out[(ql * K + k) * OC + cc], mean);
+              float var = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+              for (int k = 0; k < K; ++k) {
+                const int lk = s_idx[sq * K + k];
+                if (lk < 0) continue;
+                const float wk = s_w[sq * K + k];
+                const float dm = s_out[(ql * K + k) * OC + cc] - mean;
+                var = fmaf(wk * dm, dm, var);
+                if (need_grad) {
+                  const int row = ql * K + k;
+                  float r0 = s_act[(F + 0) * ACT_LD + row], r1 = s_act[(F + 1) * ACT_LD + row],
+                        r2 = s_act[(F + 2) * ACT_LD + row];
+                  const float* pg = m.points + 3 * (size_t)s_gidx[sq * K + k];  // the point dist2 was measured to
+                  const float dx = qx - __ldg(pg), dy = qy - __ldg(pg + 1), dz = qz - __ldg(pg + 2);
+                  if (m.after_pgo) {
+                    const float* qq = m.nb_orient + 4 * (size_t)lk;
+                    quat_rotate_active(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), r0, r1, r2, r0, r1, r2);
+                  }
+                  const float uk = nn > 0 ? __fdiv_rn(1.0f, s_d2[sq * K + k] + IDW_EPS) : 0.f;
+                  const float coef = wk * dm * (-2.f * uk);
+                  g0 += fmaf(coef, dx, wk * r0);
+                  g1 += fmaf(coef, dy, wk * r1);
+                  g2 += fmaf(coef, dz, wk * r2);
                 }
-                const float coef = wk * dm * (-2.f * uk);
-                g0 += fmaf(coef, dx, wk * r0);
-                g1 += fmaf(coef, dy, wk * r1);
-                g2 += fmaf(coef, dz, wk * r2);
               }
-            }
-            if (!p.is_color) {
-              if (p.out.sdf) p.out.sdf[qi] = mean;
-              if (p.out.sdf_std) p.out.sdf_std[qi] = sqrtf(var);
-              if (need_grad && p.out.grad) {
-                p.out.grad[3 * qi + 0] = g0;
-                p.out.grad[3 * qi + 1] = g1;
-                p.out.grad[3 * qi + 2] = g2;
-              }
-            } else {
-              if (p.out.color) p.out.color[qi * OC + cc] = mean;
-              if (need_grad && p.out.color_grad) {
-                p.out.color_grad[(qi * OC + cc) * 3 + 0] = g0;
-                p.out.color_grad[(qi * OC + cc) * 3 + 1] = g1;
-                p.out.color_grad[(qi * OC + cc) * 3 + 2] = g2;
+              if (!p.is_color) {
+                if (p.out.sdf) p.out.sdf[qi] = mean;
+                if (p.out.sdf_std) p.out.sdf_std[qi] = sqrtf(var);
+                if (need_grad && p.out.grad) {
+                  p.out.grad[3 * qi + 0] = g0;
+                  p.out.grad[3 * qi + 1] = g1;
+                  p.out.grad[3 * qi + 2] = g2;
+                }
+              } else {
+                if (p.out.color) p.out.color[qi * OC + cc] = mean;
+                if (need_grad && p.out.color_grad) {
+                  p.out.color_grad[(qi * OC + cc) * 3 + 0] = g0;
+                  p.out.color_grad[(qi * OC + cc) * 3 + 1] = g1;
+                  p.out.color_grad[(qi * OC + cc) * 3 + 2] = g2;
+                }
               }
             }
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
 }
@@ -610,6 +806,10 @@ static QueryLayout plan_layout(const QueryParams& p, int DP) {
   o += TILE * K;
   l.knn_d2 = o;
   o += TILE * K;
+  l.knn_w = o;
+  o += TILE * K;
+  l.knn_a = o;
+  o += TILE * K;
   l.q = o;
   o += TILE * 3;
   l.out = o;
@@ -697,8 +897,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   rc = validate_decoder(sdf_dec, map->feature_dim);
   if (rc) return rc;
   const int K = opts->nn_k;
-  if (K < 1 || K > PINB200_MAX_K || K > map->n_probe) {
-    set_error("nn_k %d out of range (1..%d, <= n_probe %d)", K, PINB200_MAX_K, map->n_probe);
+  if (K < 1 || K > KREG || K > map->n_probe) {
+    set_error("nn_k %d out of range (1..%d, <= n_probe %d)", K, KREG, map->n_probe);
     return PINB200_ERR_BAD_ARG;
   }
   if (n <= 0) return PINB200_OK;
@@ -719,8 +919,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   p.query_ts = query_ts;
   p.feat = map->geo_feat;
   p.n = n;
-  p.qpt = opts->weighted_first ? TILE : TILE / K;
-  p.n_tiles = (int)((n + p.qpt - 1) / p.qpt);
+  p.qpt = TILE;  // queries per super tile
+  p.n_tiles = (int)((n + TILE - 1) / TILE);
   rc = dispatch_query(p, (cudaStream_t)stream);
   if (rc) return rc;
   if (color_dec) {  // second launch: decode the colour features with the kNN the first launch saved
