@@ -564,7 +564,18 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
                   gq2 = fmaf(wk[k], r2, gq2);
                 }
               }
-              // d w_k / d q = w_k (c_k - sum_j w_j c_j),  c_k = -2 u_k (q - p_k)
+              // d w_k / d q = w_k (c_k - sum_j w_j c_j),  c_k = -2 u_k (q - p_k).
+              // sum_k w_k (a_k - abar) c_k is invariant to a common shift of the a_k; shifting by the nearest
+              // neighbour's a_0 first keeps (a_k - abar) exact when neighbours coincide (cancellation-free)
+              {
+                const float a0 = ak[0];
+                abar = 0.f;
+#pragma unroll
+                for (int k = 0; k < KREG; ++k) {
+                  ak[k] = wk[k] != 0.f ? ak[k] - a0 : 0.f;
+                  abar = fmaf(wk[k], ak[k], abar);
+                }
+              }
 #pragma unroll
               for (int k = 0; k < KREG; ++k) {
                 const float coef = wk[k] * (ak[k] - abar) * ck[k];
@@ -606,14 +617,20 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
             const int n_ch = (need_grad || !p.is_color) ? 1 : OC;
             for (int ch = 0; ch < n_ch; ++ch) {
               const int cc = need_grad ? c : ch;
-              float mean = 0.f;
-              for (int k = 0; k < K; ++k) mean = fmaf(s_w[sq * K + k], s_out[(ql * K + k) * OC + cc], mean);
+              float mean = 0.f, wsum = 0.f, msh = 0.f;
+              const float s0 = s_out[(ql * K) * OC + cc];  // nearest neighbour's value: shift for exact differences
+              for (int k = 0; k < K; ++k) {
+                const float wk = s_w[sq * K + k];
+                mean = fmaf(wk, s_out[(ql * K + k) * OC + cc], mean);
+                msh = fmaf(wk, s_out[(ql * K + k) * OC + cc] - s0, msh);
+                wsum += wk;
+              }
               float var = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
               for (int k = 0; k < K; ++k) {
                 const int lk = s_idx[sq * K + k];
                 if (lk < 0) continue;
                 const float wk = s_w[sq * K + k];
-                const float dm = s_out[(ql * K + k) * OC + cc] - mean;
+                const float dm = (s_out[(ql * K + k) * OC + cc] - s0) - msh;  // == s_k - mean, cancellation-free
                 var = fmaf(wk * dm, dm, var);
                 if (need_grad) {
                   const int row = ql * K + k;
