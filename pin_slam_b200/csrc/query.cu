@@ -43,226 +43,148 @@ struct QueryParams {
 };
 
 // ---------------------------------------------------------------------------
-// warp-per-query feature movement, G queries per iteration so that each warp keeps
-// G * ceil(K*F/32) independent 128-byte row loads in flight
+// warp-per-query feature movement.  The feature dimension FT is a template
+// parameter so that the (neighbour, column) of every load is a compile-time
+// function of the unrolled loop indices; each warp works on GQ queries at once and
+// issues all of their row loads before consuming any (GQ * K independent 128-byte
+// loads in flight per warp).
 // ---------------------------------------------------------------------------
-constexpr int GQ = 4;     // queries gathered concurrently by one warp
-constexpr int RB = 8;     // row-loads per query issued back to back
+constexpr int GQ = 4;  // queries gathered concurrently by one warp
 
-// element e = r*32 + lane of query's [K x F] neighbour-feature block -> (k, j)
-__device__ __forceinline__ void elem_kj(int r, int lane, int F, int& k, int& j) {
-  const int e = r * 32 + lane;
-  k = e / F;
-  j = e - k * F;
-}
+// FT >= 32: a neighbour row is FT/32 coalesced warp loads; FT < 32: 32/FT neighbour rows per warp load.
+template <int FT>
+struct FeatMap {
+  static constexpr int NJ = FT >= 32 ? FT / 32 : 1;     // warp loads per neighbour row
+  static constexpr int PER = FT >= 32 ? 1 : 32 / FT;    // neighbour rows per warp load
+  static constexpr int R = FT >= 32 ? KREG * NJ : (KREG + PER - 1) / PER;  // warp loads per query (K = KREG)
+};
 
-// weighted_first: act[j][row] = sum_k w_k f_k[j]  for the GQ queries ql0 + 4*g (g < GQ)
-__device__ __forceinline__ void gather_weighted_group(const float* __restrict__ feat, int F, int K, const int* s_idx,
+// weighted_first: act[j][ql] = sum_k w_k f_k[j]  for the queries ql0 + 4*g (g < GQ)
+template <int FT>
+__device__ __forceinline__ void gather_weighted_group(const float* __restrict__ feat, int K, const int* s_idx,
                                                       const float* s_w, int lane, float* s_act, int ql0, int qpt) {
-  const int R = (K * F + 31) >> 5;
-  if (F >= 32) {
-    const int nj = F >> 5;
-    float acc[GQ][4];
+  using M = FeatMap<FT>;
+  float v[GQ][M::R], w[GQ][M::R];
 #pragma unroll
-    for (int g = 0; g < GQ; ++g)
+  for (int g = 0; g < GQ; ++g) {
+    const int ql = ql0 + 4 * g;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[g][jj] = 0.f;
-    for (int r0 = 0; r0 < R; r0 += RB) {
-      float v[GQ][RB], w[GQ][RB];
-#pragma unroll
-      for (int g = 0; g < GQ; ++g) {
-        const int ql = ql0 + 4 * g;
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int r = r0 + u;
-          v[g][u] = 0.f;
-          w[g][u] = 0.f;
-          if (r < R && ql < qpt) {
-            const int k = r / nj, jj = r - k * nj;
-            const int lk = s_idx[ql * K + k];
-            w[g][u] = s_w[ql * K + k];
-            v[g][u] = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + 32 * jj + lane);
-          }
-        }
+    for (int r = 0; r < M::R; ++r) {
+      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
+      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
+      v[g][r] = 0.f;
+      w[g][r] = 0.f;
+      if (k < K && ql < qpt) {
+        const int lk = s_idx[ql * K + k];
+        w[g][r] = s_w[ql * K + k];
+        v[g][r] = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * FT + col);
       }
-#pragma unroll
-      for (int g = 0; g < GQ; ++g)
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int r = r0 + u;
-          const int jj = r % nj;  // nj in {1,2,3,4}
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (t == jj) acc[g][t] = fmaf(w[g][u], v[g][u], acc[g][t]);
-        }
     }
+  }
 #pragma unroll
-    for (int g = 0; g < GQ; ++g) {
-      const int ql = ql0 + 4 * g;
+  for (int g = 0; g < GQ; ++g) {
+    const int ql = ql0 + 4 * g;
+    if (FT >= 32) {
+      float acc[M::NJ];
+#pragma unroll
+      for (int jj = 0; jj < M::NJ; ++jj) acc[jj] = 0.f;
+#pragma unroll
+      for (int r = 0; r < M::R; ++r) acc[r % M::NJ] = fmaf(w[g][r], v[g][r], acc[r % M::NJ]);
       if (ql < qpt)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          if (jj < nj) s_act[(32 * jj + lane) * ACT_LD + ql] = acc[g][jj];
-    }
-  } else {
-    float acc[GQ];
+        for (int jj = 0; jj < M::NJ; ++jj) s_act[(32 * jj + lane) * ACT_LD + ql] = acc[jj];
+    } else {
+      float a = 0.f;
 #pragma unroll
-    for (int g = 0; g < GQ; ++g) acc[g] = 0.f;
-    for (int r0 = 0; r0 < R; r0 += RB) {
-      float v[GQ][RB], w[GQ][RB];
+      for (int r = 0; r < M::R; ++r) a = fmaf(w[g][r], v[g][r], a);
 #pragma unroll
-      for (int g = 0; g < GQ; ++g) {
-        const int ql = ql0 + 4 * g;
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int r = r0 + u;
-          int k, j;
-          elem_kj(r, lane, F, k, j);
-          v[g][u] = 0.f;
-          w[g][u] = 0.f;
-          if (r < R && k < K && ql < qpt) {
-            const int lk = s_idx[ql * K + k];
-            w[g][u] = s_w[ql * K + k];
-            v[g][u] = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + j);
-          }
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < GQ; ++g)
-#pragma unroll
-        for (int u = 0; u < RB; ++u) acc[g] = fmaf(w[g][u], v[g][u], acc[g]);
-    }
-#pragma unroll
-    for (int g = 0; g < GQ; ++g) {
-      float a = acc[g];
-      for (int off = F; off < 32; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
-      const int ql = ql0 + 4 * g;
-      if (lane < F && ql < qpt) s_act[lane * ACT_LD + ql] = a;
+      for (int off = FT; off < 32; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
+      if (lane < FT && ql < qpt) s_act[lane * ACT_LD + ql] = a;
     }
   }
 }
 
 // decode-every-neighbour: act[j][ql*K + k] = f_k[j] (0 if invalid)
-__device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat, int F, int K, const int* s_idx,
-                                                  int lane, float* s_act, int ql0, int qpt, int sq0) {
-  const int R = (K * F + 31) >> 5;
-  for (int r0 = 0; r0 < R; r0 += RB) {
-    float v[GQ][RB];
+template <int FT>
+__device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
+                                                  float* s_act, int ql0, int qpt, int sq0) {
+  using M = FeatMap<FT>;
+  float v[GQ][M::R];
 #pragma unroll
-    for (int g = 0; g < GQ; ++g) {
-      const int ql = ql0 + 4 * g;
+  for (int g = 0; g < GQ; ++g) {
+    const int ql = ql0 + 4 * g;
 #pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        int k, j;
-        elem_kj(r0 + u, lane, F, k, j);
-        v[g][u] = 0.f;
-        if (r0 + u < R && k < K && ql < qpt) {
-          const int lk = s_idx[(sq0 + ql) * K + k];
-          const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + j);
-          v[g][u] = lk < 0 ? 0.f : x;
-        }
+    for (int r = 0; r < M::R; ++r) {
+      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
+      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
+      v[g][r] = 0.f;
+      if (k < K && ql < qpt) {
+        const int lk = s_idx[(sq0 + ql) * K + k];
+        const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * FT + col);
+        v[g][r] = lk < 0 ? 0.f : x;
       }
     }
+  }
 #pragma unroll
-    for (int g = 0; g < GQ; ++g) {
-      const int ql = ql0 + 4 * g;
+  for (int g = 0; g < GQ; ++g) {
+    const int ql = ql0 + 4 * g;
 #pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        int k, j;
-        elem_kj(r0 + u, lane, F, k, j);
-        if (r0 + u < R && k < K && ql < qpt) s_act[j * ACT_LD + ql * K + k] = v[g][u];
-      }
+    for (int r = 0; r < M::R; ++r) {
+      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
+      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
+      if (k < K && ql < qpt) s_act[col * ACT_LD + ql * K + k] = v[g][r];
     }
   }
 }
 
-// a_k = <g_xbar[0..F), f_k> for the GQ queries ql0 + 4*g  ->  s_a[ql*K + k]
-__device__ __forceinline__ void feature_dots_group(const float* __restrict__ feat, int F, int K, const int* s_idx,
-                                                   int lane, const float* s_act, float* s_a, int ql0, int qpt) {
-  const int R = (K * F + 31) >> 5;
-  if (F >= 32) {
-    const int nj = F >> 5;
-    float part[GQ][8];
+// a_k = <g_xbar[0..F), f_k> for the queries ql0 + 4*g  ->  s_a[ql*K + k]
+template <int FT>
+__device__ __forceinline__ void feature_dots_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
+                                                   const float* s_act, float* s_a, int ql0, int qpt) {
+  using M = FeatMap<FT>;
+  float v[GQ][M::R];
 #pragma unroll
-    for (int g = 0; g < GQ; ++g)
+  for (int g = 0; g < GQ; ++g) {
+    const int ql = ql0 + 4 * g;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) part[g][k] = 0.f;
-    float gx[GQ][4];
-#pragma unroll
-    for (int g = 0; g < GQ; ++g)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int ql = ql0 + 4 * g;
-        gx[g][jj] = (jj < nj && ql < qpt) ? s_act[(32 * jj + lane) * ACT_LD + ql] : 0.f;
+    for (int r = 0; r < M::R; ++r) {
+      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
+      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
+      v[g][r] = 0.f;
+      if (k < K && ql < qpt) {
+        const int lk = s_idx[ql * K + k];
+        const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * FT + col);
+        v[g][r] = lk < 0 ? 0.f : x;
       }
-    for (int r0 = 0; r0 < R; r0 += RB) {
-      float v[GQ][RB];
-#pragma unroll
-      for (int g = 0; g < GQ; ++g) {
-        const int ql = ql0 + 4 * g;
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int r = r0 + u;
-          v[g][u] = 0.f;
-          if (r < R && ql < qpt) {
-            const int k = r / nj, jj = r - k * nj;
-            const int lk = s_idx[ql * K + k];
-            const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + 32 * jj + lane);
-            v[g][u] = lk < 0 ? 0.f : x;
-          }
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < GQ; ++g)
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int r = r0 + u;
-          const int k = r / nj, jj = r - k * nj;
-          float gxv = 0.f;
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (t == jj) gxv = gx[g][t];
-#pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (t == k) part[g][t] = fmaf(gxv, v[g][u], part[g][t]);
-        }
     }
+  }
 #pragma unroll
-    for (int g = 0; g < GQ; ++g) {
-      const float tot = warp_reduce8(part[g], lane);
-      const int ql = ql0 + 4 * g;
+  for (int g = 0; g < GQ; ++g) {
+    const int ql = ql0 + 4 * g;
+    const int qs = ql < qpt ? ql : 0;
+    if (FT >= 32) {
+      float gx[M::NJ];
+#pragma unroll
+      for (int jj = 0; jj < M::NJ; ++jj) gx[jj] = s_act[(32 * jj + lane) * ACT_LD + qs];
+      float part[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        part[k] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < M::NJ; ++jj) part[k] = fmaf(gx[jj], v[g][k * M::NJ + jj], part[k]);
+      }
+      const float tot = warp_reduce8(part, lane);
       const int k = warp_reduce8_owner(lane);
       if ((lane & 3) == 0 && k < K && ql < qpt) s_a[ql * K + k] = tot;
-    }
-  } else {
-    for (int r0 = 0; r0 < R; r0 += RB) {
-      float v[GQ][RB];
+    } else {
+      const float gxj = s_act[(lane % (FT >= 32 ? 32 : FT)) * ACT_LD + qs];
 #pragma unroll
-      for (int g = 0; g < GQ; ++g) {
-        const int ql = ql0 + 4 * g;
+      for (int r = 0; r < M::R; ++r) {
+        float a = gxj * v[g][r];
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          int k, j;
-          elem_kj(r0 + u, lane, F, k, j);
-          v[g][u] = 0.f;
-          if (r0 + u < R && k < K && ql < qpt) {
-            const int lk = s_idx[ql * K + k];
-            const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * F + j);
-            v[g][u] = lk < 0 ? 0.f : x * s_act[j * ACT_LD + ql];
-          }
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < GQ; ++g) {
-        const int ql = ql0 + 4 * g;
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          float a = v[g][u];
-          for (int off = 1; off < F; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
-          int k, j;
-          elem_kj(r0 + u, lane, F, k, j);
-          if (r0 + u < R && j == 0 && k < K && ql < qpt) s_a[ql * K + k] = a;
-        }
+        for (int off = 1; off < (FT >= 32 ? 1 : FT); off <<= 1) a += __shfl_xor_sync(FULL, a, off);
+        const int k = r * M::PER + lane / (FT >= 32 ? 1 : FT);
+        if ((lane % (FT >= 32 ? 32 : FT)) == 0 && k < K && ql < qpt) s_a[ql * K + k] = a;
       }
     }
   }
@@ -271,12 +193,14 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
 // ---------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------
-template <int H, int DP>
+template <int H, int FT>
 __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ QueryParams p) {
+  constexpr int DP = (FT + 3 + 3) / 4 * 4;  // decoder input width padded to a multiple of 4
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pinb200_map_view& m = p.map;
-  const int K = p.opts.nn_k, F = m.feature_dim, D = F + 3, L = p.dec.n_hidden;
+  const int K = p.opts.nn_k, L = p.dec.n_hidden;
+  constexpr int F = FT, D = FT + 3;
   const int OC = p.dec.out_dim;
   const bool wf = p.opts.weighted_first != 0;
   const bool need_grad = p.opts.need_grad != 0;
@@ -434,9 +358,9 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
 
       // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
       if (wf) {
-        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_weighted_group(feat, F, K, s_idx, s_w, lane, s_act, ql0, qpt);
+        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_weighted_group<FT>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
       } else {
-        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_rows_group(feat, F, K, s_idx, lane, s_act, ql0, qpt, sq0);
+        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_rows_group<FT>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
         // neighbour vectors of the (query, k) rows: thread per row
         if (tid < used_rows) {
           const int ql = tid / K, k = tid - ql * K, sq = sq0 + ql;
@@ -523,7 +447,7 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
         if (wf) {
           // ---- C1: a_k = <g_xbar, f_k> (warp per query, coalesced re-read of the K feature rows)
           if (need_grad) {
-            for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) feature_dots_group(feat, F, K, s_idx, lane, s_act, s_a, ql0, qpt);
+            for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) feature_dots_group<FT>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
             __syncthreads();
           }
           // ---- C2: thread per query -- chain rule through the IDW weights, outputs
@@ -793,9 +717,9 @@ static int validate_map(const pinb200_map_view* m, bool need_feat) {
       return PINB200_ERR_BAD_ARG;
     }
     const int F = m->feature_dim;
-    const bool okF = (F >= 32 && F % 32 == 0 && F <= 128) || F == 4 || F == 8 || F == 16;
+    const bool okF = F == 4 || F == 8 || F == 16 || F == 32 || F == 64;
     if (!okF) {
-      set_error("feature_dim %d unsupported (4, 8, 16, 32, 64, 96, 128)", F);
+      set_error("feature_dim %d unsupported (4, 8, 16, 32, 64)", F);
       return PINB200_ERR_UNSUPPORTED;
     }
     if (m->after_pgo && !m->nb_orient) {
@@ -840,15 +764,16 @@ static QueryLayout plan_layout(const QueryParams& p, int DP) {
   return l;
 }
 
-template <int H, int DP>
+template <int H, int FT>
 static int launch_query(QueryParams& p, cudaStream_t stream) {
+  constexpr int DP = (FT + 3 + 3) / 4 * 4;
   p.lay = plan_layout(p, DP);
   const size_t smem_bytes = (size_t)p.lay.total * sizeof(float);
   if (smem_bytes > 227 * 1024) {
     set_error("query kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
     return PINB200_ERR_UNSUPPORTED;
   }
-  auto kern = query_kernel<H, DP>;
+  auto kern = query_kernel<H, FT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -868,11 +793,15 @@ static int dispatch_query(QueryParams& p, cudaStream_t stream) {
     set_error("decoder hidden_dim %d unsupported (64)", p.dec.hidden_dim);
     return PINB200_ERR_UNSUPPORTED;
   }
-  if (D <= 12) return launch_query<64, 12>(p, stream);
-  if (D <= 20) return launch_query<64, 20>(p, stream);
-  if (D <= 36) return launch_query<64, 36>(p, stream);
-  if (D <= 68) return launch_query<64, 68>(p, stream);
-  set_error("decoder in_dim %d unsupported (<= 68)", D);
+  switch (D - 3) {
+    case 4: return launch_query<64, 4>(p, stream);
+    case 8: return launch_query<64, 8>(p, stream);
+    case 16: return launch_query<64, 16>(p, stream);
+    case 32: return launch_query<64, 32>(p, stream);
+    case 64: return launch_query<64, 64>(p, stream);
+    default: break;
+  }
+  set_error("feature_dim %d unsupported (4, 8, 16, 32, 64)", D - 3);
   return PINB200_ERR_UNSUPPORTED;
 }
 
