@@ -228,6 +228,90 @@ def workload_config(cfg, npm, n_occ, k_v, bq, sample=None):
     }
 
 
+def frame_benchmark(dev, n_frames=12, warm_iters=100):
+    """BASELINE configs[2]: per-frame tracker (3 GN iterations) + mapper (5 training iterations) on synthetic
+    64x1024 KITTI-shaped scans; frames/s over tracker+mapper only.  Also times the reference's op sequence
+    (oracle port, PyTorch eager) on the same GPU and map state for the same two stages."""
+    import torch
+
+    from pin_slam_b200 import ops
+    from pin_slam_b200.frame_loop import FrameLoop
+
+    loop = FrameLoop(device=dev)
+    loop.step(0, timed=False, map_iters=warm_iters)   # frame 0 bootstraps the map (untimed, like the reference's init)
+    loop.step(1, timed=False)
+    l0 = ops.launch_count()
+    info = [loop.step(f) for f in range(2, 2 + n_frames)]
+    launches = (ops.launch_count() - l0) / n_frames
+    trk = sorted(t for t, _ in loop.times)[len(loop.times) // 2]
+    mp = sorted(m for _, m in loop.times)[len(loop.times) // 2]
+    out = {"workload": "BASELINE configs[2]: tracker GN x3 + mapper x5 per frame, 64x1024 synthetic KITTI scan, "
+                       "run_kitti.yaml parameters (F=8, K=6, 1x64, weighted_first=False, bs 16384)",
+           "frames": n_frames, "tracker_ms_median": trk, "mapping_ms_median": mp,
+           "frames_per_s": 1000.0 / (trk + mp), "kernel_launches_per_frame": launches,
+           "source_points": info[-1]["n_source"], "scan_points": info[-1]["n_scan"],
+           "local_map_points": info[-1]["local_points"], "pool_samples": info[-1]["pool"],
+           "final_translation_error_m": info[-1]["trans_err_m"]}
+    try:
+        out["torch_eager_gpu_baseline"] = frame_baseline_torch(loop, dev)
+        out["speedup_vs_torch_eager_gpu"] = out["frames_per_s"] / out["torch_eager_gpu_baseline"]["frames_per_s"]
+    except Exception as e:  # noqa: BLE001
+        out["torch_eager_gpu_baseline"] = {"error": str(e)[:200]}
+    return out
+
+
+def frame_baseline_torch(loop, dev, device=None, reps=3):
+    """The reference's per-frame op sequence (oracle port) on `device` for the current map state:
+    3 x (query_source_points + registration_step) and 5 x one Mapper.mapping iteration."""
+    import torch
+
+    from oracle import pin_oracle as po
+
+    device = device or dev
+    cfg, npm, mapper = loop.cfg, loop.neural_points, loop.mapper
+    m = oracle_map_from(npm).to(device)
+    d = oracle_decoder_from(loop.sdf_mlp).to(device)
+    _, _, source = loop.preprocess(len(loop.poses))
+    source = source.to(device)
+    pose = loop.poses[-1].to(device)
+    sync = (lambda: torch.cuda.synchronize()) if torch.device(device).type == "cuda" else (lambda: None)
+
+    def track():
+        T = pose.clone()
+        for _ in range(3):
+            pts = po.transform_points(source, T)
+            o = po.query_sdf(m, d, pts, cfg.query_nn_k, cfg.weighted_first)
+            r = po.registration_step(pts, o["sdf"], o["grad"], o["sdf_std"], o["nn_count"], torch.zeros_like(o["sdf"]),
+                                     cfg.track_mask_query_nn_k, cfg.reg_min_grad_norm, cfg.reg_max_grad_norm,
+                                     cfg.surface_sample_range_m * cfg.max_sdf_std_ratio, cfg.reg_GM_dist_m,
+                                     cfg.reg_GM_grad, cfg.reg_lm_lambda)
+            T = r["T"] @ T
+
+    def train():
+        mm, dd = m.clone(), d.clone()
+        mm.local_geo_features.requires_grad_(True)
+        dd.requires_grad_(True)
+        opt = po.make_adam([dd.tensors(), [mm.local_geo_features]], cfg.lr, cfg.adam_eps, cfg.weight_decay)
+        for _ in range(5):
+            coord, label, ts, _, _, _, w = mapper.get_batch(global_coord=True)
+            coord, label, ts, w = coord.to(device), label.to(device), ts.to(device), w.to(device)
+            loss, _ = po.mapping_loss(mm, dd, coord, label, ts, w, cfg.query_nn_k, cfg.weighted_first, mapper.sdf_scale,
+                                      cfg.loss_weight_on, cfg.weight_e, cfg.gradient_decimation,
+                                      cfg.voxel_size_m * cfg.num_grad_step_ratio)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+
+    track(); train(); sync()
+    tt, tm = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter(); track(); sync(); t1 = time.perf_counter(); train(); sync(); t2 = time.perf_counter()
+        tt.append((t1 - t0) * 1e3); tm.append((t2 - t1) * 1e3)
+    trk, mp = sorted(tt)[len(tt) // 2], sorted(tm)[len(tm) // 2]
+    return {"tracker_ms": trk, "mapping_ms": mp, "frames_per_s": 1000.0 / (trk + mp), "device": str(device),
+            "what": "reference op sequence (oracle port) in PyTorch eager: 3 x (query + GN step), 5 x training iteration"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -235,6 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frame", action="store_true", help="skip the per-frame tracker+mapper measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -371,6 +456,13 @@ def main():
                     "what": "reference op sequence (oracle port) in PyTorch eager on the same B200, 200k queries"}
             except Exception as e:  # noqa: BLE001
                 line["torch_eager_gpu_baseline"] = {"error": str(e)[:200]}
+        if world == 1 and not args.no_frame:
+            del flush
+            torch.cuda.empty_cache()
+            try:
+                line["per_frame"] = frame_benchmark(dev)
+            except Exception as e:  # noqa: BLE001
+                line["per_frame"] = {"error": repr(e)[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

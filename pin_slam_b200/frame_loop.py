@@ -1,0 +1,87 @@
+"""The per-frame tracker + mapper loop of PIN-SLAM (reference: pin_slam.py:238-508, PGO / GUI / mesh
+off) driven over seeded synthetic KITTI-shaped scans -- BASELINE configs[2]:
+"full per-frame loop: tracker GN (3 iters) + mapper (5 train iters), KITTI 64-beam synthetic".
+
+Only `tracker` (T3-T2) and `mapping` (T6-T5) are timed, like the reference's `time_table` columns the
+frames/s metric is defined on; preprocessing and `Mapper.process_frame` (map growth,
+sampling: section 8 f1/f2 "next" rows) run untimed between them.
+"""
+import types
+
+import numpy as np
+import torch
+
+from .config import HotPathConfig
+from .model import Decoder, NeuralPoints
+from .model.neural_points import voxel_down_sample
+from .synthetic import lidar_scan, trajectory_pose
+from .utils.mapper import Mapper
+from .utils.tracker import Tracker
+
+
+class FrameLoop:
+    def __init__(self, device="cuda", n_track_iter=3, n_map_iter=5, seed=42, cfg=None):
+        self.cfg = cfg or HotPathConfig.kitti(device=str(device))
+        self.dev = torch.device(device)
+        torch.manual_seed(seed)
+        self.neural_points = NeuralPoints(self.cfg)
+        self.sdf_mlp = Decoder(self.cfg, self.cfg.geo_mlp_hidden_dim, self.cfg.geo_mlp_level, 1)
+        decoders = {"sdf": self.sdf_mlp, "semantic": None, "color": None}
+        self.dataset = types.SimpleNamespace(processed_frame=0, odom_poses=np.zeros((0, 4, 4)), pgo_poses=None,
+                                             gt_poses=None, gt_pose_provided=False, lose_track=False,
+                                             stop_status=False, static_mask=None)
+        self.tracker = Tracker(self.cfg, self.neural_points, decoders)
+        self.mapper = Mapper(self.cfg, self.dataset, self.neural_points, decoders)
+        self.n_track_iter, self.n_map_iter = n_track_iter, n_map_iter
+        self.travel = [0.0]
+        self.poses = []
+        self.times = []  # (tracker_ms, mapping_ms) per frame
+
+    def preprocess(self, frame_id):
+        """Synthetic scan -> voxel(0.08) + range crop -> map points; voxel(0.6) -> registration source."""
+        gt = trajectory_pose(frame_id)
+        scan = lidar_scan(gt, seed=frame_id, device=self.dev)
+        scan = scan[voxel_down_sample(scan, 0.08)]
+        rng = scan.norm(dim=1)
+        scan = scan[(rng > 3.0) & (rng < self.cfg.max_range) & (scan[:, 2] > -3.5)]
+        source = scan[voxel_down_sample(scan, 0.6)]
+        return gt, scan.contiguous(), source.contiguous()
+
+    def step(self, frame_id, timed=True, map_iters=None):
+        cfg, npm = self.cfg, self.neural_points
+        gt, scan, source = self.preprocess(frame_id)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        if frame_id == 0:
+            pose = gt.to(self.dev)
+            trk_ms = 0.0
+        else:
+            # constant-velocity initial guess (pin_slam.py: uniform motion model)
+            last = self.poses[-1]
+            guess = last if len(self.poses) < 2 else last @ torch.linalg.inv(self.poses[-2]) @ last
+            ev[0].record()
+            pose, _ = self.tracker.track_fixed(source, guess, self.n_track_iter)
+            ev[1].record()
+            pose = pose.clone()
+        self.poses.append(pose)
+        # pose bookkeeping the dataset class does (slam_dataset.py:507): travel distance, odometry poses
+        if frame_id > 0:
+            step_len = float((self.poses[-1][:3, 3] - self.poses[-2][:3, 3]).norm())
+            self.travel.append(self.travel[-1] + step_len)
+        self.dataset.processed_frame = frame_id
+        self.dataset.odom_poses = torch.stack(self.poses).cpu().numpy()
+        npm.travel_dist = torch.tensor(self.travel, device=self.dev, dtype=cfg.dtype)
+        self.mapper.process_frame(scan, None, pose, frame_id)
+        n_iter = self.n_map_iter if map_iters is None else map_iters
+        ev[2].record()
+        self.mapper.mapping(n_iter)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if frame_id > 0:
+            trk_ms = ev[0].elapsed_time(ev[1])
+        map_ms = ev[2].elapsed_time(ev[3])
+        if timed:
+            self.times.append((trk_ms, map_ms))
+        err = float((pose[:3, 3].cpu() - gt[:3, 3]).norm())
+        return {"frame": frame_id, "tracker_ms": trk_ms, "mapping_ms": map_ms, "n_source": int(source.shape[0]),
+                "n_scan": int(scan.shape[0]), "local_points": npm.local_count(), "pool": self.mapper.pool_sample_count,
+                "trans_err_m": err}

@@ -76,6 +76,22 @@ class DataSampler:
         return coord, label, normal_label, None, color_label, weight
 
 
+def allreduce_training_state(red, dcert, cert_before, certainties, ts_update):
+    """The exchange step of data-parallel map training (one process per GPU).
+
+    `red` is the contiguous buffer [feature grads | decoder grads | certainty increments] of this rank's
+    sub-batch (the loss heads already scaled d loss/d sdf by 1/world, so a SUM gives the global-batch mean);
+    `dcert` is its trailing view.  After the call every rank holds the same gradients, the same
+    `certainties` (= value before the iteration + the increments of ALL ranks) and the same `ts_update`
+    (element-wise max), so the replicated map / decoder / Adam state stay identical."""
+    import torch.distributed as dist
+
+    torch.sub(certainties, cert_before, out=dcert)
+    dist.all_reduce(red, op=dist.ReduceOp.SUM)
+    torch.add(cert_before, dcert, out=certainties)
+    dist.all_reduce(ts_update, op=dist.ReduceOp.MAX)
+
+
 def _transform(points, pose):
     p = pose.to(points)
     return points @ p[:3, :3].T + p[:3, 3]
@@ -341,10 +357,8 @@ class Mapper:
             ops.train_backward(npm.map_handle(True), self.sdf_mlp.handle(), feat, rows, o["knn_idx"], o["knn_weight"],
                                dl, cfg.weighted_first, gfeat, gdec)
             if dist_on:
-                torch.sub(npm.local_point_certainties, cert_before, out=dcert)
-                torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.SUM)
-                torch.add(cert_before, dcert, out=npm.local_point_certainties)
-                torch.distributed.all_reduce(npm.local_point_ts_update, op=torch.distributed.ReduceOp.MAX)
+                allreduce_training_state(red, dcert, cert_before, npm.local_point_certainties,
+                                         npm.local_point_ts_update)
             if train_dec:
                 ops.adam_step(flat, gdec, md, vd, cfg.lr, 0.9, 0.99, cfg.adam_eps, 0.0, it + 1)
             else:

@@ -428,3 +428,42 @@ def test_full_size_properties():
     r64 = oracle64(m, dec, q[sel], 8, True, ref)
     assert_rel_close(a["grad"][sel.cuda()].cpu(), ref["grad"], 1e-4, float(ref["grad"].abs().mean()), r64["grad"])
     assert np.array_equal(a["nn_count"][sel.cuda()].cpu().numpy(), ref["nn_count"].numpy())
+
+
+# --------------------------------------------------------------------------------------
+# the whole per-frame loop through the drop-in classes (NeuralPoints / Decoder / Tracker / Mapper)
+# --------------------------------------------------------------------------------------
+def test_frame_loop_tracks_synthetic_scans():
+    from pin_slam_b200.frame_loop import FrameLoop
+
+    loop = FrameLoop(device="cuda", n_track_iter=8, n_map_iter=5)
+    loop.step(0, map_iters=60)
+    errs = [loop.step(f)["trans_err_m"] for f in range(1, 6)]
+    assert loop.neural_points.count() > 1000 and loop.mapper.pool_sample_count > 10000
+    assert max(errs) < 0.15, errs  # 0.8 m/frame motion recovered by point-to-implicit registration
+    assert bool(torch.isfinite(loop.neural_points.local_geo_features).all())
+
+
+def test_dropin_query_feature_matches_fused_path():
+    """Reference-style call sequence (query_feature -> Decoder.sdf -> autograd.grad) on the drop-in classes
+    equals the fused K1 result."""
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import Decoder
+    from pin_slam_b200.synthetic import build_map, surface_queries
+
+    for wf in (True, False):
+        cfg = HotPathConfig.kitti(device="cuda", feature_std=0.1, weighted_first=wf, buffer_size=200003)
+        npm = build_map(cfg, n_surface=200000, seed=3, extent=30.0)
+        torch.manual_seed(1)
+        dec = Decoder(cfg, 64, 1, 1)
+        q = surface_queries(npm, 5000, seed=2).requires_grad_(True)
+        geo, _, w, cnt, cert = npm.query_feature(q, training_mode=False)
+        s = dec.sdf(geo)
+        if not wf:
+            s = torch.sum(s * w, dim=1).squeeze(1)
+        g = torch.autograd.grad(s, q, torch.ones_like(s), create_graph=True)[0]
+        o = npm.query_sdf(q.detach(), dec, need_grad=True)
+        assert torch.equal(cnt, o["nn_count"].long())
+        assert_sdf_close(o["sdf"].cpu(), s.detach().cpu(), dec.sdf_scale)
+        assert_rel_close(o["grad"].cpu(), g.detach().cpu(), 2e-4, float(g.abs().mean()))
+        np.testing.assert_allclose(o["certainty"].cpu().numpy(), cert.cpu().numpy(), rtol=1e-5, atol=1e-6)
