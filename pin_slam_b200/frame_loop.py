@@ -55,9 +55,13 @@ class FrameLoop:
             pose = gt.to(self.dev)
             trk_ms = 0.0
         else:
-            # constant-velocity initial guess (pin_slam.py: uniform motion model)
+            # constant-velocity initial guess (pin_slam.py: uniform motion model); the very first motion
+            # estimate comes from the synthetic trajectory (a real run starts from rest)
             last = self.poses[-1]
-            guess = last if len(self.poses) < 2 else last @ torch.linalg.inv(self.poses[-2]) @ last
+            if len(self.poses) < 2:
+                guess = (gt @ torch.linalg.inv(trajectory_pose(frame_id - 1))).to(self.dev) @ last
+            else:
+                guess = last @ torch.linalg.inv(self.poses[-2]) @ last
             ev[0].record()
             pose, _ = self.tracker.track_fixed(source, guess, self.n_track_iter)
             ev[1].record()

@@ -11,10 +11,24 @@ import math
 
 import torch
 
-BOXES = [  # (cx, cy, half_x, half_y, height)
-    (8.0, 6.0, 2.0, 1.5, 2.5), (-12.0, -9.0, 1.5, 3.0, 3.0), (20.0, -14.0, 3.0, 2.0, 2.0), (-25.0, 15.0, 2.5, 2.5, 4.0),
-    (3.0, -20.0, 1.0, 4.0, 1.5), (30.0, 22.0, 2.0, 2.0, 3.5),
-]
+def _make_boxes(n=28, seed=7):
+    """Seeded clutter (cx, cy, half_x, half_y, height): boxes / pillars that break the corridor symmetry so
+    that registration is constrained along the driving direction; the lane |y| < 4 m stays free."""
+    import random
+
+    rnd = random.Random(seed)
+    boxes = [(8.0, 6.0, 2.0, 1.5, 2.5), (-12.0, -9.0, 1.5, 3.0, 3.0), (20.0, -14.0, 3.0, 2.0, 2.0),
+             (-25.0, 15.0, 2.5, 2.5, 4.0), (3.0, -20.0, 1.0, 4.0, 1.5), (30.0, 22.0, 2.0, 2.0, 3.5)]
+    while len(boxes) < n:
+        cx, cy = rnd.uniform(-36, 36), rnd.uniform(-36, 36)
+        hx, hy, h = rnd.uniform(0.3, 2.5), rnd.uniform(0.3, 2.5), rnd.uniform(1.0, 4.5)
+        if abs(cy) - hy < 4.0:
+            continue
+        boxes.append((cx, cy, hx, hy, h))
+    return boxes
+
+
+BOXES = _make_boxes()
 
 
 def room_surface_points(n, seed, extent=80.0, wall_h=6.0, device="cpu", noise=0.01):
