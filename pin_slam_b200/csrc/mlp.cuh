@@ -78,6 +78,17 @@ __device__ __forceinline__ void stage_decoder(const pinb200_decoder_view& d, con
   for (int e = tid; e < align4(d.out_dim); e += nt) bo[e] = (d.b_out && e < d.out_dim) ? __ldg(d.b_out + e) : 0.f;
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): {d0,d1} += {a0,a1} * b.  One issue slot for two FMAs; ptxas folds the
+// broadcast operand into FFMA2's scalar .F32 source, so a 128-bit weight load feeds exactly two instructions.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b) {
+  unsigned long long d, a, bb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(bb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 // out[o] = bias[o] + sum_i w[i][o] * col[i*ACT_LD]   (w: [n_in][NOUT] in smem, warp-uniform float4 reads)
 template <int NOUT>
 __device__ __forceinline__ void matvec_col(const float* __restrict__ w, const float* __restrict__ bias,
@@ -103,10 +114,8 @@ __device__ __forceinline__ void matvec_col(const float* __restrict__ w, const fl
 #pragma unroll
     for (int o = 0; o < NOUT / 4; ++o) {
       const float4 ww = w4[o];
-      out[4 * o + 0] = fmaf(ww.x, a, out[4 * o + 0]);
-      out[4 * o + 1] = fmaf(ww.y, a, out[4 * o + 1]);
-      out[4 * o + 2] = fmaf(ww.z, a, out[4 * o + 2]);
-      out[4 * o + 3] = fmaf(ww.w, a, out[4 * o + 3]);
+      ffma2(out[4 * o + 0], out[4 * o + 1], ww.x, ww.y, a);
+      ffma2(out[4 * o + 2], out[4 * o + 3], ww.z, ww.w, a);
     }
   }
 }
