@@ -90,7 +90,7 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
 }
 
 // out[o] = bias[o] + sum_i w[i][o] * col[i*ACT_LD]   (w: [n_in][NOUT] in smem, warp-uniform float4 reads)
-template <int NOUT>
+template <int NOUT, int LD = ACT_LD>
 __device__ __forceinline__ void matvec_col(const float* __restrict__ w, const float* __restrict__ bias,
                                            const float* __restrict__ col, int n_in, float (&out)[NOUT]) {
   static_assert(NOUT % 4 == 0, "NOUT must be a multiple of 4");
@@ -109,7 +109,7 @@ __device__ __forceinline__ void matvec_col(const float* __restrict__ w, const fl
   }
 #pragma unroll 2
   for (int i = 0; i < n_in; ++i) {
-    const float a = col[i * ACT_LD];
+    const float a = col[i * LD];
     const float4* w4 = reinterpret_cast<const float4*>(w + i * NOUT);
 #pragma unroll
     for (int o = 0; o < NOUT / 4; ++o) {
@@ -142,11 +142,11 @@ __device__ __forceinline__ void apply_mask(float (&g)[H], uint64_t mk, bool leak
     if (!((mk >> j) & 1ull)) g[j] = leaky ? 0.01f * g[j] : 0.f;
 }
 
-template <int N>
+template <int N, int LD = ACT_LD>
 __device__ __forceinline__ void store_col(float* col, const float (&v)[N], int n) {
 #pragma unroll
   for (int j = 0; j < N; ++j)
-    if (j < n) col[j * ACT_LD] = v[j];
+    if (j < n) col[j * LD] = v[j];
 }
 
 }  // namespace pinb

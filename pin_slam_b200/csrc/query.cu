@@ -1,8 +1,9 @@
 // K1: fused voxel-hash kNN + IDW interpolation + decoder MLP + analytic d/dq.
 //
-// One CTA (128 threads) owns a tile of 128 decoder rows:
-//   weighted_first=1 : 128 queries, one row each (features IDW-averaged first)
-//   weighted_first=0 : floor(128/K) queries, K rows each (decode every neighbour)
+// Every WARP owns an independent tile of 32 queries (no block-wide barriers after the one-off weight
+// staging: 12 de-synchronised warps per SM overlap each other's memory and compute phases):
+//   weighted_first=1 : 32 decoder rows, one per query (features IDW-averaged first)
+//   weighted_first=0 : the 32 queries are decoded in row tiles of floor(32/K) queries x K rows
 // Phase A (warp per query): hash the query's cell, probe the C neighbour cells of
 //   the voxel hash table (one probe per lane, 32 at a time), age/distance filter,
 //   in-register warp top-K, IDW weights, coalesced gather of the neighbour feature
@@ -23,7 +24,8 @@ namespace pinb {
 
 struct QueryLayout {  // float offsets into dynamic smem
   DecSmem dec;
-  int delta, act, knn_idx, knn_gidx, knn_d2, knn_w, knn_a, q, out, nn, mask, total;
+  int delta, warp0, warp_stride, n_warps;  // CTA-shared part, then n_warps per-warp blocks
+  int act, knn_idx, knn_gidx, knn_d2, knn_w, knn_a, q, out, nn, mask, total;  // offsets inside a warp block
 };
 
 struct QueryParams {
@@ -49,7 +51,10 @@ struct QueryParams {
 // issues all of their row loads before consuming any (GQ * K independent 128-byte
 // loads in flight per warp).
 // ---------------------------------------------------------------------------
-constexpr int GQ = 4;  // queries gathered concurrently by one warp
+constexpr int GQ = 4;   // queries gathered concurrently by one warp
+constexpr int WT = 32;  // queries (= threads) per warp tile
+constexpr int WLD = 33; // leading dimension of the per-warp transposed activation tile (odd: conflict-free)
+constexpr int WPB = 12; // max warps per CTA (one CTA per SM); fewer if shared memory does not fit
 
 // FT >= 32: a neighbour row is FT/32 coalesced warp loads; FT < 32: 32/FT neighbour rows per warp load.
 template <int FT>
@@ -67,7 +72,7 @@ __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ 
   float v[GQ][M::R], w[GQ][M::R];
 #pragma unroll
   for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + 4 * g;
+    const int ql = ql0 + g;
 #pragma unroll
     for (int r = 0; r < M::R; ++r) {
       const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
@@ -83,7 +88,7 @@ __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ 
   }
 #pragma unroll
   for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + 4 * g;
+    const int ql = ql0 + g;
     if (FT >= 32) {
       float acc[M::NJ];
 #pragma unroll
@@ -92,14 +97,14 @@ __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ 
       for (int r = 0; r < M::R; ++r) acc[r % M::NJ] = fmaf(w[g][r], v[g][r], acc[r % M::NJ]);
       if (ql < qpt)
 #pragma unroll
-        for (int jj = 0; jj < M::NJ; ++jj) s_act[(32 * jj + lane) * ACT_LD + ql] = acc[jj];
+        for (int jj = 0; jj < M::NJ; ++jj) s_act[(32 * jj + lane) * WLD + ql] = acc[jj];
     } else {
       float a = 0.f;
 #pragma unroll
       for (int r = 0; r < M::R; ++r) a = fmaf(w[g][r], v[g][r], a);
 #pragma unroll
       for (int off = FT; off < 32; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
-      if (lane < FT && ql < qpt) s_act[lane * ACT_LD + ql] = a;
+      if (lane < FT && ql < qpt) s_act[lane * WLD + ql] = a;
     }
   }
 }
@@ -112,7 +117,7 @@ __device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat
   float v[GQ][M::R];
 #pragma unroll
   for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + 4 * g;
+    const int ql = ql0 + g;
 #pragma unroll
     for (int r = 0; r < M::R; ++r) {
       const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
@@ -127,12 +132,12 @@ __device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat
   }
 #pragma unroll
   for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + 4 * g;
+    const int ql = ql0 + g;
 #pragma unroll
     for (int r = 0; r < M::R; ++r) {
       const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
       const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
-      if (k < K && ql < qpt) s_act[col * ACT_LD + ql * K + k] = v[g][r];
+      if (k < K && ql < qpt) s_act[col * WLD + ql * K + k] = v[g][r];
     }
   }
 }
@@ -145,7 +150,7 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
   float v[GQ][M::R];
 #pragma unroll
   for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + 4 * g;
+    const int ql = ql0 + g;
 #pragma unroll
     for (int r = 0; r < M::R; ++r) {
       const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
@@ -160,12 +165,12 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
   }
 #pragma unroll
   for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + 4 * g;
+    const int ql = ql0 + g;
     const int qs = ql < qpt ? ql : 0;
     if (FT >= 32) {
       float gx[M::NJ];
 #pragma unroll
-      for (int jj = 0; jj < M::NJ; ++jj) gx[jj] = s_act[(32 * jj + lane) * ACT_LD + qs];
+      for (int jj = 0; jj < M::NJ; ++jj) gx[jj] = s_act[(32 * jj + lane) * WLD + qs];
       float part[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -177,7 +182,7 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
       const int k = warp_reduce8_owner(lane);
       if ((lane & 3) == 0 && k < K && ql < qpt) s_a[ql * K + k] = tot;
     } else {
-      const float gxj = s_act[(lane % (FT >= 32 ? 32 : FT)) * ACT_LD + qs];
+      const float gxj = s_act[(lane % (FT >= 32 ? 32 : FT)) * WLD + qs];
 #pragma unroll
       for (int r = 0; r < M::R; ++r) {
         float a = gxj * v[g][r];
@@ -194,10 +199,10 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
 // the fused kernel
 // ---------------------------------------------------------------------------
 template <int H, int FT>
-__global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ QueryParams p) {
+__global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constant__ QueryParams p) {
   constexpr int DP = (FT + 3 + 3) / 4 * 4;  // decoder input width padded to a multiple of 4
   extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const pinb200_map_view& m = p.map;
   const int K = p.opts.nn_k, L = p.dec.n_hidden;
   constexpr int F = FT, D = FT + 3;
@@ -208,25 +213,28 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
   const float* __restrict__ feat = p.feat;
 
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem + p.lay.delta);
-  float* s_act = smem + p.lay.act;
-  int* s_idx = reinterpret_cast<int*>(smem + p.lay.knn_idx);
-  int* s_gidx = reinterpret_cast<int*>(smem + p.lay.knn_gidx);
-  float* s_d2 = smem + p.lay.knn_d2;
-  float* s_w = smem + p.lay.knn_w;
-  float* s_a = smem + p.lay.knn_a;
-  float* s_q = smem + p.lay.q;
-  float* s_out = smem + p.lay.out;
-  int* s_nn = reinterpret_cast<int*>(smem + p.lay.nn);
-  uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + p.lay.mask);
+  float* wsm = smem + p.lay.warp0 + warp * p.lay.warp_stride;  // this warp's private tile state
+  float* s_act = wsm + p.lay.act;
+  int* s_idx = reinterpret_cast<int*>(wsm + p.lay.knn_idx);
+  int* s_gidx = reinterpret_cast<int*>(wsm + p.lay.knn_gidx);
+  float* s_d2 = wsm + p.lay.knn_d2;
+  float* s_w = wsm + p.lay.knn_w;
+  float* s_a = wsm + p.lay.knn_a;
+  float* s_q = wsm + p.lay.q;
+  float* s_out = wsm + p.lay.out;
+  int* s_nn = reinterpret_cast<int*>(wsm + p.lay.nn);
+  uint64_t* s_mask = reinterpret_cast<uint64_t*>(wsm + p.lay.mask);
 
   stage_decoder(p.dec, p.lay.dec, smem, DP, need_grad);
   if (!p.use_saved_knn) fill_probe_deltas(m, s_delta);
   __syncthreads();
 
-  const int QPT = wf ? TILE : TILE / K;                 // queries per 128-row decoder tile
-  const int n_rt = wf ? 1 : (TILE + QPT - 1) / QPT;     // row tiles per 128-query super tile
-  for (int st = blockIdx.x; st < p.n_tiles; st += gridDim.x) {
-    const long long q0s = (long long)st * TILE;
+  const int QPT = wf ? WT : WT / K;                   // queries per 32-row decoder tile
+  const int n_rt = wf ? 1 : (WT + QPT - 1) / QPT;     // row tiles per 32-query warp tile
+  const int tid = lane;                               // row / query owned by this thread inside the warp tile
+  const int nwarp = blockDim.x >> 5;
+  for (int st = blockIdx.x * nwarp + warp; st < p.n_tiles; st += gridDim.x * nwarp) {
+    const long long q0s = (long long)st * WT;
 
     // ============ phase A1: thread per query -- search, IDW weights, side effects ============
     {
@@ -315,9 +323,9 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
         }
       }
       if (wf) {  // the position part of the IDW-averaged decoder input; the tile row is this thread's column
-        s_act[(F + 0) * ACT_LD + tid] = sx;
-        s_act[(F + 1) * ACT_LD + tid] = sy;
-        s_act[(F + 2) * ACT_LD + tid] = sz;
+        s_act[(F + 0) * WLD + tid] = sx;
+        s_act[(F + 1) * WLD + tid] = sy;
+        s_act[(F + 2) * WLD + tid] = sz;
       }
       if (live && !p.is_color) {
         if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
@@ -349,18 +357,18 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
 
     for (int rt = 0; rt < n_rt; ++rt) {
       const int sq0 = rt * QPT;                              // first query of this row tile inside the super tile
-      const int qpt = min(QPT, TILE - sq0);                  // queries in this row tile
-      const int used_rows = wf ? TILE : qpt * K;
+      const int qpt = min(QPT, WT - sq0);                  // queries in this row tile
+      const int used_rows = wf ? WT : qpt * K;
 
       // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
       if (wf) {
-        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_weighted_group<FT>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
+        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_weighted_group<FT>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
       } else {
-        for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) gather_rows_group<FT>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
+        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_rows_group<FT>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
         // neighbour vectors of the (query, k) rows: thread per row
         if (tid < used_rows) {
           const int ql = tid / K, k = tid - ql * K, sq = sq0 + ql;
@@ -376,14 +384,14 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
               quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
             }
           }
-          s_act[(F + 0) * ACT_LD + tid] = nx;
-          s_act[(F + 1) * ACT_LD + tid] = ny;
-          s_act[(F + 2) * ACT_LD + tid] = nz;
+          s_act[(F + 0) * WLD + tid] = nx;
+          s_act[(F + 1) * WLD + tid] = ny;
+          s_act[(F + 2) * WLD + tid] = nz;
         } else {
-          for (int d = 0; d < D; ++d) s_act[d * ACT_LD + tid] = 0.f;  // unused rows stay finite
+          for (int d = 0; d < D; ++d) s_act[d * WLD + tid] = 0.f;  // unused rows stay finite
         }
       }
-      __syncthreads();
+      __syncwarp();
 
       // ============ phase B: decoder forward (thread per row) ============
       float* col = s_act + tid;
@@ -391,9 +399,9 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
       {
         int n_in = D;
         for (int l = 0; l < L; ++l) {
-          matvec_col<H>(smem + p.lay.dec.wt[l], smem + p.lay.dec.b[l], col, n_in, h);
-          s_mask[l * TILE + tid] = activate<H>(h, leaky);
-          if (l < L - 1) store_col<H>(col, h, H);
+          matvec_col<H, WLD>(smem + p.lay.dec.wt[l], smem + p.lay.dec.b[l], col, n_in, h);
+          s_mask[l * WT + tid] = activate<H>(h, leaky);
+          if (l < L - 1) store_col<H, WLD>(col, h, H);
           n_in = H;
         }
       }
@@ -427,28 +435,28 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
             const float* wo = smem + p.lay.dec.wout + c * H;
 #pragma unroll
             for (int j = 0; j < H; ++j) g[j] = wo[j];
-            apply_mask<H>(g, s_mask[(L - 1) * TILE + tid], leaky);
+            apply_mask<H>(g, s_mask[(L - 1) * WT + tid], leaky);
           }
           for (int l = L - 1; l >= 1; --l) {
-            store_col<H>(col, g, H);
-            matvec_col<H>(smem + p.lay.dec.w[l], nullptr, col, H, g);
-            apply_mask<H>(g, s_mask[(l - 1) * TILE + tid], leaky);
+            store_col<H, WLD>(col, g, H);
+            matvec_col<H, WLD>(smem + p.lay.dec.w[l], nullptr, col, H, g);
+            apply_mask<H>(g, s_mask[(l - 1) * WT + tid], leaky);
           }
-          store_col<H>(col, g, H);
+          store_col<H, WLD>(col, g, H);
           float gx[DP];
-          matvec_col<DP>(smem + p.lay.dec.w[0], nullptr, col, H, gx);
+          matvec_col<DP, WLD>(smem + p.lay.dec.w[0], nullptr, col, H, gx);
           const float dv = c == 0 ? dval[0] : (c == 1 ? dval[1] : (c == 2 ? dval[2] : dval[3]));
 #pragma unroll
           for (int d = 0; d < DP; ++d)
-            if (d < D) col[d * ACT_LD] = gx[d] * dv;
+            if (d < D) col[d * WLD] = gx[d] * dv;
         }
-        __syncthreads();
+        __syncwarp();
 
         if (wf) {
           // ---- C1: a_k = <g_xbar, f_k> (warp per query, coalesced re-read of the K feature rows)
           if (need_grad) {
-            for (int ql0 = warp; ql0 < qpt; ql0 += 4 * GQ) feature_dots_group<FT>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
-            __syncthreads();
+            for (int ql0 = 0; ql0 < qpt; ql0 += GQ) feature_dots_group<FT>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
+            __syncwarp();
           }
           // ---- C2: thread per query -- chain rule through the IDW weights, outputs
           const long long qi = q0s + tid;
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
             if (need_grad) {
               const int nn = s_nn[tid];
               const float qx = s_q[3 * tid], qy = s_q[3 * tid + 1], qz = s_q[3 * tid + 2];
-              const float gn0 = col[(F + 0) * ACT_LD], gn1 = col[(F + 1) * ACT_LD], gn2 = col[(F + 2) * ACT_LD];
+              const float gn0 = col[(F + 0) * WLD], gn1 = col[(F + 1) * WLD], gn2 = col[(F + 2) * WLD];
               float ak[KREG], wk[KREG], ck[KREG], dx[KREG], dy[KREG], dz[KREG];
               float abar = 0.f;
 #pragma unroll
@@ -558,8 +566,8 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
                 var = fmaf(wk * dm, dm, var);
                 if (need_grad) {
                   const int row = ql * K + k;
-                  float r0 = s_act[(F + 0) * ACT_LD + row], r1 = s_act[(F + 1) * ACT_LD + row],
-                        r2 = s_act[(F + 2) * ACT_LD + row];
+                  float r0 = s_act[(F + 0) * WLD + row], r1 = s_act[(F + 1) * WLD + row],
+                        r2 = s_act[(F + 2) * WLD + row];
                   const float* pg = m.points + 3 * (size_t)s_gidx[sq * K + k];  // the point dist2 was measured to
                   const float dx = qx - __ldg(pg), dy = qy - __ldg(pg + 1), dz = qz - __ldg(pg + 2);
                   if (m.after_pgo) {
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(TILE, 3) query_kernel(const __grid_constant__ 
             }
           }
         }
-        __syncthreads();
+        __syncwarp();
       }
     }
   }
@@ -737,30 +745,35 @@ static QueryLayout plan_layout(const QueryParams& p, int DP) {
   l.delta = o;
   o += align4(p.map.n_probe);
   l.dec = plan_decoder_smem(p.dec, DP, p.opts.need_grad != 0, o);
-  o = l.dec.end;
+  l.warp0 = align4(l.dec.end);
+  // per-warp block
+  int w = 0;
   const int act_rows = (DP > H ? DP : H);
-  l.act = o;
-  o += align4(act_rows * ACT_LD);
-  l.knn_idx = o;
-  o += TILE * K;
-  l.knn_gidx = o;
-  o += TILE * K;
-  l.knn_d2 = o;
-  o += TILE * K;
-  l.knn_w = o;
-  o += TILE * K;
-  l.knn_a = o;
-  o += TILE * K;
-  l.q = o;
-  o += TILE * 3;
-  l.out = o;
-  o += align4(TILE * p.dec.out_dim);
-  l.nn = o;
-  o += TILE;
-  o = (o + 1) & ~1;  // 8-byte align the 64-bit masks
-  l.mask = o;
-  o += 2 * TILE * p.dec.n_hidden;
-  l.total = o;
+  l.act = w;
+  w += align4(act_rows * WLD);
+  l.knn_idx = w;
+  w += WT * K;
+  l.knn_gidx = w;
+  w += WT * K;
+  l.knn_d2 = w;
+  w += WT * K;
+  l.knn_w = w;
+  w += WT * K;
+  l.knn_a = w;
+  w += WT * K;
+  l.q = w;
+  w += WT * 3;
+  l.out = w;
+  w += align4(WT * p.dec.out_dim);
+  l.nn = w;
+  w += WT;
+  w = (w + 1) & ~1;  // 8-byte align the 64-bit masks
+  l.mask = w;
+  w += 2 * WT * p.dec.n_hidden;
+  l.warp_stride = align4(w);
+  int nw = (227 * 1024 / 4 - l.warp0) / l.warp_stride;
+  l.n_warps = nw > WPB ? WPB : nw;
+  l.total = l.warp0 + l.n_warps * l.warp_stride;
   return l;
 }
 
@@ -769,10 +782,11 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
   constexpr int DP = (FT + 3 + 3) / 4 * 4;
   p.lay = plan_layout(p, DP);
   const size_t smem_bytes = (size_t)p.lay.total * sizeof(float);
-  if (smem_bytes > 227 * 1024) {
+  if (p.lay.n_warps < 1 || smem_bytes > 227 * 1024) {
     set_error("query kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
     return PINB200_ERR_UNSUPPORTED;
   }
+  const int nw = p.lay.n_warps;
   auto kern = query_kernel<H, FT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) {
@@ -780,10 +794,11 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     return PINB200_ERR_CUDA;
   }
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem_bytes);
   if (occ < 1) occ = 1;
-  const int grid = (int)std::min<long long>(p.n_tiles, (long long)sm_count() * occ);
-  kern<<<grid, TILE, smem_bytes, stream>>>(p);
+  const long long ctas_needed = (p.n_tiles + nw - 1) / nw;
+  const int grid = (int)std::min<long long>(ctas_needed, (long long)sm_count() * occ);
+  kern<<<grid, nw * 32, smem_bytes, stream>>>(p);
   return check_launch("query_kernel");
 }
 
@@ -865,8 +880,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   p.query_ts = query_ts;
   p.feat = map->geo_feat;
   p.n = n;
-  p.qpt = TILE;  // queries per super tile
-  p.n_tiles = (int)((n + TILE - 1) / TILE);
+  p.qpt = WT;  // queries per warp tile
+  p.n_tiles = (int)((n + WT - 1) / WT);
   rc = dispatch_query(p, (cudaStream_t)stream);
   if (rc) return rc;
   if (color_dec) {  // second launch: decode the colour features with the kNN the first launch saved
