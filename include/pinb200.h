@@ -70,6 +70,13 @@ typedef struct pinb200_map_view {
   int32_t cur_ts;
   float diff_travel_dist_local;
   int32_t after_pgo;           /* rotate neighbour vectors by the point quaternion (:645) */
+  /* Optional packed search records, one 32-byte sector per global point (B200 layout: a probe hit costs one
+   * sector and one dependent load level instead of three arrays and two levels):
+   *   [n_global, 8] f32 = { x, y, z, travel_dist[ts_create], bit-cast int32 id in the queried index space
+   *                         (global2local[i], or i when global2local is NULL), 0, 0, 0 }
+   * Built by the host wrapper whenever the map / local map / travel distance changes; NULL => the kernels
+   * read points / ts_create / travel_dist / global2local separately. */
+  const float* search_rec;
 } pinb200_map_view;
 
 /* Weights of one Decoder (model/decoder.py:43-51), torch nn.Linear layout. */

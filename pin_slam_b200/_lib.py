@@ -24,7 +24,7 @@ class MapView(C.Structure):
         ("certainty", c_f32p), ("ts_update", c_i32p), ("n_nb", C.c_int64), ("feature_dim", C.c_int32),
         ("probe_dx", c_i32p), ("n_probe", C.c_int32), ("resolution", C.c_float), ("max_valid_dist2", C.c_float),
         ("time_filter", C.c_int32), ("cur_ts", C.c_int32), ("diff_travel_dist_local", C.c_float),
-        ("after_pgo", C.c_int32),
+        ("after_pgo", C.c_int32), ("search_rec", c_f32p),
     ]
 
 

@@ -194,7 +194,7 @@ __device__ __forceinline__ float idw_weight(float d2, bool valid, int nn_count, 
 // thread keeps ~8 loads in flight and a 128-thread CTA ~1000.
 // ---------------------------------------------------------------------------
 constexpr int KREG = 8;
-constexpr int PROBE_BATCH = 8;
+constexpr int PROBE_BATCH = 11;  // 33 probes (the default neighbourhood) = 3 batches
 
 struct KnnRegs {
   float d2[KREG];
@@ -252,25 +252,45 @@ __device__ __forceinline__ int knn_search_thread(const pinb200_map_view& m, cons
         gi[j] = __ldg(m.slot_table + slot);
       }
     }
-    float px[PROBE_BATCH], py[PROBE_BATCH], pz[PROBE_BATCH];
-    int ts[PROBE_BATCH], li[PROBE_BATCH];
+    float px[PROBE_BATCH], py[PROBE_BATCH], pz[PROBE_BATCH], td[PROBE_BATCH];
+    int li[PROBE_BATCH];
+    if (m.search_rec) {
+      // one 32-byte record per hit: a single dependent load level
 #pragma unroll
-    for (int j = 0; j < PROBE_BATCH; ++j) {
-      px[j] = py[j] = pz[j] = 0.f;
-      ts[j] = 0;
-      li[j] = -1;
-      if (gi[j] >= 0) {
-        const float* pp = m.points + 3 * (size_t)gi[j];
-        px[j] = __ldg(pp);
-        py[j] = __ldg(pp + 1);
-        pz[j] = __ldg(pp + 2);
-        if (tf) ts[j] = __ldg(m.ts_create + gi[j]);
-        li[j] = m.global2local ? __ldg(m.global2local + gi[j]) : gi[j];
+      for (int j = 0; j < PROBE_BATCH; ++j) {
+        px[j] = py[j] = pz[j] = 0.f;
+        td[j] = td_cur;
+        li[j] = -1;
+        if (gi[j] >= 0) {
+          const float4* rp = reinterpret_cast<const float4*>(m.search_rec + 8 * (size_t)gi[j]);
+          const float4 a = __ldg(rp);
+          const float b = __ldg(reinterpret_cast<const float*>(rp + 1));
+          px[j] = a.x;
+          py[j] = a.y;
+          pz[j] = a.z;
+          td[j] = a.w;
+          li[j] = __float_as_int(b);
+        }
       }
-    }
-    float td[PROBE_BATCH];
+    } else {
+      int ts[PROBE_BATCH];
 #pragma unroll
-    for (int j = 0; j < PROBE_BATCH; ++j) td[j] = (tf && gi[j] >= 0) ? __ldg(m.travel_dist + ts[j]) : td_cur;
+      for (int j = 0; j < PROBE_BATCH; ++j) {
+        px[j] = py[j] = pz[j] = 0.f;
+        ts[j] = 0;
+        li[j] = -1;
+        if (gi[j] >= 0) {
+          const float* pp = m.points + 3 * (size_t)gi[j];
+          px[j] = __ldg(pp);
+          py[j] = __ldg(pp + 1);
+          pz[j] = __ldg(pp + 2);
+          if (tf) ts[j] = __ldg(m.ts_create + gi[j]);
+          li[j] = m.global2local ? __ldg(m.global2local + gi[j]) : gi[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PROBE_BATCH; ++j) td[j] = (tf && gi[j] >= 0) ? __ldg(m.travel_dist + ts[j]) : td_cur;
+    }
 #pragma unroll
     for (int j = 0; j < PROBE_BATCH; ++j) {
       if (gi[j] < 0) continue;

@@ -469,23 +469,37 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
               const float gn0 = col[(F + 0) * WLD], gn1 = col[(F + 1) * WLD], gn2 = col[(F + 2) * WLD];
               float ak[KREG], wk[KREG], ck[KREG], dx[KREG], dy[KREG], dz[KREG];
               float abar = 0.f;
+              // issue every neighbour load first (local position, global position, quaternion), then compute
+              float lpx[KREG], lpy[KREG], lpz[KREG], gpx[KREG], gpy[KREG], gpz[KREG];
+              float4 qt[KREG];
+              int lks[KREG];
+#pragma unroll
+              for (int k = 0; k < KREG; ++k) {
+                lks[k] = k < K ? s_idx[tid * K + k] : -1;
+                const int lk0 = lks[k] < 0 ? 0 : lks[k];
+                const int gk0 = lks[k] < 0 ? 0 : s_gidx[tid * K + k];
+                const float* pp = m.nb_points + 3 * (size_t)lk0;
+                const float* pg = m.points + 3 * (size_t)gk0;
+                lpx[k] = __ldg(pp);
+                lpy[k] = __ldg(pp + 1);
+                lpz[k] = __ldg(pp + 2);
+                gpx[k] = __ldg(pg);
+                gpy[k] = __ldg(pg + 1);
+                gpz[k] = __ldg(pg + 2);
+                qt[k] = m.after_pgo ? __ldg(reinterpret_cast<const float4*>(m.nb_orient) + lk0) : make_float4(1.f, 0.f, 0.f, 0.f);
+              }
 #pragma unroll
               for (int k = 0; k < KREG; ++k) {
                 ak[k] = wk[k] = ck[k] = dx[k] = dy[k] = dz[k] = 0.f;
-                const int lk = k < K ? s_idx[tid * K + k] : -1;
-                if (lk >= 0) {
-                  const float* pp = m.nb_points + 3 * (size_t)lk;
-                  const float ux = qx - __ldg(pp), uy = qy - __ldg(pp + 1), uz = qz - __ldg(pp + 2);
-                  const float* pg = m.points + 3 * (size_t)s_gidx[tid * K + k];  // what dist2 was measured to
-                  dx[k] = qx - __ldg(pg);
-                  dy[k] = qy - __ldg(pg + 1);
-                  dz[k] = qz - __ldg(pg + 2);
+                if (lks[k] >= 0) {
+                  const float ux = qx - lpx[k], uy = qy - lpy[k], uz = qz - lpz[k];
+                  dx[k] = qx - gpx[k];  // what dist2 was measured to
+                  dy[k] = qy - gpy[k];
+                  dz[k] = qz - gpz[k];
                   float nx = ux, ny = uy, nz = uz, r0 = gn0, r1 = gn1, r2 = gn2;
                   if (m.after_pgo) {
-                    const float* qq = m.nb_orient + 4 * (size_t)lk;
-                    const float a = __ldg(qq), b = __ldg(qq + 1), cc = __ldg(qq + 2), dd = __ldg(qq + 3);
-                    quat_rotate_passive(a, b, cc, dd, ux, uy, uz, nx, ny, nz);
-                    quat_rotate_active(a, b, cc, dd, gn0, gn1, gn2, r0, r1, r2);
+                    quat_rotate_passive(qt[k].x, qt[k].y, qt[k].z, qt[k].w, ux, uy, uz, nx, ny, nz);
+                    quat_rotate_active(qt[k].x, qt[k].y, qt[k].z, qt[k].w, gn0, gn1, gn2, r0, r1, r2);
                   }
                   wk[k] = s_w[tid * K + k];
                   ak[k] = s_a[tid * K + k] + gn0 * nx + gn1 * ny + gn2 * nz;

@@ -72,6 +72,18 @@ class MapHandle:
         v.after_pgo = int(bool(after_pgo))
         if time_filter and (travel_dist is None or cur_ts >= travel_dist.shape[0]):
             raise RuntimeError("time filter needs travel_dist[cur_ts]")
+        # packed 32-byte search records {x, y, z, travel(ts_create), id bits, 0, 0, 0}
+        n_g = points.shape[0]
+        rec = torch.zeros((n_g, 8), dtype=torch.float32, device=points.device)
+        if n_g > 0:
+            rec[:, :3] = points
+            if time_filter:
+                rec[:, 3] = travel_dist[ts_create.long()]
+            ids = global2local[:n_g] if global2local is not None else torch.arange(n_g, dtype=torch.int32,
+                                                                                  device=points.device)
+            rec[:, 4] = ids.contiguous().view(torch.float32)
+        self.keep["search_rec"] = rec
+        v.search_rec = _ptr(rec, torch.float32)
         self.view = v
         self.device = points.device
 
