@@ -196,20 +196,37 @@ int pinb200_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_
 
 /* K4 -- registration: validity mask, Geman-McClure weights, and the 6x6 normal
  * equations of point-to-implicit registration accumulated in one pass, then
- * solved on device.  Replaces utils/tracker.py:409-524 (registration_step) and
- * :652-679 (implicit_reg).  Inputs are per source point.
+ * solved on device.  Replaces utils/tracker.py:409-524 (registration_step),
+ * :652-679 (implicit_reg) and :699-744 (implicit_color_reg).  Inputs are per source point.
+ *  colour (all three NULL when unused): color_obs [N,Cc] measured colours, color_pred [N,Cc] and
+ *    color_grad [N,Cc,3] from the colour head; Cc == 3 is converted to intensity
+ *    0.299 R + 0.587 G + 0.114 B (utils/tools.py:408); color_mode 1 = consistency weight
+ *    exp(-mean|obs-pred|) on every point (tracker.py:509-514), 2 = photometric term
+ *    N += w_photo J_c^T W J_c, g += w_photo (-J_c^T W r_c) (tracker.py:720-730)
  *  sums [64] fp64 workspace/outputs (zeroed by the call):
- *    [0..35] J^T W J (row-major 6x6, unnormalised w), [36..41] -J^T W r,
- *    [42] sum w, [43] sum |r|, [44] valid count, [45] sum w r^2
+ *    [0..35] J^T W J (row-major 6x6, unnormalised w, colour term included), [36..41] -J^T W r,
+ *    [42] sum w, [43] sum |r|, [44] valid count, [45] sum w r^2, [46] sum |r_colour|
  *  result [32] fp64: [0..15] delta T (4x4 row-major), [16] valid count,
- *    [17] mean |r| in cm, [18..20] eigen-proxy: diag of normalised N[3:,3:], [21] w r^2 mean
+ *    [17] mean |r| in cm, [18..20] eigenvalues of the normalised N[3:,3:], [21] mean(w r^2),
+ *    [22..27] normalised g, [28] mean |r_colour|
  *  If t_inout != NULL (device 4x4 fp64) it is updated in place: T <- delta_T @ T
  *  (tracker.py:147). */
 int pinb200_gn_step(const float* xyz, const float* sdf, const float* grad, const float* sdf_std,
                     const int32_t* nn_count, const float* sdf_label, const float* normals, int64_t n,
                     int32_t min_nn, float min_grad_norm, float max_grad_norm, float max_sdf_std,
-                    float gm_dist, float gm_grad, float lm_lambda, double* sums, double* result,
+                    float gm_dist, float gm_grad, float lm_lambda, const float* color_obs,
+                    const float* color_pred, const float* color_grad, int32_t color_channels,
+                    int32_t color_mode, float w_photo, double* sums, double* result,
                     double* t_inout, void* stream);
+
+/* Colour head of the training loss (utils/mapper.py:804-812, utils/loss.py:31-41): L1 between the predicted and
+ * the measured colour on surface samples (|sdf_label| < surface_range), mean over (n_surface x Cc) elements,
+ * times weight_i.  n_surface is read from the device (count computed by the caller without a sync).
+ * Writes d loss / d colour [n, Cc] (zero off-surface), adds the unweighted loss to *loss. */
+int pinb200_color_loss(const float* color_pred, const float* color_label, const float* sdf_label,
+                       const float* weight, int64_t n, int32_t color_channels, float surface_range,
+                       int32_t loss_weight_on, float weight_i, float grad_scale, const float* n_surface,
+                       float* dloss_dcolor, float* loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -559,6 +559,29 @@ def implicit_reg(points, sdf_grad, sdf_residual, weight, lm_lambda=0.0):
     return tm, n_raw, g
 
 
+def color_to_intensity(c):
+    """utils/tools.py:408-410."""
+    return (0.299 * c[:, 0] + 0.587 * c[:, 1] + 0.114 * c[:, 2]).unsqueeze(1)
+
+
+def implicit_color_reg(points, sdf_grad, sdf_residual, color_grad, color_residual, weight, w_photo, lm_lambda):
+    """utils/tracker.py:699-744.  color_grad [N,Cc,3], color_residual [N,Cc] (intensity: Cc=1)."""
+    jg = torch.cat([torch.linalg.cross(points, sdf_grad), sdf_grad], -1)
+    n_mat = jg.T @ (weight * jg)
+    g = -(jg * weight).T @ sdf_residual
+    for i in range(color_residual.shape[1]):
+        jc = torch.cat([torch.linalg.cross(points, color_grad[:, i, :]), color_grad[:, i]], -1)
+        n_mat = n_mat + w_photo * (jc.T @ (weight * jc))
+        g = g + w_photo * (-(jc * weight).T @ color_residual[:, i])
+    n_raw = n_mat.clone()
+    n_mat = n_mat + lm_lambda * torch.diag(torch.diag(n_mat))
+    t = torch.linalg.inv(n_mat.to(torch.float64)) @ g.to(torch.float64)
+    tm = torch.eye(4, device=points.device, dtype=torch.float64)
+    tm[:3, :3] = expmap(t[:3])
+    tm[:3, 3] = t[3:]
+    return tm, n_raw, g
+
+
 def registration_step(
     points,
     sdf_pred,
@@ -574,8 +597,14 @@ def registration_step(
     gm_grad: Optional[float],
     lm_lambda: float,
     normals: Optional[torch.Tensor] = None,
+    colors: Optional[torch.Tensor] = None,
+    color_pred: Optional[torch.Tensor] = None,
+    color_grad: Optional[torch.Tensor] = None,
+    photo_loss_on: bool = False,
+    consist_weight_on: bool = True,
+    w_photo: float = 0.01,
 ):
-    """utils/tracker.py:409-546 (geometry-only branch, no colour)."""
+    """utils/tracker.py:409-546 (geometry, colour-consistency weight, photometric term)."""
     grad_norm = sdf_grad.norm(dim=-1, keepdim=True).squeeze()
     grad_unit = sdf_grad / grad_norm.unsqueeze(-1)
     mask = nn_count >= min_nn
@@ -602,13 +631,30 @@ def registration_step(
         if normals is None
         else (0.5 + torch.abs((normals[valid] * grad_unit[valid]).sum(dim=1))).unsqueeze(1)
     )
-    w = w_res * w_grad * w_normal
+    w_color = 1.0
+    col_res = None
+    if colors is not None:
+        c_obs, c_prd = colors[valid], color_pred[valid]
+        if c_obs.shape[1] == 3:
+            c_obs, c_prd = color_to_intensity(c_obs), color_to_intensity(c_prd)
+        if photo_loss_on:
+            cg = color_grad[valid]
+            if cg.shape[1] == 3:
+                cg = color_to_intensity(cg)  # [Nv,1,3]: linear in the channel dimension
+            col_res = c_prd - c_obs
+        elif consist_weight_on:
+            w_color = torch.exp(-torch.mean(torch.abs(c_obs - c_prd), dim=-1)).unsqueeze(1)
+    w = w_res * w_grad * w_normal * w_color
     if not isinstance(w, float):
         w = w / (2.0 * torch.mean(w))
     else:
         w = torch.full((nv, 1), w, device=points.device)
-    tm, n_raw, g = implicit_reg(vp, sg, res, w, lm_lambda)
+    if col_res is not None:
+        tm, n_raw, g = implicit_color_reg(vp, sg, res, cg, col_res, w, w_photo, lm_lambda)
+    else:
+        tm, n_raw, g = implicit_reg(vp, sg, res, w, lm_lambda)
     return {
+        "color_residual_mean": None if col_res is None else torch.mean(torch.abs(col_res)).item(),
         "T": tm,
         "N": n_raw,
         "g": g,

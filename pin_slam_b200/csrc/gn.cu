@@ -19,11 +19,13 @@ __global__ void __launch_bounds__(256) gn_accumulate_kernel(
     const float* __restrict__ xyz, const float* __restrict__ sdf, const float* __restrict__ grad,
     const float* __restrict__ sdf_std, const int32_t* __restrict__ nn_count, const float* __restrict__ sdf_label,
     const float* __restrict__ normals, long long n, int min_nn, float min_gn, float max_gn, float max_std,
-    float gm_dist, float gm_grad, double* __restrict__ sums) {
-  // 21 upper-triangular entries of N, 6 of g, 4 scalars
-  float acc[31];
+    float gm_dist, float gm_grad, const float* __restrict__ c_obs, const float* __restrict__ c_pred,
+    const float* __restrict__ c_grad, int cc, int color_mode, float w_photo, double* __restrict__ sums) {
+  // 21 upper-triangular entries of N, 6 of g, 5 scalars
+  constexpr int NA = 32;
+  float acc[NA];
 #pragma unroll
-  for (int i = 0; i < 31; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gx = grad[3 * i], gy = grad[3 * i + 1], gz = grad[3 * i + 2];
     const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
@@ -46,6 +48,32 @@ __global__ void __launch_bounds__(256) gn_accumulate_kernel(
       const float inv = 1.f / gn;
       w *= 0.5f + fabsf(normals[3 * i] * gx * inv + normals[3 * i + 1] * gy * inv + normals[3 * i + 2] * gz * inv);
     }
+    // colour: intensity of the measured / predicted colour and of the colour gradient (tools.py:408)
+    float rc = 0.f, cgx = 0.f, cgy = 0.f, cgz = 0.f;
+    if (color_mode) {
+      float io, ip;
+      if (cc == 3) {
+        const float k0 = 0.299f, k1 = 0.587f, k2 = 0.114f;
+        io = k0 * c_obs[3 * i] + k1 * c_obs[3 * i + 1] + k2 * c_obs[3 * i + 2];
+        ip = k0 * c_pred[3 * i] + k1 * c_pred[3 * i + 1] + k2 * c_pred[3 * i + 2];
+        if (c_grad) {
+          const float* g3 = c_grad + 9 * i;
+          cgx = k0 * g3[0] + k1 * g3[3] + k2 * g3[6];
+          cgy = k0 * g3[1] + k1 * g3[4] + k2 * g3[7];
+          cgz = k0 * g3[2] + k1 * g3[5] + k2 * g3[8];
+        }
+      } else {
+        io = c_obs[i * cc];
+        ip = c_pred[i * cc];
+        if (c_grad) {
+          cgx = c_grad[(i * cc) * 3];
+          cgy = c_grad[(i * cc) * 3 + 1];
+          cgz = c_grad[(i * cc) * 3 + 2];
+        }
+      }
+      rc = ip - io;
+      if (color_mode == 1) w *= expf(-fabsf(io - ip));  // consistency weight (tracker.py:509-514)
+    }
     // J = [p x g, g]  (tracker.py:652-655)
     float J[6];
     J[0] = py * gz - pz * gy;
@@ -65,20 +93,41 @@ __global__ void __launch_bounds__(256) gn_accumulate_kernel(
       }
       acc[21 + a] = fmaf(-wa, r, acc[21 + a]);
     }
+    if (color_mode == 2) {  // photometric term (tracker.py:720-730)
+      float Jc[6];
+      Jc[0] = py * cgz - pz * cgy;
+      Jc[1] = pz * cgx - px * cgz;
+      Jc[2] = px * cgy - py * cgx;
+      Jc[3] = cgx;
+      Jc[4] = cgy;
+      Jc[5] = cgz;
+      int e2 = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const float wa = w_photo * w * Jc[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) {
+          acc[e2] = fmaf(wa, Jc[b], acc[e2]);
+          ++e2;
+        }
+        acc[21 + a] = fmaf(-wa, rc, acc[21 + a]);
+      }
+    }
     acc[27] += w;
     acc[28] += fabsf(r);
     acc[29] += 1.f;
     acc[30] = fmaf(w * r, r, acc[30]);
+    acc[31] += fabsf(rc);
   }
-  __shared__ float s_red[8][31];
+  __shared__ float s_red[8][NA];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < 31; ++i) {
+  for (int i = 0; i < NA; ++i) {
     const float v = warp_sum(acc[i]);
     if (lane == 0) s_red[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 31) {
+  if (threadIdx.x < NA) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)s_red[w][threadIdx.x];
     // scatter the packed triangle back to the full symmetric layout
@@ -206,6 +255,7 @@ __global__ void gn_solve_kernel(const double* __restrict__ sums, float lm_lambda
     sym3_eig(tr, result + 18);            // eigenvalues of N_raw[3:,3:] (tracker.py:685-686)
     result[21] = sums[45] * sc / cnt;     // mean(w r^2) (tracker.py:692)
     for (int i = 0; i < 6; ++i) result[22 + i] = g[i];
+    result[28] = sums[46] / cnt;          // mean |colour residual| (tracker.py:531)
   }
   for (int i = 0; i < 16; ++i) result[i] = dT[i];
   if (t_inout) {  // T <- dT @ T (tracker.py:147)
@@ -228,10 +278,18 @@ using namespace pinb;
 extern "C" int pinb200_gn_step(const float* xyz, const float* sdf, const float* grad, const float* sdf_std,
                                const int32_t* nn_count, const float* sdf_label, const float* normals, int64_t n,
                                int32_t min_nn, float min_grad_norm, float max_grad_norm, float max_sdf_std,
-                               float gm_dist, float gm_grad, float lm_lambda, double* sums, double* result,
-                               double* t_inout, void* stream) {
+                               float gm_dist, float gm_grad, float lm_lambda, const float* color_obs,
+                               const float* color_pred, const float* color_grad, int32_t color_channels,
+                               int32_t color_mode, float w_photo, double* sums, double* result, double* t_inout,
+                               void* stream) {
   if (!xyz || !sdf || !grad || !nn_count || !sums || !result || n < 0) {
     set_error("gn_step: null argument");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (color_mode < 0 || color_mode > 2 ||
+      (color_mode && (!color_obs || !color_pred || color_channels < 1 || (color_mode == 2 && !color_grad)))) {
+    set_error("gn_step: colour mode %d needs color_obs/color_pred (and color_grad for the photometric term)",
+              color_mode);
     return PINB200_ERR_BAD_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -243,7 +301,8 @@ extern "C" int pinb200_gn_step(const float* xyz, const float* sdf, const float* 
   if (n > 0) {
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 2);
     gn_accumulate_kernel<<<grid, 256, 0, st>>>(xyz, sdf, grad, sdf_std, nn_count, sdf_label, normals, n, min_nn,
-                                               min_grad_norm, max_grad_norm, max_sdf_std, gm_dist, gm_grad, sums);
+                                               min_grad_norm, max_grad_norm, max_sdf_std, gm_dist, gm_grad, color_obs, color_pred,
+                                               color_grad, color_channels, color_mode, w_photo, sums);
     int rc = check_launch("gn_accumulate_kernel");
     if (rc) return rc;
   }

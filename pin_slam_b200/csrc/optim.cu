@@ -78,9 +78,52 @@ __global__ void mapping_loss_kernel(const float* __restrict__ sdf, const float* 
   }
 }
 
+// L1 colour loss on surface samples (utils/mapper.py:804-812, utils/loss.py:31-41)
+__global__ void color_loss_kernel(const float* __restrict__ pred, const float* __restrict__ lab,
+                                  const float* __restrict__ sdf_label, const float* __restrict__ weight, long long n,
+                                  int cc, float surf, int weighted, float weight_i, float gscale,
+                                  const float* __restrict__ n_surface, float* __restrict__ dl,
+                                  float* __restrict__ loss) {
+  const float cnt = fmaxf(*n_surface, 1.f) * (float)cc;
+  float acc = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n * cc; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / cc;
+    float g = 0.f;
+    if (fabsf(sdf_label[i]) < surf) {
+      const float w = weighted ? fabsf(weight[i]) : 1.f;
+      const float d = pred[e] - lab[e];
+      acc += w * fabsf(d);
+      g = gscale * weight_i * w * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / cnt;
+    }
+    dl[e] = g;
+  }
+  if (loss) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc / cnt);
+  }
+}
+
 }  // namespace pinb
 
 using namespace pinb;
+
+extern "C" int pinb200_color_loss(const float* color_pred, const float* color_label, const float* sdf_label,
+                                  const float* weight, int64_t n, int32_t color_channels, float surface_range,
+                                  int32_t loss_weight_on, float weight_i, float grad_scale, const float* n_surface,
+                                  float* dloss_dcolor, float* loss, void* stream) {
+  if (!color_pred || !color_label || !sdf_label || !n_surface || !dloss_dcolor || color_channels < 1 ||
+      (loss_weight_on && !weight)) {
+    set_error("color_loss: null argument");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  const long long work = n * color_channels;
+  const int grid = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 4);
+  color_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(color_pred, color_label, sdf_label, weight, n,
+                                                            color_channels, surface_range, loss_weight_on, weight_i,
+                                                            grad_scale, n_surface, dloss_dcolor, loss);
+  return check_launch("color_loss_kernel");
+}
 
 extern "C" int pinb200_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                                  double beta1, double beta2, double eps, double weight_decay, int32_t step,

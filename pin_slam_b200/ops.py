@@ -253,7 +253,8 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_de
 
 
 def gn_step(xyz, sdf, grad, sdf_std, nn_count, *, min_nn, min_grad_norm, max_grad_norm, max_sdf_std, gm_dist,
-            gm_grad, lm_lambda, sdf_label=None, normals=None, t_inout=None, sums=None, result=None):
+            gm_grad, lm_lambda, sdf_label=None, normals=None, t_inout=None, sums=None, result=None, color_obs=None,
+            color_pred=None, color_grad=None, color_mode=0, w_photo=0.0):
     """K4.  Returns (result[32] f64 device tensor, sums[64] f64 device tensor)."""
     lib = _lib.load()
     dev = xyz.device
@@ -266,8 +267,23 @@ def gn_step(xyz, sdf, grad, sdf_std, nn_count, *, min_nn, min_grad_norm, max_gra
                              _ptr(sdf_label, torch.float32), _ptr(normals, torch.float32), xyz.shape[0], int(min_nn),
                              float(min_grad_norm), float(max_grad_norm), float(max_sdf_std),
                              float(gm_dist or 0.0), float(gm_grad or 0.0), float(lm_lambda),
-                             _ptr(sums, torch.float64), _ptr(result, torch.float64), _ptr(t_inout, torch.float64),
+                             _ptr(color_obs, torch.float32), _ptr(color_pred, torch.float32),
+                             _ptr(color_grad, torch.float32), 0 if color_obs is None else int(color_obs.shape[1]),
+                             int(color_mode), float(w_photo), _ptr(sums, torch.float64), _ptr(result, torch.float64), _ptr(t_inout, torch.float64),
                              _stream())
     _lib.check(rc, "pinb200_gn_step")
     _count(2)
     return result, sums
+
+
+def color_loss(color_pred, color_label, sdf_label, weight, surface_range, loss_weight_on, weight_i, n_surface, dloss,
+               loss, grad_scale: float = 1.0):
+    lib = _lib.load()
+    n, cc = color_pred.shape
+    rc = lib.pinb200_color_loss(_ptr(color_pred, torch.float32), _ptr(color_label, torch.float32),
+                                _ptr(sdf_label, torch.float32), _ptr(weight, torch.float32), n, cc, float(surface_range),
+                                int(bool(loss_weight_on)), float(weight_i), float(grad_scale),
+                                _ptr(n_surface, torch.float32), _ptr(dloss, torch.float32), _ptr(loss, torch.float32),
+                                _stream())
+    _lib.check(rc, "pinb200_color_loss")
+    _count()

@@ -300,8 +300,6 @@ class Mapper:
     def mapping(self, iter_count):
         """Reference: utils/mapper.py:600-844."""
         cfg = self.config
-        if cfg.color_on and cfg.weight_i > 0:
-            raise NotImplementedError("colour-head training is not implemented in the B200 path yet")
         if not (cfg.main_loss_type == "bce" and cfg.numerical_grad and cfg.opt_adam):
             raise NotImplementedError("B200 mapper supports the reference defaults: bce loss, numerical Eikonal, Adam")
         iter_count = max(1, iter_count + self.adaptive_iter_offset)
@@ -314,13 +312,27 @@ class Mapper:
         flat = self.sdf_mlp.flat_parameters()  # decoder weights live in (and are views of) this vector
         n_dec = flat.numel()
         m_rows = npm.local_count()
-        # one contiguous reduction buffer: [feature grads | decoder grads | certainty increments]
-        red = torch.zeros(feat.numel() + n_dec + m_rows, device=dev, dtype=torch.float32)
-        gfeat = red[: feat.numel()].view_as(feat)
-        gdec = red[feat.numel(): feat.numel() + n_dec]
-        dcert = red[feat.numel() + n_dec:]
+        color_on = bool(cfg.color_on and cfg.weight_i > 0 and self.color_mlp is not None and self.color_pool is not None)
+        cfeat = npm.local_color_features.data if color_on else None
+        cflat = self.color_mlp.flat_parameters() if color_on else None
+        n_cf = cfeat.numel() if color_on else 0
+        n_cd = cflat.numel() if color_on else 0
+        train_cdec = color_on and any(p.requires_grad for p in self.color_mlp.parameters())
+        # one contiguous reduction buffer:
+        # [feature grads | decoder grads | colour-feature grads | colour-decoder grads | certainty increments]
+        red = torch.zeros(feat.numel() + n_dec + n_cf + n_cd + m_rows, device=dev, dtype=torch.float32)
+        o0 = feat.numel()
+        gfeat = red[:o0].view_as(feat)
+        gdec = red[o0: o0 + n_dec]
+        gcfeat = red[o0 + n_dec: o0 + n_dec + n_cf].view_as(cfeat) if color_on else None
+        gcdec = red[o0 + n_dec + n_cf: o0 + n_dec + n_cf + n_cd] if color_on else None
+        dcert = red[o0 + n_dec + n_cf + n_cd:]
         mf, vf = torch.zeros_like(feat), torch.zeros_like(feat)
         md, vd = torch.zeros_like(flat), torch.zeros_like(flat)
+        if color_on:
+            mcf, vcf = torch.zeros_like(cfeat), torch.zeros_like(cfeat)
+            mcd, vcd = torch.zeros_like(cflat), torch.zeros_like(cflat)
+            closs = torch.zeros(1, device=dev)
         losses = torch.zeros(2, device=dev)
         dec_step = cfg.gradient_decimation
         eik_on = cfg.ekional_loss_on and cfg.weight_e > 0
@@ -331,7 +343,7 @@ class Mapper:
             shifts[2 * a + 1, 0, a] = -eps_num
         out = self._work
         for it in range(iter_count):
-            coord, label, ts, _, _, _, weight = self.get_batch(global_coord=not self.ba_done_flag)
+            coord, label, ts, _, _, color_label, weight = self.get_batch(global_coord=not self.ba_done_flag)
             if self.ba_done_flag:
                 tf = self.used_poses[ts.long()].to(coord)
                 coord = (tf[:, :3, :3] @ coord.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
@@ -347,7 +359,8 @@ class Mapper:
                 cert_before = npm.local_point_certainties.clone()
             o = ops.query_sdf(npm.map_handle(True), self.sdf_mlp.handle(), rows, nn_k=cfg.query_nn_k,
                               weighted_first=cfg.weighted_first, training_mode=True, training_rows=n, need_grad=False,
-                              query_ts=ts.contiguous(), save_knn=True, out=out)
+                              query_ts=ts.contiguous(), save_knn=True, out=out,
+                              color_dec=self.color_mlp.handle(sigmoid_out=True) if color_on else None)
             dl = out.get("dl")
             if dl is None or dl.shape[0] != rows.shape[0]:
                 dl = out["dl"] = torch.empty(rows.shape[0], device=dev)
@@ -356,6 +369,14 @@ class Mapper:
                              grad_scale=1.0 / world)
             ops.train_backward(npm.map_handle(True), self.sdf_mlp.handle(), feat, rows, o["knn_idx"], o["knn_weight"],
                                dl, cfg.weighted_first, gfeat, gdec)
+            if color_on:  # colour head: L1 on surface samples (mapper.py:804-812), its own backward through K2
+                label_c, weight_c = label.contiguous(), weight.contiguous()
+                n_surf = (label_c.abs() < cfg.surface_sample_range_m).sum().float().reshape(1)
+                dlc = torch.empty((n, self.color_mlp.out_dim), device=dev)
+                ops.color_loss(o["color"][:n], color_label.contiguous(), label_c, weight_c, cfg.surface_sample_range_m,
+                               cfg.loss_weight_on, cfg.weight_i, n_surf, dlc, closs, grad_scale=1.0 / world)
+                ops.train_backward(npm.map_handle(True), self.color_mlp.handle(sigmoid_out=True), cfeat, rows[:n],
+                                   o["knn_idx"][:n], o["knn_weight"][:n], dlc, cfg.weighted_first, gcfeat, gcdec)
             if dist_on:
                 allreduce_training_state(red, dcert, cert_before, npm.local_point_certainties,
                                          npm.local_point_ts_update)
@@ -364,6 +385,12 @@ class Mapper:
             else:
                 gdec.zero_()
             ops.adam_step(feat, gfeat, mf, vf, cfg.lr, 0.9, 0.99, cfg.adam_eps, cfg.weight_decay, it + 1)
+            if color_on:
+                if train_cdec:
+                    ops.adam_step(cflat, gcdec, mcd, vcd, cfg.lr, 0.9, 0.99, cfg.adam_eps, 0.0, it + 1)
+                else:
+                    gcdec.zero_()
+                ops.adam_step(cfeat, gcfeat, mcf, vcf, cfg.lr, 0.9, 0.99, cfg.adam_eps, cfg.weight_decay, it + 1)
             self.total_iter += 1
         self.last_losses = losses
         npm.assign_local_to_global()

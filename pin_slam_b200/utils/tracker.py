@@ -56,8 +56,17 @@ class Tracker:
                 o.get("color_grad"), None, mask, o["certainty"] if query_certainty else None,
                 o["sdf_std"] if query_sdf else None)
 
+    def _color_setup(self, source_colors):
+        """(colour decoder, need colour gradient, K4 colour mode) for this call (tracker.py:385-386, 493-514)."""
+        cfg = self.config
+        if source_colors is None or not cfg.color_on or self.color_mlp is None:
+            return None, False, 0
+        if cfg.photometric_loss_on:
+            return self.color_mlp, True, 2
+        return self.color_mlp, False, (1 if cfg.consist_wieght_on else 0)
+
     def _gn(self, xyz, o, source_normals, source_sdf, min_grad_norm, max_grad_norm, gm_dist, gm_grad, lm_lambda,
-            t_dev):
+            t_dev, source_colors=None, color_mode=0):
         if self._sums is None:
             self._sums = torch.empty(64, dtype=torch.float64, device=xyz.device)
             self._result = torch.empty(32, dtype=torch.float64, device=xyz.device)
@@ -66,19 +75,22 @@ class Tracker:
                            min_nn=cfg.track_mask_query_nn_k, min_grad_norm=min_grad_norm,
                            max_grad_norm=max_grad_norm, max_sdf_std=cfg.surface_sample_range_m * cfg.max_sdf_std_ratio,
                            gm_dist=gm_dist, gm_grad=gm_grad, lm_lambda=lm_lambda, sdf_label=source_sdf,
-                           normals=source_normals, t_inout=t_dev, sums=self._sums, result=self._result)
+                           normals=source_normals, t_inout=t_dev, sums=self._sums, result=self._result,
+                           color_obs=None if not color_mode else source_colors[:, : cfg.color_channel].contiguous(),
+                           color_pred=o.get("color") if color_mode else None,
+                           color_grad=o.get("color_grad") if color_mode == 2 else None, color_mode=color_mode,
+                           w_photo=cfg.photometric_loss_weight)
 
     def registration_step(self, points, normals, sdf_labels, colors, min_grad_norm, max_grad_norm, GM_dist=None,
                           GM_grad=None, lm_lambda=0.0, vis_weight_pc=False):
         """One GN/LM step on already transformed points (reference: utils/tracker.py:367-611).
         Returns (T, cov_mat, eigenvalues, weight_point_cloud, valid_points, sdf_residual_mean_cm,
         color_residual_mean)."""
-        if colors is not None and self.config.color_on and self.config.photometric_loss_on:
-            raise NotImplementedError("photometric registration term is not implemented in the B200 path yet")
+        cdec, cgrad, cmode = self._color_setup(colors)
         o = self.neural_points.query_sdf(points.contiguous(), self.sdf_mlp, query_locally=self.reg_local_map,
-                                         need_grad=True, out=self._out)
+                                         need_grad=True, color_decoder=cdec, color_grad=cgrad, out=self._out)
         res, sums = self._gn(points.contiguous(), o, normals, sdf_labels, min_grad_norm, max_grad_norm, GM_dist,
-                             GM_grad, lm_lambda, None)
+                             GM_grad, lm_lambda, None, colors, cmode)
         r = res.cpu().numpy()
         T = torch.tensor(r[:16].reshape(4, 4), dtype=torch.float64, device=points.device)
         gnorm = o["grad"].norm(dim=-1)
@@ -88,7 +100,7 @@ class Tracker:
         cov, eig = None, None
         if vis_weight_pc and r[16] >= 10:
             cov, eig = self._cov_eig(sums, r)
-        return T, cov, eig, None, points[valid], float(r[17]), None
+        return T, cov, eig, None, points[valid], float(r[17]), (float(r[28]) if cmode == 2 else None)
 
     @staticmethod
     def _cov_eig(sums, r):
@@ -105,8 +117,7 @@ class Tracker:
         """Reference: utils/tracker.py:43-225.  Returns (T [4,4] f64, cov_mat, weight_point_cloud, valid_flag)."""
         cfg = self.config
         dev = source_points.device
-        if source_colors is not None and cfg.color_on and cfg.photometric_loss_on:
-            raise NotImplementedError("photometric registration term is not implemented in the B200 path yet")
+        cdec, cgrad, cmode = self._color_setup(source_colors)
         T_dev = (torch.eye(4, dtype=torch.float64, device=dev) if init_pose is None
                  else init_pose.to(device=dev, dtype=torch.float64).clone().contiguous())
         gm_dist = cfg.reg_GM_dist_m if cfg.reg_GM_dist_m > 0 else None
@@ -123,9 +134,11 @@ class Tracker:
         res_cm, n_valid, i = 0.0, 0, 0
         for i in range(iter_n):
             o = self.neural_points.query_sdf(src, self.sdf_mlp, query_locally=self.reg_local_map, need_grad=True,
-                                             transform=T_dev, want_xyz=True, out=self._out)
+                                             transform=T_dev, want_xyz=True, color_decoder=cdec, color_grad=cgrad,
+                                             out=self._out)
             res, sums = self._gn(o["xyz"], o, source_normals, source_sdf, cfg.reg_min_grad_norm,
-                                 cfg.reg_max_grad_norm, gm_dist, gm_grad, cfg.reg_lm_lambda, T_dev)
+                                 cfg.reg_max_grad_norm, gm_dist, gm_grad, cfg.reg_lm_lambda, T_dev, source_colors,
+                                 cmode)
             r = res.cpu().numpy()  # the one host sync of the iteration
             n_valid, res_cm = int(r[16]), float(r[17])
             dT = r[:16].reshape(4, 4)
@@ -155,16 +168,19 @@ class Tracker:
             cov_mat = None
         return T, cov_mat, None, valid_flag
 
-    def track_fixed(self, source_points, init_pose, n_iter: int, source_normals=None, source_sdf=None):
+    def track_fixed(self, source_points, init_pose, n_iter: int, source_normals=None, source_sdf=None,
+                    source_colors=None):
         """Exactly `n_iter` GN iterations with NO host synchronisation at all (benchmark configuration
         "tracker GN (3 iters)"): the pose stays on the device and K4 updates it in place."""
         cfg = self.config
         T_dev = init_pose.to(dtype=torch.float64).clone().contiguous()
         src = source_points.contiguous()
+        cdec, cgrad, cmode = self._color_setup(source_colors)
         for _ in range(n_iter):
             o = self.neural_points.query_sdf(src, self.sdf_mlp, query_locally=self.reg_local_map, need_grad=True,
-                                             transform=T_dev, want_xyz=True, out=self._out)
+                                             transform=T_dev, want_xyz=True, color_decoder=cdec, color_grad=cgrad,
+                                             out=self._out)
             self._gn(o["xyz"], o, source_normals, source_sdf, cfg.reg_min_grad_norm, cfg.reg_max_grad_norm,
                      cfg.reg_GM_dist_m if cfg.reg_GM_dist_m > 0 else None,
-                     cfg.reg_GM_grad if cfg.reg_GM_grad > 0 else None, cfg.reg_lm_lambda, T_dev)
+                     cfg.reg_GM_grad if cfg.reg_GM_grad > 0 else None, cfg.reg_lm_lambda, T_dev, source_colors, cmode)
         return T_dev, self._result

@@ -241,6 +241,25 @@ def gen_query_fixture(kind, seed, weighted_first, after_pgo=False, color=False, 
                                       cfg.surface_sample_range_m * cfg.max_sdf_std_ratio,
                                       cfg.reg_GM_dist_m, cfg.reg_GM_grad, cfg.reg_lm_lambda], dtype=np.float64)
 
+    # a9/a11: registration with colour -- photometric term (implicit_color_reg) and consistency weight
+    if color:
+        g2 = torch.Generator().manual_seed(seed + 31)
+        src_col = torch.rand(q.shape[0], 3, generator=g2)
+        out["reg_color.source_colors"] = src_col.numpy()
+        min_gn, max_gn = 1e-6, 10.0  # sdf_scale is 0.0055 in the Replica config: random-decoder gradients are tiny
+        for tag, photo in (("photo", True), ("consist", False)):
+            cfg.photometric_loss_on = photo
+            T, _, _, _, valid_points, res_cm, col_res = trk.registration_step(
+                q.clone(), None, torch.zeros(q.shape[0]), src_col.clone(), min_gn, max_gn,
+                cfg.reg_GM_dist_m, cfg.reg_GM_grad, cfg.reg_lm_lambda, False)
+            out[f"reg_color.{tag}.T"] = T.numpy()
+            out[f"reg_color.{tag}.valid_count"] = np.int64(valid_points.shape[0])
+            out[f"reg_color.{tag}.residual_cm"] = np.float64(res_cm)
+            out[f"reg_color.{tag}.color_residual"] = np.float64(-1.0 if col_res is None else col_res)
+        out["reg_color.params"] = np.array([min_gn, max_gn, cfg.surface_sample_range_m * cfg.max_sdf_std_ratio,
+                                            cfg.reg_GM_dist_m, cfg.reg_GM_grad, cfg.reg_lm_lambda,
+                                            cfg.photometric_loss_weight], dtype=np.float64)
+
     # a4 training-mode side effects (certainty scatter_add, ts amax) on a copy
     ts = torch.full((q.shape[0],), int(npm.cur_ts), dtype=torch.int32)
     ts[::3] = int(npm.cur_ts) + 1
@@ -341,6 +360,10 @@ def gen_train_fixture(kind, seed, weighted_first, iters=3, bs=2048, color=False,
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "replica_query":  # regenerate a single fixture (the reference's map growth is not bit-reproducible
+        gen_query_fixture("replica", 5, weighted_first=True, color=True)  # run to run: duplicate-slot index_put)
+        sys.exit(0)
     gen_query_fixture("kitti", 1, weighted_first=False)
     gen_query_fixture("kitti", 2, weighted_first=True)
     gen_query_fixture("cfg2", 3, weighted_first=True)

@@ -21,6 +21,7 @@ pytestmark = pytest.mark.gpu
 
 QUERY_FIXTURES = ["query_kitti_nwf", "query_kitti_wf", "query_cfg2_wf", "query_cfg2_nwf_pgo", "query_replica_wf_color"]
 TRAIN_FIXTURES = ["train_kitti_nwf", "train_cfg2_wf"]
+TRAIN_FIXTURES_ALL = TRAIN_FIXTURES + ["train_replica_wf_color"]
 
 
 def ops():
@@ -249,6 +250,28 @@ def test_gn_step_matches_reference(name):
     np.testing.assert_allclose(T0.cpu().numpy(), res[:16].reshape(4, 4), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("mode", ["photo", "consist"])
+def test_gn_step_with_colour_matches_reference(mode):
+    """Photometric term (implicit_color_reg) and colour-consistency weight against the reference's
+    registration_step on the Replica-config fixture."""
+    fx = load_npz("query_replica_wf_color")
+    q = t(fx["q"])
+    mn, mx, max_std, gmd, gmg, lam, w_photo = [float(v) for v in fx["reg_color.params"]]
+    nn = torch.where(t(fx["trk.mask"]), 100, 0).to(torch.int32)
+    res, sums = ops().gn_step(q.cuda(), t(fx["trk.sdf"]).cuda(), t(fx["trk.grad"]).cuda(), t(fx["trk.sdf_std"]).cuda(),
+                              nn.cuda(), min_nn=1, min_grad_norm=mn, max_grad_norm=mx, max_sdf_std=max_std,
+                              gm_dist=gmd, gm_grad=gmg, lm_lambda=lam,
+                              color_obs=t(fx["reg_color.source_colors"]).cuda(), color_pred=t(fx["trk.color"]).cuda(),
+                              color_grad=t(fx["trk.color_grad"]).cuda(), color_mode=2 if mode == "photo" else 1,
+                              w_photo=w_photo)
+    r = res.cpu().numpy()
+    assert int(r[16]) == int(fx[f"reg_color.{mode}.valid_count"])
+    np.testing.assert_allclose(r[17], float(fx[f"reg_color.{mode}.residual_cm"]), rtol=1e-5)
+    if mode == "photo":
+        np.testing.assert_allclose(r[28], float(fx["reg_color.photo.color_residual"]), rtol=1e-5)
+    np.testing.assert_allclose(r[:16].reshape(4, 4), fx[f"reg_color.{mode}.T"], rtol=5e-4, atol=5e-5)
+
+
 def test_gn_step_too_few_points_gives_identity():
     n = 50
     z = torch.zeros(n, device="cuda")
@@ -349,7 +372,27 @@ def test_adam_matches_torch():
     np.testing.assert_allclose(pc.cpu().numpy(), ref.detach().numpy(), rtol=2e-6, atol=2e-7)
 
 
-@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def _flat_handle(dec, sigmoid_out=False):
+    """Decoder handle whose weights are views into ONE flat parameter vector (the layout K2 / K3 use)."""
+    flat = flat_decoder_params(dec).cuda()
+    off = 0
+    ws, bs = [], []
+    for w, b in dec.hidden:
+        ws.append(flat[off:off + w.numel()].view_as(w)); off += w.numel()
+        bs.append(flat[off:off + b.numel()].view_as(b)); off += b.numel()
+    wo = flat[off:off + dec.out[0].numel()].view_as(dec.out[0]); off += dec.out[0].numel()
+    bo = flat[off:off + dec.out[1].numel()].view_as(dec.out[1])
+    return flat, ops().DecoderHandle(ws, bs, wo, bo, out_scale=1.0 if sigmoid_out else dec.sdf_scale,
+                                     sigmoid_out=sigmoid_out)
+
+
+def _ref_flat(fx, name, dec):
+    return np.concatenate([fx[f"after.{name}.layers.{i}.{p}"].reshape(-1) for i in range(len(dec.hidden))
+                           for p in ("weight", "bias")] + [fx[f"after.{name}.lout.weight"].reshape(-1),
+                                                           fx[f"after.{name}.lout.bias"].reshape(-1)])
+
+
+@pytest.mark.parametrize("name", TRAIN_FIXTURES_ALL)
 def test_three_mapping_iterations_match_reference(name):
     """Mapper.mapping for 3 iterations: fused forward + loss + K2 + K3 vs the reference's post-step state."""
     fx = load_npz(name)
@@ -360,22 +403,33 @@ def test_three_mapping_iterations_match_reference(name):
     _, sdf_scale, weight_e, eps_num, lr, adam_eps, wd, *_ = [float(v) for v in fx["cfg.floats"]]
     mh = map_handle_from_oracle(m, True)
     feat = mh.keep["geo_feat"]
-    flat = flat_decoder_params(dec).cuda()
-    # decoder handle whose weights are views into the flat parameter vector (Adam updates them in place)
-    views, off = [], 0
-    ws, bs = [], []
-    for w, b in dec.hidden:
-        ws.append(flat[off:off + w.numel()].view_as(w)); off += w.numel()
-        bs.append(flat[off:off + b.numel()].view_as(b)); off += b.numel()
-    wo = flat[off:off + dec.out[0].numel()].view_as(dec.out[0]); off += dec.out[0].numel()
-    bo = flat[off:off + dec.out[1].numel()].view_as(dec.out[1])
-    dh = ops().DecoderHandle(ws, bs, wo, bo, out_scale=dec.sdf_scale)
+    flat, dh = _flat_handle(dec)
+    color = "map.color_features" in fx
     gfeat, gdec = torch.zeros_like(feat), torch.zeros_like(flat)
     mf, vf = torch.zeros_like(feat), torch.zeros_like(feat)
     md, vd = torch.zeros_like(flat), torch.zeros_like(flat)
+    if color:
+        cdec = decoder_from_fixture(fx, "color_mlp")
+        cflat, ch = _flat_handle(cdec, sigmoid_out=True)
+        cfeat = mh.keep["color_feat"]
+        gcfeat, gcdec = torch.zeros_like(cfeat), torch.zeros_like(cflat)
+        mcf, vcf, mcd, vcd = (torch.zeros_like(cfeat), torch.zeros_like(cfeat), torch.zeros_like(cflat),
+                              torch.zeros_like(cflat))
+        surf_range, weight_i = float(fx["cfg.floats"][7]), float(fx["cfg.floats"][8])
+    lw = bool(fx["cfg.loss_weight_on"])
     for it in range(int(fx["n_iters"])):
-        _cuda_train_iteration(mh, dh, fx, it, k, wf, sdf_scale, weight_e, eps_num, bool(fx["cfg.loss_weight_on"]),
-                              flat.numel(), gfeat, gdec)
+        _cuda_train_iteration(mh, dh, fx, it, k, wf, sdf_scale, weight_e, eps_num, lw, flat.numel(), gfeat, gdec)
+        if color:  # colour head on the sample rows (mapper.py:668-671, 804-812)
+            coord = t(fx[f"batch{it}.coord"]).cuda()
+            label, weight = t(fx[f"batch{it}.sdf_label"]).cuda(), t(fx[f"batch{it}.weight"]).cuda()
+            o = ops().query_sdf(mh, dh, coord, nn_k=k, weighted_first=wf, need_grad=False, color_dec=ch, save_knn=True)
+            n_surf = (label.abs() < surf_range).sum().float().reshape(1)
+            dlc = torch.empty_like(o["color"])
+            ops().color_loss(o["color"], t(fx[f"batch{it}.color"]).cuda(), label, weight, surf_range, lw, weight_i,
+                             n_surf, dlc, torch.zeros(1, device="cuda"))
+            ops().train_backward(mh, ch, cfeat, coord, o["knn_idx"], o["knn_weight"], dlc, wf, gcfeat, gcdec)
+            ops().adam_step(cflat, gcdec, mcd, vcd, lr, 0.9, 0.99, adam_eps, 0.0, it + 1)
+            ops().adam_step(cfeat, gcfeat, mcf, vcf, lr, 0.9, 0.99, adam_eps, wd, it + 1)
         ops().adam_step(flat, gdec, md, vd, lr, 0.9, 0.99, adam_eps, 0.0, it + 1)
         ops().adam_step(feat, gfeat, mf, vf, lr, 0.9, 0.99, adam_eps, wd, it + 1)
     torch.cuda.synchronize()
@@ -387,10 +441,10 @@ def test_three_mapping_iterations_match_reference(name):
         assert np.abs(a - b).max() <= max_abs
 
     close_frac(feat.cpu().numpy(), fx["after.local_geo_features"])
-    ref_flat = np.concatenate([fx[f"after.sdf_mlp.layers.{i}.{p}"].reshape(-1) for i in range(len(dec.hidden))
-                               for p in ("weight", "bias")] + [fx["after.sdf_mlp.lout.weight"].reshape(-1),
-                                                               fx["after.sdf_mlp.lout.bias"].reshape(-1)])
-    close_frac(flat.cpu().numpy(), ref_flat)
+    close_frac(flat.cpu().numpy(), _ref_flat(fx, "sdf_mlp", dec))
+    if color:
+        close_frac(cfeat.cpu().numpy(), fx["after.local_color_features"])
+        close_frac(cflat.cpu().numpy(), _ref_flat(fx, "color_mlp", cdec))
     np.testing.assert_allclose(mh.keep["certainty"].cpu().numpy(), fx["after.local_point_certainties"], rtol=1e-4,
                                atol=1e-4)
     assert np.array_equal(mh.keep["ts_update"].cpu().numpy(), fx["after.local_point_ts_update"])

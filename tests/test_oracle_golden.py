@@ -160,3 +160,21 @@ def test_mapping_iterations(name):
     if color:
         close_frac(m.local_color_features.detach(), fx["after.local_color_features"])
         close_frac(cdec.out[0].detach(), fx["after.color_mlp.lout.weight"])
+
+
+@pytest.mark.parametrize("mode", ["photo", "consist"])
+def test_registration_step_with_colour(mode):
+    """utils/tracker.py:493-542 + implicit_color_reg (:699-744) on the Replica-config fixture."""
+    fx = load_npz("query_replica_wf_color")
+    q = t(fx["q"])
+    mn, mx, max_std, gmd, gmg, lam, w_photo = [float(v) for v in fx["reg_color.params"]]
+    out = po.registration_step(
+        q, t(fx["trk.sdf"]), t(fx["trk.grad"]), t(fx["trk.sdf_std"]), torch.where(t(fx["trk.mask"]), 100, 0),
+        torch.zeros(q.shape[0]), 1, mn, mx, max_std, gmd, gmg, lam, colors=t(fx["reg_color.source_colors"]),
+        color_pred=t(fx["trk.color"]), color_grad=t(fx["trk.color_grad"]), photo_loss_on=(mode == "photo"),
+        w_photo=w_photo)
+    assert out["valid_count"] == int(fx[f"reg_color.{mode}.valid_count"])
+    close(out["residual_cm"], float(fx[f"reg_color.{mode}.residual_cm"]), 1e-6, 0)
+    if mode == "photo":
+        close(out["color_residual_mean"], float(fx["reg_color.photo.color_residual"]), 1e-6, 0)
+    close(out["T"], fx[f"reg_color.{mode}.T"], 2e-4, 2e-5)
