@@ -521,5 +521,5 @@ def test_dropin_query_feature_matches_fused_path():
         o = npm.query_sdf(q.detach(), dec, need_grad=True)
         assert torch.equal(cnt, o["nn_count"].long())
         assert_sdf_close(o["sdf"].cpu(), s.detach().cpu(), dec.sdf_scale)
-        assert_rel_close(o["grad"].cpu(), g.detach().cpu(), 2e-4, float(g.abs().mean()))
+        assert_rel_close(o["grad"].cpu(), g.detach().cpu(), 2e-4, float(g.detach().abs().mean()))
         np.testing.assert_allclose(o["certainty"].cpu().numpy(), cert.cpu().numpy(), rtol=1e-5, atol=1e-6)
