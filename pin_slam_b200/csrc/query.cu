@@ -19,13 +19,14 @@
 #include <algorithm>
 
 #include "mlp.cuh"
+#include "mlp_mma.cuh"
 
 namespace pinb {
 
 struct QueryLayout {  // float offsets into dynamic smem
-  DecSmem dec;
+  MmaDecSmem dec;
   int delta, warp0, warp_stride, n_warps;  // CTA-shared part, then n_warps per-warp blocks
-  int act, knn_idx, knn_gidx, knn_d2, knn_w, knn_a, q, out, nn, mask, total;  // offsets inside a warp block
+  int act, knn_idx, knn_gidx, knn_d2, knn_w, knn_a, q, out, dv, nn, mask, total;  // offsets inside a warp block
 };
 
 struct QueryParams {
@@ -53,7 +54,6 @@ struct QueryParams {
 // ---------------------------------------------------------------------------
 constexpr int GQ = 4;   // queries gathered concurrently by one warp
 constexpr int WT = 32;  // queries (= threads) per warp tile
-constexpr int WLD = 33; // leading dimension of the per-warp transposed activation tile (odd: conflict-free)
 constexpr int WPB = 12; // max warps per CTA (one CTA per SM); fewer if shared memory does not fit
 
 // FT >= 32: a neighbour row is FT/32 coalesced warp loads; FT < 32: 32/FT neighbour rows per warp load.
@@ -65,7 +65,7 @@ struct FeatMap {
 };
 
 // weighted_first: act[j][ql] = sum_k w_k f_k[j]  for the queries ql0 + 4*g (g < GQ)
-template <int FT>
+template <int FT, int LDX>
 __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ feat, int K, const int* s_idx,
                                                       const float* s_w, int lane, float* s_act, int ql0, int qpt) {
   using M = FeatMap<FT>;
@@ -97,20 +97,20 @@ __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ 
       for (int r = 0; r < M::R; ++r) acc[r % M::NJ] = fmaf(w[g][r], v[g][r], acc[r % M::NJ]);
       if (ql < qpt)
 #pragma unroll
-        for (int jj = 0; jj < M::NJ; ++jj) s_act[(32 * jj + lane) * WLD + ql] = acc[jj];
+        for (int jj = 0; jj < M::NJ; ++jj) s_act[ql * LDX + 32 * jj + lane] = acc[jj];
     } else {
       float a = 0.f;
 #pragma unroll
       for (int r = 0; r < M::R; ++r) a = fmaf(w[g][r], v[g][r], a);
 #pragma unroll
       for (int off = FT; off < 32; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
-      if (lane < FT && ql < qpt) s_act[lane * WLD + ql] = a;
+      if (lane < FT && ql < qpt) s_act[ql * LDX + lane] = a;
     }
   }
 }
 
 // decode-every-neighbour: act[j][ql*K + k] = f_k[j] (0 if invalid)
-template <int FT>
+template <int FT, int LDX>
 __device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
                                                   float* s_act, int ql0, int qpt, int sq0) {
   using M = FeatMap<FT>;
@@ -137,13 +137,13 @@ __device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat
     for (int r = 0; r < M::R; ++r) {
       const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
       const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
-      if (k < K && ql < qpt) s_act[col * WLD + ql * K + k] = v[g][r];
+      if (k < K && ql < qpt) s_act[(ql * K + k) * LDX + col] = v[g][r];
     }
   }
 }
 
 // a_k = <g_xbar[0..F), f_k> for the queries ql0 + 4*g  ->  s_a[ql*K + k]
-template <int FT>
+template <int FT, int LDX>
 __device__ __forceinline__ void feature_dots_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
                                                    const float* s_act, float* s_a, int ql0, int qpt) {
   using M = FeatMap<FT>;
@@ -170,7 +170,7 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
     if (FT >= 32) {
       float gx[M::NJ];
 #pragma unroll
-      for (int jj = 0; jj < M::NJ; ++jj) gx[jj] = s_act[(32 * jj + lane) * WLD + qs];
+      for (int jj = 0; jj < M::NJ; ++jj) gx[jj] = s_act[qs * LDX + 32 * jj + lane];
       float part[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -182,7 +182,7 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
       const int k = warp_reduce8_owner(lane);
       if ((lane & 3) == 0 && k < K && ql < qpt) s_a[ql * K + k] = tot;
     } else {
-      const float gxj = s_act[(lane % (FT >= 32 ? 32 : FT)) * WLD + qs];
+      const float gxj = s_act[qs * LDX + (lane % (FT >= 32 ? 32 : FT))];
 #pragma unroll
       for (int r = 0; r < M::R; ++r) {
         float a = gxj * v[g][r];
@@ -200,7 +200,10 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
 // ---------------------------------------------------------------------------
 template <int H, int FT>
 __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constant__ QueryParams p) {
-  constexpr int DP = (FT + 3 + 3) / 4 * 4;  // decoder input width padded to a multiple of 4
+  static_assert(H == 64, "the tensor-core decoder is written for hidden_dim 64");
+  constexpr int KP0 = (FT + 3 + 7) / 8 * 8;        // decoder input width padded to the MMA k-step
+  constexpr int KT0 = KP0 / 8;                     // k-steps of layer 0 == n-tiles of the input gradient
+  constexpr int LDX = (KP0 > H ? KP0 : H) + 4;     // row-major tile leading dimension (== 4 or 12 mod 32)
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const pinb200_map_view& m = p.map;
@@ -222,10 +225,11 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
   float* s_a = wsm + p.lay.knn_a;
   float* s_q = wsm + p.lay.q;
   float* s_out = wsm + p.lay.out;
+  float* s_dv = wsm + p.lay.dv;
   int* s_nn = reinterpret_cast<int*>(wsm + p.lay.nn);
   uint64_t* s_mask = reinterpret_cast<uint64_t*>(wsm + p.lay.mask);
 
-  stage_decoder(p.dec, p.lay.dec, smem, DP, need_grad);
+  stage_mma_decoder(p.dec, p.lay.dec, smem);
   if (!p.use_saved_knn) fill_probe_deltas(m, s_delta);
   __syncthreads();
 
@@ -322,10 +326,12 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
           }
         }
       }
-      if (wf) {  // the position part of the IDW-averaged decoder input; the tile row is this thread's column
-        s_act[(F + 0) * WLD + tid] = sx;
-        s_act[(F + 1) * WLD + tid] = sy;
-        s_act[(F + 2) * WLD + tid] = sz;
+      if (wf) {  // the position part of the IDW-averaged decoder input (this thread's tile row) + zero padding
+        s_act[tid * LDX + F + 0] = sx;
+        s_act[tid * LDX + F + 1] = sy;
+        s_act[tid * LDX + F + 2] = sz;
+#pragma unroll
+        for (int d = D; d < KP0; ++d) s_act[tid * LDX + d] = 0.f;
       }
       if (live && !p.is_color) {
         if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
@@ -366,9 +372,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
 
       // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
       if (wf) {
-        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_weighted_group<FT>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
+        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_weighted_group<FT, LDX>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
       } else {
-        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_rows_group<FT>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
+        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_rows_group<FT, LDX>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
         // neighbour vectors of the (query, k) rows: thread per row
         if (tid < used_rows) {
           const int ql = tid / K, k = tid - ql * K, sq = sq0 + ql;
@@ -384,78 +390,102 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
               quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
             }
           }
-          s_act[(F + 0) * WLD + tid] = nx;
-          s_act[(F + 1) * WLD + tid] = ny;
-          s_act[(F + 2) * WLD + tid] = nz;
+          s_act[tid * LDX + F + 0] = nx;
+          s_act[tid * LDX + F + 1] = ny;
+          s_act[tid * LDX + F + 2] = nz;
+#pragma unroll
+          for (int d = D; d < KP0; ++d) s_act[tid * LDX + d] = 0.f;
         } else {
-          for (int d = 0; d < D; ++d) s_act[d * WLD + tid] = 0.f;  // unused rows stay finite
+          for (int d = 0; d < KP0; ++d) s_act[tid * LDX + d] = 0.f;  // unused rows stay finite
         }
       }
       __syncwarp();
 
-      // ============ phase B: decoder forward (thread per row) ============
-      float* col = s_act + tid;
-      float h[H];
-      {
-        int n_in = D;
-        for (int l = 0; l < L; ++l) {
-          matvec_col<H, WLD>(smem + p.lay.dec.wt[l], smem + p.lay.dec.b[l], col, n_in, h);
-          s_mask[l * WT + tid] = activate<H>(h, leaky);
-          if (l < L - 1) store_col<H, WLD>(col, h, H);
-          n_in = H;
-        }
+      // ============ phase B: decoder on the tensor cores (warp-level 3xTF32 MMA) ============
+      float acc[2][8][4];
+      warp_gemm_3xtf32<KT0, 8, false, LDX>(acc, s_act, smem + p.lay.dec.whi[0], smem + p.lay.dec.wlo[0], p.lay.dec.ldw[0], lane);
+      s_mask[lane] = bias_act_frags<8>(acc, smem + p.lay.dec.b[0], leaky, lane);
+      for (int l = 1; l < L; ++l) {
+        __syncwarp();
+        store_frags<8, LDX>(s_act, acc, lane);
+        __syncwarp();
+        warp_gemm_3xtf32<8, 8, false, LDX>(acc, s_act, smem + p.lay.dec.whi[l], smem + p.lay.dec.wlo[l], p.lay.dec.ldw[l], lane);
+        s_mask[l * WT + lane] = bias_act_frags<8>(acc, smem + p.lay.dec.b[l], leaky, lane);
       }
-      float dval[4];  // d value / d pre-activation output, per channel (OC <= 4)
+      // output head(s): dot with w_out over the 64 hidden units; 4 lanes share a row
+      for (int c = 0; c < OC; ++c) {
+        const float* wo = smem + p.lay.dec.wout + c * H;
+        float part[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        dval[c] = 0.f;
-        if (c < OC) {
-          const float* wo = smem + p.lay.dec.wout + c * H;
-          float o = smem[p.lay.dec.bout + c];
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int j = 0; j < H; ++j) o = fmaf(wo[j], h[j], o);
-          float v;
-          if (p.dec.sigmoid_out) {
-            v = 1.f / (1.f + expf(-o));
-            dval[c] = v * (1.f - v);
-          } else {
-            v = o * p.dec.out_scale;
-            dval[c] = p.dec.out_scale;
+          for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) part[mt][e >> 1] = fmaf(acc[mt][nt][e], wo[frag_col(nt, e, lane)], part[mt][e >> 1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float v = part[mt][hh];
+            v += __shfl_xor_sync(FULL, v, 1);
+            v += __shfl_xor_sync(FULL, v, 2);
+            if ((lane & 3) == 0) {
+              const int row = mt * 16 + (lane >> 2) + 8 * hh;
+              const float o = v + smem[p.lay.dec.bout + c];
+              float val, dv;
+              if (p.dec.sigmoid_out) {
+                val = 1.f / (1.f + expf(-o));
+                dv = val * (1.f - val);
+              } else {
+                val = o * p.dec.out_scale;
+                dv = p.dec.out_scale;
+              }
+              s_out[row * OC + c] = val;
+              s_dv[row * 4 + c] = dv;
+            }
           }
-          s_out[tid * OC + c] = v;
-        }
       }
+      __syncwarp();
 
       // ======== per output channel: backward to the decoder input, then the IDW chain rule ========
       const int n_pass = need_grad ? OC : 1;
       for (int c = 0; c < n_pass; ++c) {
         if (need_grad) {
-          float g[H];
-          {
-            const float* wo = smem + p.lay.dec.wout + c * H;
+          const float* wo = smem + p.lay.dec.wout + c * H;
 #pragma unroll
-            for (int j = 0; j < H; ++j) g[j] = wo[j];
-            apply_mask<H>(g, s_mask[(L - 1) * WT + tid], leaky);
-          }
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[mt][nt][e] = wo[frag_col(nt, e, lane)];
+          mask_frags<8>(acc, s_mask[(L - 1) * WT + lane], leaky);
           for (int l = L - 1; l >= 1; --l) {
-            store_col<H, WLD>(col, g, H);
-            matvec_col<H, WLD>(smem + p.lay.dec.w[l], nullptr, col, H, g);
-            apply_mask<H>(g, s_mask[(l - 1) * WT + tid], leaky);
+            __syncwarp();
+            store_frags<8, LDX>(s_act, acc, lane);
+            __syncwarp();
+            warp_gemm_3xtf32<8, 8, true, LDX>(acc, s_act, smem + p.lay.dec.whi[l], smem + p.lay.dec.wlo[l], p.lay.dec.ldw[l], lane);
+            mask_frags<8>(acc, s_mask[(l - 1) * WT + lane], leaky);
           }
-          store_col<H, WLD>(col, g, H);
-          float gx[DP];
-          matvec_col<DP, WLD>(smem + p.lay.dec.w[0], nullptr, col, H, gx);
-          const float dv = c == 0 ? dval[0] : (c == 1 ? dval[1] : (c == 2 ? dval[2] : dval[3]));
+          __syncwarp();
+          store_frags<8, LDX>(s_act, acc, lane);
+          __syncwarp();
+          float gxa[2][KT0][4];
+          warp_gemm_3xtf32<8, KT0, true, LDX>(gxa, s_act, smem + p.lay.dec.whi[0], smem + p.lay.dec.wlo[0], p.lay.dec.ldw[0], lane);
 #pragma unroll
-          for (int d = 0; d < DP; ++d)
-            if (d < D) col[d * WLD] = gx[d] * dv;
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < KT0; ++nt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) gxa[mt][nt][e] *= s_dv[frag_row(mt, e, lane) * 4 + c];
+          __syncwarp();
+          store_frags<KT0, LDX>(s_act, gxa, lane);
         }
         __syncwarp();
 
         if (wf) {
           // ---- C1: a_k = <g_xbar, f_k> (warp per query, coalesced re-read of the K feature rows)
           if (need_grad) {
-            for (int ql0 = 0; ql0 < qpt; ql0 += GQ) feature_dots_group<FT>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
+            for (int ql0 = 0; ql0 < qpt; ql0 += GQ) feature_dots_group<FT, LDX>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
             __syncwarp();
           }
           // ---- C2: thread per query -- chain rule through the IDW weights, outputs
@@ -466,7 +496,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
             if (need_grad) {
               const int nn = s_nn[tid];
               const float qx = s_q[3 * tid], qy = s_q[3 * tid + 1], qz = s_q[3 * tid + 2];
-              const float gn0 = col[(F + 0) * WLD], gn1 = col[(F + 1) * WLD], gn2 = col[(F + 2) * WLD];
+              const float gn0 = s_act[tid * LDX + F + 0], gn1 = s_act[tid * LDX + F + 1], gn2 = s_act[tid * LDX + F + 2];
               float ak[KREG], wk[KREG], ck[KREG], dx[KREG], dy[KREG], dz[KREG];
               float abar = 0.f;
               // issue every neighbour load first (local position, global position, quaternion), then compute
@@ -580,8 +610,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
                 var = fmaf(wk * dm, dm, var);
                 if (need_grad) {
                   const int row = ql * K + k;
-                  float r0 = s_act[(F + 0) * WLD + row], r1 = s_act[(F + 1) * WLD + row],
-                        r2 = s_act[(F + 2) * WLD + row];
+                  float r0 = s_act[row * LDX + F + 0], r1 = s_act[row * LDX + F + 1], r2 = s_act[row * LDX + F + 2];
                   const float* pg = m.points + 3 * (size_t)s_gidx[sq * K + k];  // the point dist2 was measured to
                   const float dx = qx - __ldg(pg), dy = qy - __ldg(pg + 1), dz = qz - __ldg(pg + 2);
                   if (m.after_pgo) {
@@ -752,19 +781,19 @@ static int validate_map(const pinb200_map_view* m, bool need_feat) {
   return PINB200_OK;
 }
 
-static QueryLayout plan_layout(const QueryParams& p, int DP) {
+static QueryLayout plan_layout(const QueryParams& p, int KP0) {
   QueryLayout l{};
   const int H = p.dec.hidden_dim, K = p.opts.nn_k;
   int o = 0;
   l.delta = o;
   o += align4(p.map.n_probe);
-  l.dec = plan_decoder_smem(p.dec, DP, p.opts.need_grad != 0, o);
+  l.dec = plan_mma_decoder_smem(p.dec, KP0, o);
   l.warp0 = align4(l.dec.end);
   // per-warp block
   int w = 0;
-  const int act_rows = (DP > H ? DP : H);
+  const int ldx = (KP0 > H ? KP0 : H) + 4;
   l.act = w;
-  w += align4(act_rows * WLD);
+  w += align4(WT * ldx);
   l.knn_idx = w;
   w += WT * K;
   l.knn_gidx = w;
@@ -779,6 +808,8 @@ static QueryLayout plan_layout(const QueryParams& p, int DP) {
   w += WT * 3;
   l.out = w;
   w += align4(WT * p.dec.out_dim);
+  l.dv = w;
+  w += WT * 4;
   l.nn = w;
   w += WT;
   w = (w + 1) & ~1;  // 8-byte align the 64-bit masks
@@ -793,8 +824,8 @@ static QueryLayout plan_layout(const QueryParams& p, int DP) {
 
 template <int H, int FT>
 static int launch_query(QueryParams& p, cudaStream_t stream) {
-  constexpr int DP = (FT + 3 + 3) / 4 * 4;
-  p.lay = plan_layout(p, DP);
+  constexpr int KP0 = (FT + 3 + 7) / 8 * 8;
+  p.lay = plan_layout(p, KP0);
   const size_t smem_bytes = (size_t)p.lay.total * sizeof(float);
   if (p.lay.n_warps < 1 || smem_bytes > 227 * 1024) {
     set_error("query kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
