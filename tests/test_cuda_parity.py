@@ -358,8 +358,8 @@ def test_train_backward_matches_autograd(name):
     assert_sdf_close(sdf[:n].cpu(), parts["sdf_pred"], dec0.sdf_scale)
     np.testing.assert_allclose(losses.cpu().numpy(), [float(parts["bce"]), float(parts["eikonal"])], rtol=2e-5)
     g64 = _oracle_train_grads(fx, double=True)
-    assert_rel_close(gfeat.cpu(), gfeat_ref, 1e-4, float(gfeat_ref.abs().max()) * 1e-2, g64[5])
-    assert_rel_close(gdec.cpu(), gdec_ref, 1e-4, float(gdec_ref.abs().max()) * 1e-2, g64[6])
+    assert_rel_close(gfeat.cpu(), gfeat_ref, 1e-4, float(gfeat_ref.abs().max()) * 1e-2, g64[5], kink_rows=8)
+    assert_rel_close(gdec.cpu(), gdec_ref, 1e-4, float(gdec_ref.abs().max()) * 1e-2, g64[6], kink_rows=8)
     # training side effects of the forward
     np.testing.assert_allclose(mh.keep["certainty"].cpu().numpy(), m.local_point_certainties.numpy(), rtol=1e-5,
                                atol=1e-5)
