@@ -194,8 +194,7 @@ __device__ __forceinline__ float idw_weight(float d2, bool valid, int nn_count, 
 // thread keeps ~8 loads in flight and a 128-thread CTA ~1000.
 // ---------------------------------------------------------------------------
 constexpr int KREG = 8;
-constexpr int PROBE_BATCH = 11;      // 33 probes (the default neighbourhood) = 3 record batches
-constexpr int MAX_PROBE_REGS = 33;   // neighbourhoods up to this size keep all slot ids in registers
+constexpr int PROBE_BATCH = 11;  // 33 probes (the default neighbourhood) = 3 batches
 
 struct KnnRegs {
   float d2[KREG];
@@ -277,35 +276,15 @@ __device__ __forceinline__ int knn_search_thread(const pinb200_map_view& m, cons
   const float td_cur = tf ? __ldg(m.travel_dist + m.cur_ts) : 0.f;
   const uint32_t B = (uint32_t)m.buffer_size;
   const int C = m.n_probe;
-  // level 1: every slot-table probe of the neighbourhood is issued before any is consumed (C <= MAX_PROBE_REGS)
-  int gall[MAX_PROBE_REGS];
-  const bool all_first = C <= MAX_PROBE_REGS;
-  if (all_first) {
-#pragma unroll
-    for (int c = 0; c < MAX_PROBE_REGS; ++c) {
-      gall[c] = -1;
-      if (c < C) {
-        uint32_t slot = r0 + s_delta[c];
-        if (slot >= B) slot -= B;
-        gall[c] = __ldg(m.slot_table + slot);
-      }
-    }
-  }
-#pragma unroll
-  for (int c0 = 0; c0 < MAX_PROBE_REGS + PROBE_BATCH; c0 += PROBE_BATCH) {
-    if (c0 >= C) break;
+  for (int c0 = 0; c0 < C; c0 += PROBE_BATCH) {
     int gi[PROBE_BATCH];
 #pragma unroll
     for (int j = 0; j < PROBE_BATCH; ++j) {
       gi[j] = -1;
       if (c0 + j < C) {
-        if (all_first) {
-          gi[j] = (c0 + j < MAX_PROBE_REGS) ? gall[(c0 + j < MAX_PROBE_REGS) ? c0 + j : 0] : -1;
-        } else {
-          uint32_t slot = r0 + s_delta[c0 + j];
-          if (slot >= B) slot -= B;
-          gi[j] = __ldg(m.slot_table + slot);
-        }
+        uint32_t slot = r0 + s_delta[c0 + j];
+        if (slot >= B) slot -= B;
+        gi[j] = __ldg(m.slot_table + slot);
       }
     }
     float px[PROBE_BATCH], py[PROBE_BATCH], pz[PROBE_BATCH], td[PROBE_BATCH];

@@ -110,9 +110,6 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&acc)[2][NT][4], const f
       split_tf32(xr[4], ah[mt][2], al[mt][2]);
       split_tf32(xr[8 * LDX + 4], ah[mt][3], al[mt][3]);
     }
-    // all B fragments of this k-step first, then three passes over the 2 x NT accumulators so that consecutive
-    // tensor-core instructions never depend on each other (the three terms of one accumulator are 2*NT apart)
-    uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       int o0, o1;
@@ -123,23 +120,18 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&acc)[2][NT][4], const f
         o0 = (kk * 8 + t) * ldw + nt * 8 + g;
         o1 = o0 + 4 * ldw;
       }
-      bh[nt][0] = __float_as_uint(whi[o0]);
-      bh[nt][1] = __float_as_uint(whi[o1]);
-      bl[nt][0] = __float_as_uint(wlo[o0]);
-      bl[nt][1] = __float_as_uint(wlo[o1]);
+      uint32_t bh[2], bl[2];
+      bh[0] = __float_as_uint(whi[o0]);
+      bh[1] = __float_as_uint(whi[o1]);
+      bl[0] = __float_as_uint(wlo[o0]);
+      bl[1] = __float_as_uint(wlo[o1]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_tf32(acc[mt][nt], al[mt], bh);  // small terms first
+        mma_tf32(acc[mt][nt], ah[mt], bl);
+        mma_tf32(acc[mt][nt], ah[mt], bh);
+      }
     }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], al[mt], bh[nt]);  // small terms first
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
   }
 }
 
