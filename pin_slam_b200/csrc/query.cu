@@ -831,7 +831,13 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     set_error("query kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
     return PINB200_ERR_UNSUPPORTED;
   }
-  const int nw = p.lay.n_warps;
+  // small batches (tracker: a few thousand points, mapper: ~26k rows): spread the warp tiles over all SMs
+  // instead of packing 10-12 warps into a few CTAs
+  int nw = p.lay.n_warps;
+  {
+    const long long per_sm = (p.n_tiles + sm_count() - 1) / sm_count();
+    if (per_sm < nw) nw = (int)std::max<long long>(1, per_sm);
+  }
   auto kern = query_kernel<H, FT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) {
