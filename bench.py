@@ -312,6 +312,80 @@ def frame_baseline_torch(loop, dev, device=None, reps=3):
             "what": "reference op sequence (oracle port) in PyTorch eager: 3 x (query + GN step), 5 x training iteration"}
 
 
+def mapper_benchmark(args):
+    """BASELINE configs[4]: mapper-only data-parallel training.  A 2M-sample replay pool sharded over the ranks,
+    per-GPU batch 16384 (weak scaling), K1 forward + loss heads + K2 backward + ONE NCCL all-reduce of
+    [feature grads | decoder grads | certainty increments] + K3 Adam per iteration.  value = samples/s (all ranks)."""
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    from pin_slam_b200 import ops
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import Decoder
+    from pin_slam_b200.synthetic import build_map, surface_queries
+    from pin_slam_b200.utils.mapper import Mapper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = HotPathConfig.kitti(device=str(dev), feature_std=0.05, bs_new_sample=0, local_map_radius=1e4)
+    npm = build_map(cfg, n_surface=2_000_000, seed=0, extent=80.0)   # identical replica on every rank (same seed)
+    torch.manual_seed(42)
+    dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    ds = types.SimpleNamespace(processed_frame=0, lose_track=False, stop_status=False, gt_pose_provided=False,
+                               odom_poses=None, pgo_poses=None, gt_poses=None)
+    mapper = Mapper(cfg, ds, npm, {"sdf": dec, "semantic": None, "color": None})
+    pool_total = 2_000_000
+    n = pool_total // world                                        # this rank's shard of the replay pool
+    g = torch.Generator().manual_seed(100 + rank)
+    coord = surface_queries(npm, n, seed=200 + rank, sigma=0.15)
+    mapper.global_coord_pool = coord
+    mapper.coord_pool = coord
+    mapper.sdf_label_pool = (0.15 * torch.randn(n, generator=g)).to(dev)
+    mapper.weight_pool = (torch.rand(n, generator=g) * 0.8 + 0.6).to(dev)
+    mapper.time_pool = torch.zeros(n, dtype=torch.int32, device=dev)
+    mapper.pool_sample_count = n
+    torch.manual_seed(1000 + rank)                                  # per-rank batch draws
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mapper.mapping(max(args.warmup, 3))
+    barrier()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mapper.mapping(args.steps)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "mapper training throughput (samples/s, all GPUs)", "value": cfg.bs * world / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: mapper-only, 2M-sample pool sharded over ranks, bs/GPU 16384, "
+                                   "run_kitti.yaml parameters, NCCL all-reduce of feature+decoder grads per iteration",
+                       "local_points": int(npm.local_count()), "pool_per_rank": n,
+                       "allreduce_floats": int(npm.local_geo_features.numel() + dec.flat_parameters().numel()
+                                               + npm.local_count()),
+                       "parallelism": f"dp{world}"},
+            "gpu_launches": ops.launch_count() - l0}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,10 +394,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true", help="skip the per-frame tracker+mapper measurement")
+    ap.add_argument("--workload", default="query", choices=["query", "mapper"],
+                    help="query = BASELINE configs[1] (default, the headline); mapper = configs[4] data-parallel training")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "mapper":
+        mapper_benchmark(args)
         return
 
     import torch

@@ -534,3 +534,39 @@ def test_dropin_query_feature_matches_fused_path():
         assert_sdf_close(o["sdf"].cpu(), s.detach().cpu(), dec.sdf_scale)
         assert_rel_close(o["grad"].cpu(), g.detach().cpu(), 2e-4, float(g.detach().abs().mean()), kink_rows=3)
         np.testing.assert_allclose(o["certainty"].cpu().numpy(), cert.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_dropin_pickles_and_installs_under_reference_module_names(tmp_path):
+    """utils/tools.py:295-317 pickles the whole NeuralPoints module after clear_temp(); pin_slam.py:157-165 reloads
+    it, reassigns .config and calls recreate_hash.  install() must make `model.neural_points` resolve to the drop-in."""
+    import importlib
+    import sys
+
+    import pin_slam_b200.install as inst
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import Decoder
+    from pin_slam_b200.synthetic import build_map, surface_queries
+
+    inst.install()
+    assert importlib.import_module("model.neural_points").NeuralPoints.__module__ == "pin_slam_b200.model.neural_points"
+    assert sys.modules["model.decoder"].Decoder is Decoder
+    cfg = HotPathConfig.kitti(device="cuda", feature_std=0.1, buffer_size=200003)
+    npm = build_map(cfg, n_surface=100000, seed=4, extent=20.0)
+    torch.manual_seed(0)
+    dec = Decoder(cfg, 64, 1, 1)
+    q = surface_queries(npm, 2000, seed=1)
+    before = npm.query_sdf(q, dec, need_grad=True)
+    sdf0, grad0 = before["sdf"].clone(), before["grad"].clone()
+    npm.clear_temp()
+    path = tmp_path / "pin_map.pth"
+    torch.save({"neural_points": npm, "geo_decoder": dec.state_dict()}, path)
+    blob = torch.load(path, weights_only=False)
+    npm2 = blob["neural_points"]
+    npm2.config = cfg
+    npm2.travel_dist = torch.zeros(4, device="cuda")
+    npm2.recreate_hash(torch.tensor([0.0, 0.0, 1.0], device="cuda"), None, True, False)
+    dec2 = Decoder(cfg, 64, 1, 1)
+    dec2.load_state_dict(blob["geo_decoder"])
+    after = npm2.query_sdf(q, dec2, need_grad=True)
+    assert torch.equal(after["nn_count"], before["nn_count"])
+    assert torch.allclose(after["sdf"], sdf0, atol=1e-7) and torch.allclose(after["grad"], grad0, atol=1e-6)
