@@ -550,7 +550,7 @@ def test_dropin_pickles_and_installs_under_reference_module_names(tmp_path):
     inst.install()
     assert importlib.import_module("model.neural_points").NeuralPoints.__module__ == "pin_slam_b200.model.neural_points"
     assert sys.modules["model.decoder"].Decoder is Decoder
-    cfg = HotPathConfig.kitti(device="cuda", feature_std=0.1, buffer_size=200003)
+    cfg = HotPathConfig.kitti(device="cuda", feature_std=0.1)  # full-size table: no collision-order ambiguity
     npm = build_map(cfg, n_surface=100000, seed=4, extent=20.0)
     torch.manual_seed(0)
     dec = Decoder(cfg, 64, 1, 1)
