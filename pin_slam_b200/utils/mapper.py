@@ -270,7 +270,8 @@ class Mapper:
         else:
             index = torch.randint(0, self.pool_sample_count, (bs,), device=self.device)
         coord = (self.global_coord_pool if global_coord else self.coord_pool)[index, :]
-        color = self.color_pool[index] if self.color_pool is not None else None
+        has_color = self.color_pool is not None and self.color_pool.shape[0] == self.sdf_label_pool.shape[0]
+        color = self.color_pool[index] if has_color else None
         return coord, self.sdf_label_pool[index], self.time_pool[index], None, None, color, self.weight_pool[index]
 
     # ------------------------------------------------------------------ queries
@@ -312,7 +313,8 @@ class Mapper:
         flat = self.sdf_mlp.flat_parameters()  # decoder weights live in (and are views of) this vector
         n_dec = flat.numel()
         m_rows = npm.local_count()
-        color_on = bool(cfg.color_on and cfg.weight_i > 0 and self.color_mlp is not None and self.color_pool is not None)
+        color_on = bool(cfg.color_on and cfg.weight_i > 0 and self.color_mlp is not None and self.color_pool is not None
+                        and self.color_pool.shape[0] > 0)
         cfeat = npm.local_color_features.data if color_on else None
         cflat = self.color_mlp.flat_parameters() if color_on else None
         n_cf = cfeat.numel() if color_on else 0
