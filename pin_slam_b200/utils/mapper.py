@@ -14,9 +14,9 @@ One training iteration (reference: ~590 ATen ops + ~32 host syncs, mapper.py:623
                         like the reference's per-frame setup_optimizer)
 
 With torch.distributed initialised (one process per GPU, NCCL over NVLink) every rank trains on its
-own sub-batch of its pool shard and the gradients / certainty increments are summed with ONE
-all-reduce per iteration (plus a max-reduce of the timestamps); map, decoder and Adam state stay
-replicated and bit-identical across ranks.
+own sub-batch of its pool shard and the gradients are summed with ONE all-reduce per iteration
+(certainty increments / timestamps are reduced once per mapping() call); map, decoder and Adam
+state stay replicated and bit-identical across ranks.
 """
 import math
 
@@ -76,19 +76,25 @@ class DataSampler:
         return coord, label, normal_label, None, color_label, weight
 
 
-def allreduce_training_state(red, dcert, cert_before, certainties, ts_update):
-    """The exchange step of data-parallel map training (one process per GPU).
-
-    `red` is the contiguous buffer [feature grads | decoder grads | certainty increments] of this rank's
-    sub-batch (the loss heads already scaled d loss/d sdf by 1/world, so a SUM gives the global-batch mean);
-    `dcert` is its trailing view.  After the call every rank holds the same gradients, the same
-    `certainties` (= value before the iteration + the increments of ALL ranks) and the same `ts_update`
-    (element-wise max), so the replicated map / decoder / Adam state stay identical."""
+def allreduce_gradients(red):
+    """Per-iteration exchange step of data-parallel map training (one process per GPU): ONE all-reduce (sum) over
+    the contiguous buffer [feature grads | decoder grads | colour-feature grads | colour-decoder grads].  The loss
+    heads already scaled d loss/d sdf by 1/world, so the sum is the global-batch mean gradient; every rank then
+    applies the identical Adam step, keeping map features, decoder and optimiser state bit-identical."""
     import torch.distributed as dist
 
-    torch.sub(certainties, cert_before, out=dcert)
     dist.all_reduce(red, op=dist.ReduceOp.SUM)
-    torch.add(cert_before, dcert, out=certainties)
+
+
+def allreduce_map_statistics(cert_at_start, certainties, ts_update):
+    """Once per mapping() call: the per-point certainty increments of all ranks are summed and the last-update
+    timestamps max-reduced.  Neither feeds back into the training iterations (the reference only reads them
+    between frames), so they do not need a collective per iteration."""
+    import torch.distributed as dist
+
+    delta = certainties - cert_at_start
+    dist.all_reduce(delta, op=dist.ReduceOp.SUM)
+    torch.add(cert_at_start, delta, out=certainties)
     dist.all_reduce(ts_update, op=dist.ReduceOp.MAX)
 
 
@@ -320,15 +326,14 @@ class Mapper:
         n_cf = cfeat.numel() if color_on else 0
         n_cd = cflat.numel() if color_on else 0
         train_cdec = color_on and any(p.requires_grad for p in self.color_mlp.parameters())
-        # one contiguous reduction buffer:
-        # [feature grads | decoder grads | colour-feature grads | colour-decoder grads | certainty increments]
-        red = torch.zeros(feat.numel() + n_dec + n_cf + n_cd + m_rows, device=dev, dtype=torch.float32)
+        # one contiguous reduction buffer: [feature grads | decoder grads | colour-feature grads | colour-decoder grads]
+        red = torch.zeros(feat.numel() + n_dec + n_cf + n_cd, device=dev, dtype=torch.float32)
         o0 = feat.numel()
         gfeat = red[:o0].view_as(feat)
         gdec = red[o0: o0 + n_dec]
         gcfeat = red[o0 + n_dec: o0 + n_dec + n_cf].view_as(cfeat) if color_on else None
         gcdec = red[o0 + n_dec + n_cf: o0 + n_dec + n_cf + n_cd] if color_on else None
-        dcert = red[o0 + n_dec + n_cf + n_cd:]
+        cert_at_start = npm.local_point_certainties.clone() if dist_on else None
         mf, vf = torch.zeros_like(feat), torch.zeros_like(feat)
         md, vd = torch.zeros_like(flat), torch.zeros_like(flat)
         if color_on:
@@ -357,8 +362,6 @@ class Mapper:
             else:
                 ne = 0
                 rows = coord.contiguous()
-            if dist_on:
-                cert_before = npm.local_point_certainties.clone()
             o = ops.query_sdf(npm.map_handle(True), self.sdf_mlp.handle(), rows, nn_k=cfg.query_nn_k,
                               weighted_first=cfg.weighted_first, training_mode=True, training_rows=n, need_grad=False,
                               query_ts=ts.contiguous(), save_knn=True, out=out,
@@ -380,8 +383,7 @@ class Mapper:
                 ops.train_backward(npm.map_handle(True), self.color_mlp.handle(sigmoid_out=True), cfeat, rows[:n],
                                    o["knn_idx"][:n], o["knn_weight"][:n], dlc, cfg.weighted_first, gcfeat, gcdec)
             if dist_on:
-                allreduce_training_state(red, dcert, cert_before, npm.local_point_certainties,
-                                         npm.local_point_ts_update)
+                allreduce_gradients(red)
             if train_dec:
                 ops.adam_step(flat, gdec, md, vd, cfg.lr, 0.9, 0.99, cfg.adam_eps, 0.0, it + 1)
             else:
@@ -394,6 +396,8 @@ class Mapper:
                     gcdec.zero_()
                 ops.adam_step(cfeat, gcfeat, mcf, vcf, cfg.lr, 0.9, 0.99, cfg.adam_eps, cfg.weight_decay, it + 1)
             self.total_iter += 1
+        if dist_on:
+            allreduce_map_statistics(cert_at_start, npm.local_point_certainties, npm.local_point_ts_update)
         self.last_losses = losses
         npm.assign_local_to_global()
 

@@ -20,19 +20,18 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from pin_slam_b200.utils.mapper import allreduce_training_state
+    from pin_slam_b200.utils.mapper import allreduce_gradients, allreduce_map_statistics
 
     g = torch.Generator().manual_seed(100 + rank)
     m_rows, f, n_dec = 50, 8, 30
-    red = torch.zeros(m_rows * f + n_dec + m_rows)
-    red[: m_rows * f + n_dec] = torch.randn(m_rows * f + n_dec, generator=g) / world   # pre-scaled by 1/world
-    dcert = red[m_rows * f + n_dec:]
+    red = torch.randn(m_rows * f + n_dec, generator=g) / world   # gradients pre-scaled by 1/world
     cert_before = torch.arange(m_rows, dtype=torch.float32)
     delta = torch.rand(m_rows, generator=g)
     cert = cert_before + delta
     ts = torch.randint(0, 100, (m_rows,), generator=g, dtype=torch.int32)
     grads_local = red[: m_rows * f + n_dec].clone()
-    allreduce_training_state(red, dcert, cert_before, cert, ts)
+    allreduce_gradients(red)
+    allreduce_map_statistics(cert_before, cert, ts)
     # plain lists: torch tensors in an mp.Queue are passed through shared-memory handles that can
     # outlive the producer badly
     q.put((rank, grads_local.tolist(), delta.tolist(), red[: m_rows * f + n_dec].tolist(), cert.tolist(), ts.tolist()))
