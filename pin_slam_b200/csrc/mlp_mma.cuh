@@ -32,8 +32,8 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 struct MmaDecSmem {  // float offsets from the dynamic-smem base
-  int whi[PINB200_MAX_HIDDEN_LAYERS];  // [H][ldw_l]  fp32 weights, torch layout, zero padded (split into TF32 hi/lo
-  int wlo[PINB200_MAX_HIDDEN_LAYERS];  //             parts in registers when a B fragment is loaded); wlo == whi
+  int whi[PINB200_MAX_HIDDEN_LAYERS];  // [H][ldw_l]  tf32 "hi" part, torch layout, zero padded
+  int wlo[PINB200_MAX_HIDDEN_LAYERS];  // [H][ldw_l]  tf32 "lo" part
   int b[PINB200_MAX_HIDDEN_LAYERS];    // [H]
   int ldw[PINB200_MAX_HIDDEN_LAYERS];  // in_pad_l + 4
   int wout, bout, end;
@@ -48,7 +48,8 @@ inline MmaDecSmem plan_mma_decoder_smem(const pinb200_decoder_view& d, int KP0, 
   for (int l = 0; l < d.n_hidden; ++l) {
     s.ldw[l] = (l == 0 ? KP0 : H) + 4;
     s.whi[l] = o;
-    s.wlo[l] = o;  // one fp32 copy: halves the shared-memory footprint of the decoder (more resident warps)
+    o += H * s.ldw[l];
+    s.wlo[l] = o;
     o += H * s.ldw[l];
     s.b[l] = o;
     o += H;
@@ -66,9 +67,14 @@ __device__ __forceinline__ void stage_mma_decoder(const pinb200_decoder_view& d,
   for (int l = 0; l < d.n_hidden; ++l) {
     const int in = l == 0 ? d.in_dim : H, ldw = s.ldw[l];
     float* hi = smem + s.whi[l];
+    float* lo = smem + s.wlo[l];
     for (int e = tid; e < H * ldw; e += nt) {
       const int j = e / ldw, i = e - j * ldw;
-      hi[e] = i < in ? __ldg(d.w[l] + (size_t)j * in + i) : 0.f;
+      const float w = i < in ? __ldg(d.w[l] + (size_t)j * in + i) : 0.f;
+      uint32_t h, lw;
+      split_tf32(w, h, lw);
+      hi[e] = __uint_as_float(h);
+      lo[e] = __uint_as_float(lw);
     }
     float* bb = smem + s.b[l];
     for (int e = tid; e < H; e += nt) bb[e] = d.b[l] ? __ldg(d.b[l] + e) : 0.f;
@@ -115,8 +121,10 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&acc)[2][NT][4], const f
         o1 = o0 + 4 * ldw;
       }
       uint32_t bh[2], bl[2];
-      split_tf32(whi[o0], bh[0], bl[0]);
-      split_tf32(whi[o1], bh[1], bl[1]);
+      bh[0] = __float_as_uint(whi[o0]);
+      bh[1] = __float_as_uint(whi[o1]);
+      bl[0] = __float_as_uint(wlo[o0]);
+      bl[1] = __float_as_uint(wlo[o1]);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         mma_tf32(acc[mt][nt], al[mt], bh);  // small terms first
