@@ -228,6 +228,16 @@ int pinb200_color_loss(const float* color_pred, const float* color_label, const 
                        int32_t loss_weight_on, float weight_i, float grad_scale, const float* n_surface,
                        float* dloss_dcolor, float* loss, void* stream);
 
+/* Batch assembly of one map-training iteration in ONE launch (utils/mapper.py:482-503 pool gathers +
+ * :990-1002 the six +-eps shifted copies of every `decimation`-th sample):
+ *   rows  [n + 6*ne, 3] = [ coord_pool[index] | x+e_x | x-e_x | x+e_y | x-e_y | x+e_z | x-e_z ],  ne = ceil(n/decimation)
+ *   label [n], ts [n], weight [n] gathered with the same index; color [n,cc] if color_pool != NULL.
+ * `index` are the int64 draws of torch.randint (the RNG stream stays the reference's). */
+int pinb200_assemble_batch(const float* coord_pool, const float* label_pool, const int32_t* ts_pool,
+                           const float* weight_pool, const float* color_pool, int32_t color_channels,
+                           const int64_t* index, int64_t n, int32_t decimation, float eps, float* rows,
+                           float* label, int32_t* ts, float* weight, float* color, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ SIGNATURES = {
     "pinb200_gn_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f32p, c_f32p,
                                   c_f32p, C.c_int32, C.c_int32, C.c_float, c_f64p, c_f64p, c_f64p, C.c_void_p]),
+    "pinb200_assemble_batch": (C.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_int32, C.c_float, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_void_p]),
     "pinb200_color_loss": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p]),
 }

@@ -103,9 +103,61 @@ __global__ void color_loss_kernel(const float* __restrict__ pred, const float* _
   }
 }
 
+// one thread per sample: pool gathers + the six shifted numerical-gradient rows of every decimation-th sample
+__global__ void assemble_batch_kernel(const float* __restrict__ cp, const float* __restrict__ lp,
+                                      const int32_t* __restrict__ tp, const float* __restrict__ wp,
+                                      const float* __restrict__ colp, int cc, const long long* __restrict__ index,
+                                      long long n, int dec, float eps, float* __restrict__ rows,
+                                      float* __restrict__ label, int32_t* __restrict__ ts, float* __restrict__ weight,
+                                      float* __restrict__ color) {
+  const long long ne = (n + dec - 1) / dec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = index[i];
+    const float x = cp[3 * s], y = cp[3 * s + 1], z = cp[3 * s + 2];
+    rows[3 * i] = x;
+    rows[3 * i + 1] = y;
+    rows[3 * i + 2] = z;
+    label[i] = lp[s];
+    ts[i] = tp[s];
+    weight[i] = wp[s];
+    if (colp)
+      for (int c = 0; c < cc; ++c) color[i * cc + c] = colp[s * cc + c];
+    if (dec > 0 && i % dec == 0) {
+      const long long j = i / dec;
+      float* r = rows + 3 * n;
+      const float sh[6][3] = {{eps, 0, 0}, {-eps, 0, 0}, {0, eps, 0}, {0, -eps, 0}, {0, 0, eps}, {0, 0, -eps}};
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        float* o = r + 3 * (a * ne + j);
+        o[0] = x + sh[a][0];
+        o[1] = y + sh[a][1];
+        o[2] = z + sh[a][2];
+      }
+    }
+  }
+}
+
 }  // namespace pinb
 
 using namespace pinb;
+
+extern "C" int pinb200_assemble_batch(const float* coord_pool, const float* label_pool, const int32_t* ts_pool,
+                                      const float* weight_pool, const float* color_pool, int32_t color_channels,
+                                      const int64_t* index, int64_t n, int32_t decimation, float eps, float* rows,
+                                      float* label, int32_t* ts, float* weight, float* color, void* stream) {
+  if (!coord_pool || !label_pool || !ts_pool || !weight_pool || !index || !rows || !label || !ts || !weight ||
+      (color_pool && !color)) {
+    set_error("assemble_batch: null argument");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (n <= 0) return PINB200_OK;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  assemble_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(coord_pool, label_pool, ts_pool, weight_pool,
+                                                                color_pool, color_channels,
+                                                                reinterpret_cast<const long long*>(index), n, decimation,
+                                                                eps, rows, label, ts, weight, color);
+  return check_launch("assemble_batch_kernel");
+}
 
 extern "C" int pinb200_color_loss(const float* color_pred, const float* color_label, const float* sdf_label,
                                   const float* weight, int64_t n, int32_t color_channels, float surface_range,

@@ -287,3 +287,30 @@ def color_loss(color_pred, color_label, sdf_label, weight, surface_range, loss_w
                                 _stream())
     _lib.check(rc, "pinb200_color_loss")
     _count()
+
+
+def assemble_batch(coord_pool, label_pool, ts_pool, weight_pool, color_pool, index, decimation, eps, out: dict):
+    """Pool gathers + numerical-gradient rows of one training iteration in one launch; buffers live in `out`."""
+    lib = _lib.load()
+    n = index.shape[0]
+    dev = index.device
+    ne = (n + decimation - 1) // decimation if decimation > 0 else 0
+    cc = 0 if color_pool is None else color_pool.shape[1]
+
+    def buf(name, shape, dtype=torch.float32):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+
+    rows = buf("rows", (n + 6 * ne, 3))
+    label, ts, weight = buf("label", (n,)), buf("ts", (n,), torch.int32), buf("weight", (n,))
+    color = buf("color_label", (n, cc)) if cc else None
+    rc = lib.pinb200_assemble_batch(_ptr(coord_pool, torch.float32), _ptr(label_pool, torch.float32),
+                                    _ptr(ts_pool, torch.int32), _ptr(weight_pool, torch.float32),
+                                    _ptr(color_pool, torch.float32), cc, _ptr(index, torch.int64), n, int(decimation),
+                                    float(eps), _ptr(rows), _ptr(label), _ptr(ts), _ptr(weight), _ptr(color), _stream())
+    _lib.check(rc, "pinb200_assemble_batch")
+    _count()
+    return rows, label, ts, weight, color, ne

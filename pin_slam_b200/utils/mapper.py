@@ -128,6 +128,7 @@ class Mapper:
         self.pool_sample_count = 0
         self.last_losses = None
         self._work = {}
+        self._batch = {}
         self.init_pool()
 
     # ------------------------------------------------------------------ pool
@@ -263,8 +264,8 @@ class Mapper:
                         self.adaptive_iter_offset = 10
 
     # ------------------------------------------------------------------ batches
-    def get_batch(self, global_coord=False, bs=None):
-        """Same torch.randint calls as the reference (mapper.py:452-503) so the RNG stream is shared."""
+    def draw_batch_index(self, bs=None):
+        """The batch draw of the reference (mapper.py:452-480): same torch.randint calls, same RNG stream."""
         cfg = self.config
         bs = cfg.bs if bs is None else bs
         lose = getattr(self.dataset, "lose_track", False) or getattr(self.dataset, "stop_status", False)
@@ -272,9 +273,12 @@ class Mapper:
             n_new = min(self.new_idx.shape[0], cfg.bs_new_sample)
             hist = torch.randint(0, self.pool_sample_count, (bs - n_new,), device=self.device)
             pick = torch.randint(0, self.new_idx.shape[0], (n_new,), device=self.device)
-            index = torch.cat((hist, self.new_idx[pick]), dim=0)
-        else:
-            index = torch.randint(0, self.pool_sample_count, (bs,), device=self.device)
+            return torch.cat((hist, self.new_idx[pick]), dim=0)
+        return torch.randint(0, self.pool_sample_count, (bs,), device=self.device)
+
+    def get_batch(self, global_coord=False, bs=None):
+        """Reference-compatible batch tuple (mapper.py:452-503)."""
+        index = self.draw_batch_index(bs)
         coord = (self.global_coord_pool if global_coord else self.coord_pool)[index, :]
         has_color = self.color_pool is not None and self.color_pool.shape[0] == self.sdf_label_pool.shape[0]
         color = self.color_pool[index] if has_color else None
@@ -350,18 +354,29 @@ class Mapper:
             shifts[2 * a + 1, 0, a] = -eps_num
         out = self._work
         for it in range(iter_count):
-            coord, label, ts, _, _, color_label, weight = self.get_batch(global_coord=not self.ba_done_flag)
-            if self.ba_done_flag:
-                tf = self.used_poses[ts.long()].to(coord)
-                coord = (tf[:, :3, :3] @ coord.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
-            n = coord.shape[0]
-            if eik_on:
-                sub = coord[::dec_step]
-                ne = sub.shape[0]
-                rows = torch.cat((coord, (sub.unsqueeze(0) + shifts).reshape(-1, 3)), 0)
+            fused_batch = (type(self).get_batch is Mapper.get_batch and "get_batch" not in self.__dict__
+                           and not self.ba_done_flag)
+            if fused_batch:
+                # one launch: pool gathers + the 6 shifted numerical-gradient copies of every dec_step-th sample
+                index = self.draw_batch_index()
+                has_color = color_on and self.color_pool.shape[0] == self.sdf_label_pool.shape[0]
+                rows, label, ts, weight, color_label, ne = ops.assemble_batch(
+                    self.global_coord_pool, self.sdf_label_pool, self.time_pool, self.weight_pool,
+                    self.color_pool if has_color else None, index, dec_step if eik_on else 0, eps_num, self._batch)
+                n = index.shape[0]
             else:
-                ne = 0
-                rows = coord.contiguous()
+                coord, label, ts, _, _, color_label, weight = self.get_batch(global_coord=not self.ba_done_flag)
+                if self.ba_done_flag:
+                    tf = self.used_poses[ts.long()].to(coord)
+                    coord = (tf[:, :3, :3] @ coord.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+                n = coord.shape[0]
+                if eik_on:
+                    sub = coord[::dec_step]
+                    ne = sub.shape[0]
+                    rows = torch.cat((coord, (sub.unsqueeze(0) + shifts).reshape(-1, 3)), 0)
+                else:
+                    ne = 0
+                    rows = coord.contiguous()
             o = ops.query_sdf(npm.map_handle(True), self.sdf_mlp.handle(), rows, nn_k=cfg.query_nn_k,
                               weighted_first=cfg.weighted_first, training_mode=True, training_rows=n, need_grad=False,
                               query_ts=ts.contiguous(), save_knn=True, out=out,
