@@ -234,16 +234,18 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
   __syncthreads();
 
   const int QPT = wf ? WT : WT / K;                   // queries per 32-row decoder tile
-  const int n_rt = wf ? 1 : (WT + QPT - 1) / QPT;     // row tiles per 32-query warp tile
+  const int WQ = p.qpt;                               // queries per warp tile (<= WT; small launches use fewer so
+                                                      // that every resident warp gets work: latency, not issue, bound)
+  const int n_rt = wf ? 1 : (WQ + QPT - 1) / QPT;     // row tiles per warp tile
   const int tid = lane;                               // row / query owned by this thread inside the warp tile
   const int nwarp = blockDim.x >> 5;
   for (int st = blockIdx.x * nwarp + warp; st < p.n_tiles; st += gridDim.x * nwarp) {
-    const long long q0s = (long long)st * WT;
+    const long long q0s = (long long)st * WQ;
 
     // ============ phase A1: thread per query -- search, IDW weights, side effects ============
     {
       const long long qi = q0s + tid;
-      const bool live = qi < p.n;
+      const bool live = tid < WQ && qi < p.n;
       KnnRegs Lk;
       knn_regs_init(Lk);
       int cnt = 0;
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
 
     for (int rt = 0; rt < n_rt; ++rt) {
       const int sq0 = rt * QPT;                              // first query of this row tile inside the super tile
-      const int qpt = min(QPT, WT - sq0);                  // queries in this row tile
+      const int qpt = min(QPT, WQ - sq0);                  // queries in this row tile
       const int used_rows = wf ? WT : qpt * K;
 
       // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
           }
           // ---- C2: thread per query -- chain rule through the IDW weights, outputs
           const long long qi = q0s + tid;
-          if (qi < p.n) {
+          if (tid < WQ && qi < p.n) {
             const float val = s_out[tid * OC + c];
             float gq0 = 0.f, gq1 = 0.f, gq2 = 0.f;
             if (need_grad) {
@@ -835,6 +837,19 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
   // instead of packing 10-12 warps into a few CTAs
   int nw = p.lay.n_warps;
   {
+    // queries per warp tile: a full 32 when there is enough work to occupy every resident warp, fewer (whole
+    // decoder row tiles in decode-every-neighbour mode) for the tracker / mapper sized launches
+    const long long slots = (long long)sm_count() * nw;
+    const long long per_warp = (p.n + slots - 1) / slots;
+    int wq;
+    if (p.opts.weighted_first) {
+      wq = (int)std::min<long long>(WT, std::max<long long>(GQ, (per_warp + GQ - 1) / GQ * GQ));
+    } else {
+      const int qpt_rows = WT / p.opts.nn_k;
+      wq = (int)std::min<long long>(WT, (per_warp + qpt_rows - 1) / qpt_rows * qpt_rows);
+    }
+    p.qpt = wq;
+    p.n_tiles = (int)((p.n + wq - 1) / wq);
     const long long per_sm = (p.n_tiles + sm_count() - 1) / sm_count();
     if (per_sm < nw) nw = (int)std::max<long long>(1, per_sm);
   }
