@@ -219,6 +219,28 @@ int pinb200_gn_step(const float* xyz, const float* sdf, const float* grad, const
                     int32_t color_mode, float w_photo, double* sums, double* result,
                     double* t_inout, void* stream);
 
+/* Parameters of pinb200_gn_step as one struct (same meaning), for pinb200_track_iterations. */
+typedef struct pinb200_gn_opts {
+  const float* sdf_label;  /* [N] or NULL */
+  const float* normals;    /* [N,3] or NULL */
+  const float* color_obs;  /* [N,Cc] or NULL */
+  int32_t color_channels, color_mode;
+  int32_t min_nn;
+  float min_grad_norm, max_grad_norm, max_sdf_std, gm_dist, gm_grad, lm_lambda, w_photo;
+  double* sums;   /* [64] */
+  double* result; /* [32] */
+} pinb200_gn_opts;
+
+/* `n_iter` Gauss-Newton iterations of the tracker loop (utils/tracker.py:104-176) issued by ONE host call:
+ * each iteration = pinb200_query_sdf (opts->transform must be the device pose T, want xyz/grad outputs) followed by
+ * pinb200_gn_step on its outputs with t_inout = opts->transform, so the pose never leaves the device.
+ * With n_iter == 1 this is one iteration of the reference loop (the caller reads result[] for its convergence
+ * logic); the fixed-iteration benchmark configuration uses n_iter == 3 without any host sync. */
+int pinb200_track_iterations(const pinb200_map_view* map, const pinb200_decoder_view* sdf_dec,
+                             const pinb200_decoder_view* color_dec, const float* source_xyz, int64_t n,
+                             const pinb200_query_opts* opts, const pinb200_query_out* out,
+                             const pinb200_gn_opts* gn, int32_t n_iter, void* stream);
+
 /* Colour head of the training loss (utils/mapper.py:804-812, utils/loss.py:31-41): L1 between the predicted and
  * the measured colour on surface samples (|sdf_label| < surface_range), mean over (n_surface x Cc) elements,
  * times weight_i.  n_surface is read from the device (count computed by the caller without a sync).
@@ -227,6 +249,13 @@ int pinb200_color_loss(const float* color_pred, const float* color_label, const 
                        const float* weight, int64_t n, int32_t color_channels, float surface_range,
                        int32_t loss_weight_on, float weight_i, float grad_scale, const float* n_surface,
                        float* dloss_dcolor, float* loss, void* stream);
+
+/* Packed 32-byte search records of the global map (pinb200_map_view.search_rec): one launch writes
+ * rec[i] = {x, y, z, travel_dist[ts_create[i]] (0 if travel_dist == NULL), bits(global2local[i]) (i if NULL), 0, 0, 0}.
+ * Replaces the separate reads of neural_points / point_ts_create / travel_dist / global2local
+ * (model/neural_points.py:538-581) inside the search loop by one 32-byte load per probe hit. */
+int pinb200_build_search_records(const float* points, const int32_t* ts_create, const float* travel_dist,
+                                 const int32_t* global2local, int64_t n_global, float* search_rec, void* stream);
 
 /* Batch assembly of one map-training iteration in ONE launch (utils/mapper.py:482-503 pool gathers +
  * :990-1002 the six +-eps shifted copies of every `decimation`-th sample):

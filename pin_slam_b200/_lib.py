@@ -47,6 +47,14 @@ class QueryOut(C.Structure):
                 ("knn_dist2", c_f32p), ("knn_weight", c_f32p), ("knn_gidx", c_i32p), ("xyz", c_f32p)]
 
 
+class GnOpts(C.Structure):
+    _fields_ = [("sdf_label", c_f32p), ("normals", c_f32p), ("color_obs", c_f32p), ("color_channels", C.c_int32),
+                ("color_mode", C.c_int32), ("min_nn", C.c_int32), ("min_grad_norm", C.c_float),
+                ("max_grad_norm", C.c_float), ("max_sdf_std", C.c_float), ("gm_dist", C.c_float),
+                ("gm_grad", C.c_float), ("lm_lambda", C.c_float), ("w_photo", C.c_float), ("sums", c_f64p),
+                ("result", c_f64p)]
+
+
 # name -> (restype, argtypes); every symbol include/pinb200.h declares
 SIGNATURES = {
     "pinb200_version": (C.c_int, []),
@@ -69,8 +77,12 @@ SIGNATURES = {
     "pinb200_gn_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f32p, c_f32p,
                                   c_f32p, C.c_int32, C.c_int32, C.c_float, c_f64p, c_f64p, c_f64p, C.c_void_p]),
+    "pinb200_build_search_records": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int64, c_f32p, C.c_void_p]),
     "pinb200_assemble_batch": (C.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_int32, C.c_float, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_void_p]),
+    "pinb200_track_iterations": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,
+                                           C.c_int64, C.POINTER(QueryOpts), C.POINTER(QueryOut), C.POINTER(GnOpts),
+                                           C.c_int32, C.c_void_p]),
     "pinb200_color_loss": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p]),
 }

@@ -309,3 +309,29 @@ extern "C" int pinb200_gn_step(const float* xyz, const float* sdf, const float* 
   gn_solve_kernel<<<1, 32, 0, st>>>(sums, lm_lambda, result, t_inout);
   return check_launch("gn_solve_kernel");
 }
+
+
+extern "C" int pinb200_track_iterations(const pinb200_map_view* map, const pinb200_decoder_view* sdf_dec,
+                                        const pinb200_decoder_view* color_dec, const float* source_xyz, int64_t n,
+                                        const pinb200_query_opts* opts, const pinb200_query_out* out,
+                                        const pinb200_gn_opts* gn, int32_t n_iter, void* stream) {
+  if (!opts || !out || !gn || !gn->sums || !gn->result) {
+    set_error("track_iterations: null argument");
+    return PINB200_ERR_BAD_ARG;
+  }
+  if (!opts->transform || !out->xyz || !out->sdf || !out->grad || !out->sdf_std || !out->nn_count) {
+    set_error("track_iterations: needs opts->transform and the xyz/sdf/grad/sdf_std/nn_count outputs");
+    return PINB200_ERR_BAD_ARG;
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    int rc = pinb200_query_sdf(map, sdf_dec, color_dec, source_xyz, nullptr, n, opts, out, stream);
+    if (rc) return rc;
+    rc = pinb200_gn_step(out->xyz, out->sdf, out->grad, out->sdf_std, out->nn_count, gn->sdf_label, gn->normals, n,
+                         gn->min_nn, gn->min_grad_norm, gn->max_grad_norm, gn->max_sdf_std, gn->gm_dist, gn->gm_grad,
+                         gn->lm_lambda, gn->color_mode ? gn->color_obs : nullptr, gn->color_mode ? out->color : nullptr,
+                         gn->color_mode == 2 ? out->color_grad : nullptr, gn->color_channels, gn->color_mode,
+                         gn->w_photo, gn->sums, gn->result, const_cast<double*>(opts->transform), stream);
+    if (rc) return rc;
+  }
+  return PINB200_OK;
+}

@@ -17,6 +17,8 @@
 // Replaces model/neural_points.py:530-746,950-1009, model/decoder.py:61-85,112,
 // utils/tools.py:247-260, utils/tracker.py:313-328 of the reference.
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "mlp.cuh"
 #include "mlp_mma.cuh"
@@ -854,14 +856,30 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     if (per_sm < nw) nw = (int)std::max<long long>(1, per_sm);
   }
   auto kern = query_kernel<H, FT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return PINB200_ERR_CUDA;
+  // the attribute / occupancy calls cost a few microseconds each: remember the answer per (device, warps, smem)
+  struct Cached {
+    int dev, nw, occ;
+    size_t smem;
+  };
+  static std::mutex mu;
+  static std::vector<Cached> cache;
+  int occ = 0, dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Cached& c : cache)
+      if (c.dev == dev && c.nw == nw && c.smem == smem_bytes) occ = c.occ;
+    if (occ == 0) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return PINB200_ERR_CUDA;
+      }
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem_bytes);
+      if (occ < 1) occ = 1;
+      cache.push_back({dev, nw, occ, smem_bytes});
+    }
   }
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem_bytes);
-  if (occ < 1) occ = 1;
   const long long ctas_needed = (p.n_tiles + nw - 1) / nw;
   const int grid = (int)std::min<long long>(ctas_needed, (long long)sm_count() * occ);
   kern<<<grid, nw * 32, smem_bytes, stream>>>(p);

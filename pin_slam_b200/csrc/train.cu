@@ -2,20 +2,26 @@
 // feature interpolation, from the kNN ids/weights the forward saved.
 //
 // Per 128-row tile (same row <-> thread mapping as K1):
-//   A  warp per query : re-gather the decoder input rows from the saved kNN
+//   A  thread per row : re-gather the decoder input rows from the saved kNN (float4 feature-row loads)
 //   B  thread per row : forward, keeping every layer's activations in shared memory
 //   C  tile reductions: dW_out, then for each layer l = L-1..0
 //        dW_l  += G_l^T A_{l-1}   (128-row tile GEMM, thread-owned 4 x NI output blocks)
 //        G_{l-1} = mask * (W_l^T G_l)  (thread per row)
-//   D  warp per query : scatter d loss / d feature rows with coalesced atomics
+//   D  thread per row : scatter d loss / d feature rows with 16-byte vector reductions
 // Decoder gradients are accumulated per CTA in shared memory over all its tiles
 // and flushed once with atomics.
 //
 // Replaces the autograd reverse pass of utils/mapper.py:816-817 through
 // model/neural_points.py:597-731 (index_put_ accumulate) and model/decoder.py:61-85.
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "mlp.cuh"
+
+#ifndef PINB_K2_MIN_CTAS
+#define PINB_K2_MIN_CTAS 3  // resident CTAs per SM the register allocation targets (12 warps)
+#endif
 
 namespace pinb {
 
@@ -38,20 +44,6 @@ struct TrainParams {
   float* grad_dec;
   TrainLayout lay;
 };
-
-__device__ __forceinline__ void gather_weighted_t(const float* __restrict__ feat, int F, int K, int my_idx, float my_w,
-                                                  int lane, float* s_x, int row) {
-  for (int j0 = 0; j0 < F; j0 += 32) {
-    const int j = j0 + lane;
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const int lk = __shfl_sync(FULL, my_idx, k);
-      const float wk = __shfl_sync(FULL, my_w, k);
-      if (lk >= 0 && j < F) acc = fmaf(wk, __ldg(feat + (size_t)lk * F + j), acc);
-    }
-    if (j < F) s_x[j * ACT_LD + row] = acc;
-  }
-}
 
 // dW[j][i] += sum_r G[j][r] * A[i][r]; db[j] += sum_r G[j][r]   (thread-owned 4 x NI blocks)
 template <int NI>
@@ -91,7 +83,7 @@ __device__ __forceinline__ void tile_gemm_acc(const float* __restrict__ G, const
 }
 
 template <int H, int DP>
-__global__ void __launch_bounds__(TILE, 1) train_bwd_kernel(const __grid_constant__ TrainParams p) {
+__global__ void __launch_bounds__(TILE, PINB_K2_MIN_CTAS) train_bwd_kernel(const __grid_constant__ TrainParams p) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pinb200_map_view& m = p.map;
@@ -126,71 +118,122 @@ __global__ void __launch_bounds__(TILE, 1) train_bwd_kernel(const __grid_constan
   const int off_wout = off, off_bout = off + OC * H;
 
   const int QPT = p.qpt;
+  // feature rows are 16-byte aligned multiples of 4 floats: vector loads and vector reductions
+  const bool vec_ok = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.grad_feat) & 15) == 0);
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const long long q0 = (long long)tile * QPT;
-    // ---------------- A: rebuild decoder inputs ----------------
-    for (int e = tid; e < TILE * 4; e += TILE) s_go[e] = 0.f;
-    __syncthreads();
-    for (int ql = warp; ql < QPT; ql += TILE / 32) {
+    // ---------------- A: rebuild decoder inputs (thread per tile row) ----------------
+    // every thread issues its own idx / weight / point / feature-row loads (a feature row is >= 16 contiguous
+    // bytes, read as float4): one dependent round trip per tile instead of one per query
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s_go[tid * 4 + c] = 0.f;
+    if (!wf) {
+      const int ql = tid / K, k = tid - ql * K;
       const long long qi = q0 + ql;
-      const int row0 = wf ? ql : ql * K;
-      const int nrows = wf ? 1 : K;
-      if (qi >= p.n) {
-        for (int e = lane; e < D * nrows; e += 32) s_x[(e / nrows) * ACT_LD + row0 + (e % nrows)] = 0.f;
-        if (lane < K) {
-          s_idx[ql * K + lane] = -1;
-          s_w[ql * K + lane] = 0.f;
-        }
-        continue;
+      int lk = -1;
+      float w = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+      const bool live = ql < QPT && qi < p.n;
+      if (live) {
+        lk = __ldg(p.knn_idx + qi * K + k);
+        w = __ldg(p.knn_w + qi * K + k);
       }
-      const float qx = __ldg(p.query_xyz + 3 * qi), qy = __ldg(p.query_xyz + 3 * qi + 1),
-                  qz = __ldg(p.query_xyz + 3 * qi + 2);
-      const int lk = lane < K ? __ldg(p.knn_idx + qi * K + lane) : -1;
-      const float w = lane < K ? __ldg(p.knn_w + qi * K + lane) : 0.f;
-      float nx = 0.f, ny = 0.f, nz = 0.f;
+      if (ql < QPT) {
+        s_idx[tid] = lk;
+        s_w[tid] = w;
+      }
       if (lk >= 0) {
         const float* pp = m.nb_points + 3 * (size_t)lk;
-        nx = __fsub_rn(qx, __ldg(pp));
-        ny = __fsub_rn(qy, __ldg(pp + 1));
-        nz = __fsub_rn(qz, __ldg(pp + 2));
+        nx = __fsub_rn(__ldg(p.query_xyz + 3 * qi), __ldg(pp));
+        ny = __fsub_rn(__ldg(p.query_xyz + 3 * qi + 1), __ldg(pp + 1));
+        nz = __fsub_rn(__ldg(p.query_xyz + 3 * qi + 2), __ldg(pp + 2));
         if (m.after_pgo) {
           const float* qq = m.nb_orient + 4 * (size_t)lk;
           quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
         }
-      }
-      if (lane < K) {
-        s_idx[ql * K + lane] = lk;
-        s_w[ql * K + lane] = w;
-      }
-      if (wf) {
-        gather_weighted_t(feat, F, K, lk, w, lane, s_x, row0);
-        const float sx = warp_sum(w * nx), sy = warp_sum(w * ny), sz = warp_sum(w * nz);
-        if (lane == 0) {
-          s_x[(F + 0) * ACT_LD + row0] = sx;
-          s_x[(F + 1) * ACT_LD + row0] = sy;
-          s_x[(F + 2) * ACT_LD + row0] = sz;
+        const float* fr = feat + (size_t)lk * F;
+        if (vec_ok) {
+          for (int j = 0; j < F; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(fr + j));
+            s_x[(j + 0) * ACT_LD + tid] = v.x;
+            s_x[(j + 1) * ACT_LD + tid] = v.y;
+            s_x[(j + 2) * ACT_LD + tid] = v.z;
+            s_x[(j + 3) * ACT_LD + tid] = v.w;
+          }
+        } else {
+          for (int j = 0; j < F; ++j) s_x[j * ACT_LD + tid] = __ldg(fr + j);
         }
-        if (lane < OC) s_go[row0 * 4 + lane] = __ldg(p.dl + qi * OC + lane);
+        for (int c = 0; c < OC; ++c) s_go[tid * 4 + c] = __ldg(p.dl + qi * OC + c) * w;
       } else {
-        const int items = K * F;
-        for (int it0 = 0; it0 < items; it0 += 32) {
-          const int it = it0 + lane;
-          const int k = it / F, j = it - k * F;
-          const int lkk = __shfl_sync(FULL, lk, k < K ? k : 0);
-          if (it < items) s_x[j * ACT_LD + row0 + k] = lkk >= 0 ? __ldg(feat + (size_t)lkk * F + j) : 0.f;
-        }
-        if (lane < K) {
-          s_x[(F + 0) * ACT_LD + row0 + lane] = nx;
-          s_x[(F + 1) * ACT_LD + row0 + lane] = ny;
-          s_x[(F + 2) * ACT_LD + row0 + lane] = nz;
-          for (int c = 0; c < OC; ++c) s_go[(row0 + lane) * 4 + c] = __ldg(p.dl + qi * OC + c) * w;
+        for (int j = 0; j < F; ++j) s_x[j * ACT_LD + tid] = 0.f;
+      }
+      s_x[(F + 0) * ACT_LD + tid] = nx;
+      s_x[(F + 1) * ACT_LD + tid] = ny;
+      s_x[(F + 2) * ACT_LD + tid] = nz;
+    } else {
+      const long long qi = q0 + tid;
+      const bool live = qi < p.n;
+      int lks[PINB200_MAX_K];
+      float ws[PINB200_MAX_K];
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+      for (int k = 0; k < PINB200_MAX_K; ++k) {
+        lks[k] = (live && k < K) ? __ldg(p.knn_idx + qi * K + k) : -1;
+        ws[k] = (live && k < K) ? __ldg(p.knn_w + qi * K + k) : 0.f;
+        if (k < K) {
+          s_idx[tid * K + k] = lks[k];
+          s_w[tid * K + k] = ws[k];
         }
       }
-    }
-    {  // rows of the tile no query maps to (K does not divide 128): keep them finite, their G is 0
-      const int used = QPT * (wf ? 1 : K);
-      if (tid >= used)
-        for (int d = 0; d < D; ++d) s_x[d * ACT_LD + tid] = 0.f;
+      float qx = 0.f, qy = 0.f, qz = 0.f;
+      if (live) {
+        qx = __ldg(p.query_xyz + 3 * qi);
+        qy = __ldg(p.query_xyz + 3 * qi + 1);
+        qz = __ldg(p.query_xyz + 3 * qi + 2);
+        for (int c = 0; c < OC; ++c) s_go[tid * 4 + c] = __ldg(p.dl + qi * OC + c);
+      }
+#pragma unroll
+      for (int k = 0; k < PINB200_MAX_K; ++k) {
+        if (lks[k] < 0) continue;
+        const float* pp = m.nb_points + 3 * (size_t)lks[k];
+        float nx = __fsub_rn(qx, __ldg(pp)), ny = __fsub_rn(qy, __ldg(pp + 1)), nz = __fsub_rn(qz, __ldg(pp + 2));
+        if (m.after_pgo) {
+          const float* qq = m.nb_orient + 4 * (size_t)lks[k];
+          quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
+        }
+        sx = fmaf(ws[k], nx, sx);
+        sy = fmaf(ws[k], ny, sy);
+        sz = fmaf(ws[k], nz, sz);
+      }
+      s_x[(F + 0) * ACT_LD + tid] = sx;
+      s_x[(F + 1) * ACT_LD + tid] = sy;
+      s_x[(F + 2) * ACT_LD + tid] = sz;
+      if (vec_ok) {
+        for (int j = 0; j < F; j += 4) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < PINB200_MAX_K; ++k) {
+            if (lks[k] < 0) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(feat + (size_t)lks[k] * F + j));
+            acc.x = fmaf(ws[k], v.x, acc.x);
+            acc.y = fmaf(ws[k], v.y, acc.y);
+            acc.z = fmaf(ws[k], v.z, acc.z);
+            acc.w = fmaf(ws[k], v.w, acc.w);
+          }
+          s_x[(j + 0) * ACT_LD + tid] = acc.x;
+          s_x[(j + 1) * ACT_LD + tid] = acc.y;
+          s_x[(j + 2) * ACT_LD + tid] = acc.z;
+          s_x[(j + 3) * ACT_LD + tid] = acc.w;
+        }
+      } else {
+        for (int j = 0; j < F; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < PINB200_MAX_K; ++k)
+            if (lks[k] >= 0) acc = fmaf(ws[k], __ldg(feat + (size_t)lks[k] * F + j), acc);
+          s_x[j * ACT_LD + tid] = acc;
+        }
+      }
     }
     __syncthreads();
 
@@ -276,29 +319,34 @@ __global__ void __launch_bounds__(TILE, 1) train_bwd_kernel(const __grid_constan
       }
     }
 
-    // ---------------- D: scatter feature gradients ----------------
-    for (int ql = warp; ql < QPT; ql += TILE / 32) {
-      const long long qi = q0 + ql;
-      if (qi >= p.n) continue;
-      const int lk = lane < K ? s_idx[ql * K + lane] : -1;
-      if (wf) {
-        const float w = lane < K ? s_w[ql * K + lane] : 0.f;
-        for (int j0 = 0; j0 < F; j0 += 32) {
-          const int j = j0 + lane;
-          const float gx = j < F ? s_x[j * ACT_LD + ql] : 0.f;
-          for (int k = 0; k < K; ++k) {
-            const int lkk = __shfl_sync(FULL, lk, k);
-            const float wk = __shfl_sync(FULL, w, k);
-            if (lkk >= 0 && j < F) atomicAdd(p.grad_feat + (size_t)lkk * F + j, wk * gx);
-          }
+    // ---------------- D: scatter feature gradients (thread per tile row, 16-byte vector reductions) ----------------
+    if (!wf) {
+      const int ql = tid / K;
+      const int lk = ql < QPT ? s_idx[tid] : -1;
+      if (lk >= 0) {
+        float* gr = p.grad_feat + (size_t)lk * F;
+        if (vec_ok) {
+          for (int j = 0; j < F; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(gr + j),
+                      make_float4(s_x[(j + 0) * ACT_LD + tid], s_x[(j + 1) * ACT_LD + tid], s_x[(j + 2) * ACT_LD + tid],
+                                  s_x[(j + 3) * ACT_LD + tid]));
+        } else {
+          for (int j = 0; j < F; ++j) atomicAdd(gr + j, s_x[j * ACT_LD + tid]);
         }
-      } else {
-        const int items = K * F, row0 = ql * K;
-        for (int it0 = 0; it0 < items; it0 += 32) {
-          const int it = it0 + lane;
-          const int k = it / F, j = it - k * F;
-          const int lkk = __shfl_sync(FULL, lk, k < K ? k : 0);
-          if (it < items && lkk >= 0) atomicAdd(p.grad_feat + (size_t)lkk * F + j, s_x[j * ACT_LD + row0 + k]);
+      }
+    } else if (q0 + tid < p.n) {
+      for (int k = 0; k < K; ++k) {
+        const int lk = s_idx[tid * K + k];
+        if (lk < 0) continue;
+        const float w = s_w[tid * K + k];
+        float* gr = p.grad_feat + (size_t)lk * F;
+        if (vec_ok) {
+          for (int j = 0; j < F; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(gr + j),
+                      make_float4(w * s_x[(j + 0) * ACT_LD + tid], w * s_x[(j + 1) * ACT_LD + tid],
+                                  w * s_x[(j + 2) * ACT_LD + tid], w * s_x[(j + 3) * ACT_LD + tid]));
+        } else {
+          for (int j = 0; j < F; ++j) atomicAdd(gr + j, w * s_x[j * ACT_LD + tid]);
         }
       }
     }
@@ -341,14 +389,29 @@ static int launch_train(TrainParams& p, cudaStream_t stream) {
     return PINB200_ERR_UNSUPPORTED;
   }
   auto kern = train_bwd_kernel<H, DP>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return PINB200_ERR_CUDA;
+  struct Cached {
+    int dev, occ;
+    size_t smem;
+  };
+  static std::mutex mu;
+  static std::vector<Cached> cache;
+  int occ = 0, dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Cached& c : cache)
+      if (c.dev == dev && c.smem == smem_bytes) occ = c.occ;
+    if (occ == 0) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return PINB200_ERR_CUDA;
+      }
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem_bytes);
+      if (occ < 1) occ = 1;
+      cache.push_back({dev, occ, smem_bytes});
+    }
   }
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem_bytes);
-  if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>(p.n_tiles, (long long)sm_count() * occ);
   kern<<<grid, TILE, smem_bytes, stream>>>(p);
   return check_launch("train_bwd_kernel");

@@ -63,7 +63,9 @@ class Decoder(nn.Module):
     # ---- kernel view ----
     def handle(self, sigmoid_out: bool = False) -> ops.DecoderHandle:
         """pinb200_decoder_view over the live parameter storage (rebuilt if a parameter was re-allocated)."""
-        ps = [p for l in self.layers for p in (l.weight, l.bias)] + [self.lout.weight, self.lout.bias]
+        ps = self._handle.get("ps")
+        if ps is None or ps[-2] is not self.lout.weight:  # Parameter objects are stable; their storage may move
+            ps = [p for l in self.layers for p in (l.weight, l.bias)] + [self.lout.weight, self.lout.bias]
         key = (sigmoid_out,) + tuple(0 if p is None else p.data_ptr() for p in ps)
         h = self._handle.get("h")
         if h is None or self._handle.get("key") != key:
@@ -72,7 +74,7 @@ class Decoder(nn.Module):
                                   None if self.lout.bias is None else self.lout.bias.data,
                                   out_scale=1.0 if sigmoid_out else self.sdf_scale, leaky=self.use_leaky_relu,
                                   sigmoid_out=sigmoid_out)
-            self._handle = {"h": h, "key": key}
+            self._handle = {"h": h, "key": key, "ps": ps}
         return h
 
     def flat_parameters(self) -> torch.Tensor:

@@ -130,6 +130,7 @@ class NeuralPoints(nn.Module):
         self.local_point_certainties = torch.empty((0,), dtype=self.dtype, device=self.device)
         self.local_point_ts_update = torch.empty((0,), device=self.device, dtype=torch.int32)
         self.local_mask = None
+        self._local_idx = None
         self.global2local = None
 
         self._handles = {}
@@ -270,39 +271,47 @@ class NeuralPoints(nn.Module):
                 recent = torch.abs(cur_ts - ts_used) < diff_ts_local
             if reboot_map:
                 recent = recent & (ts_used >= self.reboot_ts)
-            if torch.sum(recent) < 100:
-                recent = torch.ones(n, dtype=torch.bool, device=self.device)
+            # fewer than 100 recent points: keep everything (decided on the device, no host sync)
+            recent = recent | (recent.sum() < 100)
         else:
             recent = torch.ones(n, dtype=torch.bool, device=self.device)
         near = ((self.neural_points - sensor_position) ** 2).sum(-1) < self.local_map_radius**2
         keep = recent & near
-        self.local_neural_points = self.neural_points[keep]
-        self.local_point_orientations = self.point_orientations[keep]
-        self.local_point_certainties = self.point_certainties[keep]
-        self.local_point_ts_update = self.point_ts_update[keep]
-        keep = torch.cat((keep, torch.ones(1, dtype=torch.bool, device=self.device)))  # padding row travels along
-        self.local_mask = keep
-        g2l = torch.cumsum(keep, 0, dtype=torch.int32) - 1
+        # ONE host sync (the local point count); every gather below reuses the index list instead of
+        # re-running a boolean-mask compaction per tensor
+        idx = torch.nonzero(keep).squeeze(1)
+        n_local = idx.shape[0]
+        idx_pad = torch.cat((idx, torch.full((1,), n, dtype=idx.dtype, device=self.device)))  # padding row travels along
+        self.local_neural_points = self.neural_points.index_select(0, idx)
+        self.local_point_orientations = self.point_orientations.index_select(0, idx)
+        self.local_point_certainties = self.point_certainties.index_select(0, idx)
+        self.local_point_ts_update = self.point_ts_update.index_select(0, idx)
+        self.local_mask = torch.cat((keep, torch.ones(1, dtype=torch.bool, device=self.device)))
+        self._local_idx = idx_pad
         # Reference quirk kept on purpose (model/neural_points.py:498): `torch.full_like(bool_mask, -1).long()`
         # evaluates to +1, so neural points OUTSIDE the local map translate to local id 1 instead of "invalid";
         # only the trailing padding entry is -1.  STRICT_REFERENCE_G2L=False gives the intended -1.
-        miss = 1 if (self.STRICT_REFERENCE_G2L and int(keep.sum()) > 2) else -1
-        g2l = torch.where(keep, g2l, torch.full_like(g2l, miss))
+        miss = 1 if (self.STRICT_REFERENCE_G2L and n_local + 1 > 2) else -1
+        g2l = torch.full((n + 1,), miss, dtype=torch.int32, device=self.device)
+        g2l[idx] = torch.arange(n_local, dtype=torch.int32, device=self.device)
         g2l[-1] = -1
-        self.global2local = g2l.contiguous()
-        self.local_geo_features = nn.Parameter(self.geo_features[keep])
+        self.global2local = g2l
+        self.local_geo_features = nn.Parameter(self.geo_features.index_select(0, idx_pad))
         if self.color_features is not None:
-            self.local_color_features = nn.Parameter(self.color_features[keep])
+            self.local_color_features = nn.Parameter(self.color_features.index_select(0, idx_pad))
         self.local_orientation = sensor_orientation
         self._invalidate()
 
     def assign_local_to_global(self):
-        keep = self.local_mask
-        self.geo_features[keep] = self.local_geo_features.data
+        idx_pad = getattr(self, "_local_idx", None)
+        if idx_pad is None or idx_pad.shape[0] != self.local_geo_features.shape[0]:
+            idx_pad = self._local_idx = torch.nonzero(self.local_mask).squeeze(1)
+        idx = idx_pad[:-1]
+        self.geo_features.index_copy_(0, idx_pad, self.local_geo_features.data)
         if self.color_features is not None:
-            self.color_features[keep] = self.local_color_features.data
-        self.point_certainties[keep[:-1]] = self.local_point_certainties
-        self.point_ts_update[keep[:-1]] = self.local_point_ts_update
+            self.color_features.index_copy_(0, idx_pad, self.local_color_features.data)
+        self.point_certainties.index_copy_(0, idx, self.local_point_certainties)
+        self.point_ts_update.index_copy_(0, idx, self.local_point_ts_update)
 
     # ---------------------------------------------------------------- kernel views
     def map_handle(self, query_locally: bool = True) -> ops.MapHandle:
@@ -502,6 +511,7 @@ class NeuralPoints(nn.Module):
         self.local_point_certainties = None
         self.local_point_ts_update = None
         self.local_mask = None
+        self._local_idx = None
         self.global2local = None
         self._handles = {}
         if clean_more:

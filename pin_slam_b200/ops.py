@@ -6,7 +6,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import DecoderView, MapView, QueryOpts, QueryOut
+from ._lib import DecoderView, GnOpts, MapView, QueryOpts, QueryOut
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -72,16 +72,16 @@ class MapHandle:
         v.after_pgo = int(bool(after_pgo))
         if time_filter and (travel_dist is None or cur_ts >= travel_dist.shape[0]):
             raise RuntimeError("time filter needs travel_dist[cur_ts]")
-        # packed 32-byte search records {x, y, z, travel(ts_create), id bits, 0, 0, 0}
+        # packed 32-byte search records {x, y, z, travel(ts_create), id bits, 0, 0, 0}: one launch
         n_g = points.shape[0]
-        rec = torch.zeros((n_g, 8), dtype=torch.float32, device=points.device)
+        rec = torch.empty((n_g, 8), dtype=torch.float32, device=points.device)
         if n_g > 0:
-            rec[:, :3] = points
-            if time_filter:
-                rec[:, 3] = travel_dist[ts_create.long()]
-            ids = global2local[:n_g] if global2local is not None else torch.arange(n_g, dtype=torch.int32,
-                                                                                  device=points.device)
-            rec[:, 4] = ids.contiguous().view(torch.float32)
+            rc = _lib.load().pinb200_build_search_records(
+                _ptr(points, torch.float32), _ptr(ts_create, torch.int32),
+                _ptr(travel_dist, torch.float32) if time_filter else None, _ptr(global2local, torch.int32), n_g,
+                _ptr(rec), _stream())
+            _lib.check(rc, "pinb200_build_search_records")
+            _count()
         self.keep["search_rec"] = rec
         v.search_rec = _ptr(rec, torch.float32)
         self.view = v
@@ -121,13 +121,9 @@ class DecoderHandle:
         return int(_lib.load().pinb200_decoder_param_count(C.byref(self.view)))
 
 
-def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int, weighted_first: bool,
-              training_mode: bool = False, need_grad: bool = True, query_ts: Optional[torch.Tensor] = None,
-              color_dec: Optional[DecoderHandle] = None, color_grad: bool = False,
-              transform: Optional[torch.Tensor] = None, save_knn: bool = False, want_xyz: bool = False,
-              training_rows: int = 0, out: Optional[dict] = None):
-    """K1.  Returns a dict of freshly allocated (or caller-provided `out`) CUDA tensors."""
-    lib = _lib.load()
+def _query_args(xyz, nn_k, weighted_first, training_mode, need_grad, color_dec, color_grad, transform, save_knn,
+                want_xyz, training_rows, out):
+    """Output buffers (held in the dict `o`) + the two plain-C structs of a K1 launch."""
     n = xyz.shape[0]
     dev = xyz.device
     o = {} if out is None else out
@@ -160,12 +156,46 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
             qo.color_grad = _ptr(buf("color_grad", (n, cc, 3)))
     opts = QueryOpts(int(nn_k), int(bool(weighted_first)), int(bool(training_mode)), int(bool(need_grad)),
                      int(training_rows), _ptr(transform, torch.float64))
+    return o, qo, opts
+
+
+def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int, weighted_first: bool,
+              training_mode: bool = False, need_grad: bool = True, query_ts: Optional[torch.Tensor] = None,
+              color_dec: Optional[DecoderHandle] = None, color_grad: bool = False,
+              transform: Optional[torch.Tensor] = None, save_knn: bool = False, want_xyz: bool = False,
+              training_rows: int = 0, out: Optional[dict] = None):
+    """K1.  Returns a dict of freshly allocated (or caller-provided `out`) CUDA tensors."""
+    lib = _lib.load()
+    o, qo, opts = _query_args(xyz, nn_k, weighted_first, training_mode, need_grad, color_dec, color_grad, transform,
+                              save_knn, want_xyz, training_rows, out)
     rc = lib.pinb200_query_sdf(C.byref(mh.view), C.byref(dec.view),
                                C.byref(color_dec.view) if color_dec is not None else None,
-                               _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), n, C.byref(opts), C.byref(qo),
-                               _stream())
+                               _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), xyz.shape[0], C.byref(opts),
+                               C.byref(qo), _stream())
     _lib.check(rc, "pinb200_query_sdf")
     _count(2 if color_dec is not None else 1)
+    return o
+
+
+def track_iterations(mh: MapHandle, dec: DecoderHandle, src: torch.Tensor, t_dev: torch.Tensor, n_iter: int, *,
+                     nn_k: int, weighted_first: bool, min_nn, min_grad_norm, max_grad_norm, max_sdf_std, gm_dist,
+                     gm_grad, lm_lambda, sums, result, sdf_label=None, normals=None, color_dec=None, color_grad=False,
+                     color_obs=None, color_mode=0, w_photo=0.0, out: Optional[dict] = None):
+    """`n_iter` x (K1 with the device pose `t_dev` + K4 updating it in place) from ONE host call.
+    Returns the K1 output dict of the last iteration; `result`/`sums` hold the last K4 outputs."""
+    lib = _lib.load()
+    o, qo, opts = _query_args(src, nn_k, weighted_first, False, True, color_dec, color_grad, t_dev, False, True, 0, out)
+    g = GnOpts(_ptr(sdf_label, torch.float32), _ptr(normals, torch.float32),
+               _ptr(color_obs, torch.float32) if color_mode else None,
+               0 if color_obs is None else int(color_obs.shape[1]), int(color_mode), int(min_nn), float(min_grad_norm),
+               float(max_grad_norm), float(max_sdf_std), float(gm_dist or 0.0), float(gm_grad or 0.0), float(lm_lambda),
+               float(w_photo), _ptr(sums, torch.float64), _ptr(result, torch.float64))
+    rc = lib.pinb200_track_iterations(C.byref(mh.view), C.byref(dec.view),
+                                      C.byref(color_dec.view) if color_dec is not None else None,
+                                      _ptr(src, torch.float32), src.shape[0], C.byref(opts), C.byref(qo), C.byref(g),
+                                      int(n_iter), _stream())
+    _lib.check(rc, "pinb200_track_iterations")
+    _count(n_iter * ((2 if color_dec is not None else 1) + 2))
     return o
 
 

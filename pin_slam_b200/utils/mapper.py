@@ -330,28 +330,26 @@ class Mapper:
         n_cf = cfeat.numel() if color_on else 0
         n_cd = cflat.numel() if color_on else 0
         train_cdec = color_on and any(p.requires_grad for p in self.color_mlp.parameters())
-        # one contiguous reduction buffer: [feature grads | decoder grads | colour-feature grads | colour-decoder grads]
-        red = torch.zeros(feat.numel() + n_dec + n_cf + n_cd, device=dev, dtype=torch.float32)
-        o0 = feat.numel()
-        gfeat = red[:o0].view_as(feat)
-        gdec = red[o0: o0 + n_dec]
-        gcfeat = red[o0 + n_dec: o0 + n_dec + n_cf].view_as(cfeat) if color_on else None
-        gcdec = red[o0 + n_dec + n_cf: o0 + n_dec + n_cf + n_cd] if color_on else None
-        cert_at_start = npm.local_point_certainties.clone() if dist_on else None
-        mf, vf = torch.zeros_like(feat), torch.zeros_like(feat)
-        md, vd = torch.zeros_like(flat), torch.zeros_like(flat)
+        # ONE zero-filled arena: [feature grads | decoder grads | colour-feature grads | colour-decoder grads]
+        # (the data-parallel reduction buffer `red`), then the Adam moments of the same four blocks, then the
+        # loss accumulators
+        n_red = feat.numel() + n_dec + n_cf + n_cd
+        arena = torch.zeros(3 * n_red + 4, device=dev, dtype=torch.float32)
+        red, m_all, v_all = arena[:n_red], arena[n_red: 2 * n_red], arena[2 * n_red: 3 * n_red]
+        o0, o1, o2 = feat.numel(), feat.numel() + n_dec, feat.numel() + n_dec + n_cf
+        gfeat, mf, vf = (b[:o0].view_as(feat) for b in (red, m_all, v_all))
+        gdec, md, vd = (b[o0:o1] for b in (red, m_all, v_all))
+        gcfeat = gcdec = mcf = vcf = mcd = vcd = closs = None
         if color_on:
-            mcf, vcf = torch.zeros_like(cfeat), torch.zeros_like(cfeat)
-            mcd, vcd = torch.zeros_like(cflat), torch.zeros_like(cflat)
-            closs = torch.zeros(1, device=dev)
-        losses = torch.zeros(2, device=dev)
+            gcfeat, mcf, vcf = (b[o1:o2].view_as(cfeat) for b in (red, m_all, v_all))
+            gcdec, mcd, vcd = (b[o2:n_red] for b in (red, m_all, v_all))
+            closs = arena[3 * n_red + 2: 3 * n_red + 3]
+        losses = arena[3 * n_red: 3 * n_red + 2]
+        cert_at_start = npm.local_point_certainties.clone() if dist_on else None
         dec_step = cfg.gradient_decimation
         eik_on = cfg.ekional_loss_on and cfg.weight_e > 0
         eps_num = cfg.voxel_size_m * cfg.num_grad_step_ratio
-        shifts = torch.zeros(6, 1, 3, device=dev)
-        for a in range(3):
-            shifts[2 * a, 0, a] = eps_num
-            shifts[2 * a + 1, 0, a] = -eps_num
+        shifts = None
         out = self._work
         for it in range(iter_count):
             fused_batch = (type(self).get_batch is Mapper.get_batch and "get_batch" not in self.__dict__
@@ -371,6 +369,10 @@ class Mapper:
                     coord = (tf[:, :3, :3] @ coord.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
                 n = coord.shape[0]
                 if eik_on:
+                    if shifts is None:
+                        e = eps_num
+                        shifts = torch.tensor([[e, 0, 0], [-e, 0, 0], [0, e, 0], [0, -e, 0], [0, 0, e], [0, 0, -e]],
+                                              device=dev, dtype=torch.float32).unsqueeze(1)
                     sub = coord[::dec_step]
                     ne = sub.shape[0]
                     rows = torch.cat((coord, (sub.unsqueeze(0) + shifts).reshape(-1, 3)), 0)

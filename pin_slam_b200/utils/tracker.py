@@ -81,6 +81,24 @@ class Tracker:
                            color_grad=o.get("color_grad") if color_mode == 2 else None, color_mode=color_mode,
                            w_photo=cfg.photometric_loss_weight)
 
+    def _iterate(self, src, t_dev, n_iter, source_normals, source_sdf, source_colors, cdec, cgrad, cmode):
+        """n_iter x (K1 + K4) on the device pose `t_dev` from one host call (pinb200_track_iterations)."""
+        cfg, npm = self.config, self.neural_points
+        if self._sums is None or self._sums.device != src.device:
+            self._sums = torch.empty(64, dtype=torch.float64, device=src.device)
+            self._result = torch.empty(32, dtype=torch.float64, device=src.device)
+        o = ops.track_iterations(
+            npm.map_handle(self.reg_local_map), self.sdf_mlp.handle(), src, t_dev, n_iter, nn_k=cfg.query_nn_k,
+            weighted_first=cfg.weighted_first, min_nn=cfg.track_mask_query_nn_k, min_grad_norm=cfg.reg_min_grad_norm,
+            max_grad_norm=cfg.reg_max_grad_norm, max_sdf_std=cfg.surface_sample_range_m * cfg.max_sdf_std_ratio,
+            gm_dist=cfg.reg_GM_dist_m if cfg.reg_GM_dist_m > 0 else None,
+            gm_grad=cfg.reg_GM_grad if cfg.reg_GM_grad > 0 else None, lm_lambda=cfg.reg_lm_lambda, sums=self._sums,
+            result=self._result, sdf_label=source_sdf, normals=source_normals,
+            color_dec=None if cdec is None else cdec.handle(sigmoid_out=True), color_grad=cgrad,
+            color_obs=None if not cmode else source_colors[:, : cfg.color_channel].contiguous(), color_mode=cmode,
+            w_photo=cfg.photometric_loss_weight, out=self._out)
+        return o, self._result, self._sums
+
     def registration_step(self, points, normals, sdf_labels, colors, min_grad_norm, max_grad_norm, GM_dist=None,
                           GM_grad=None, lm_lambda=0.0, vis_weight_pc=False):
         """One GN/LM step on already transformed points (reference: utils/tracker.py:367-611).
@@ -133,12 +151,7 @@ class Tracker:
         cov_mat, eigenvalues = None, None
         res_cm, n_valid, i = 0.0, 0, 0
         for i in range(iter_n):
-            o = self.neural_points.query_sdf(src, self.sdf_mlp, query_locally=self.reg_local_map, need_grad=True,
-                                             transform=T_dev, want_xyz=True, color_decoder=cdec, color_grad=cgrad,
-                                             out=self._out)
-            res, sums = self._gn(o["xyz"], o, source_normals, source_sdf, cfg.reg_min_grad_norm,
-                                 cfg.reg_max_grad_norm, gm_dist, gm_grad, cfg.reg_lm_lambda, T_dev, source_colors,
-                                 cmode)
+            _, res, sums = self._iterate(src, T_dev, 1, source_normals, source_sdf, source_colors, cdec, cgrad, cmode)
             r = res.cpu().numpy()  # the one host sync of the iteration
             n_valid, res_cm = int(r[16]), float(r[17])
             dT = r[:16].reshape(4, 4)
@@ -176,11 +189,5 @@ class Tracker:
         T_dev = init_pose.to(dtype=torch.float64).clone().contiguous()
         src = source_points.contiguous()
         cdec, cgrad, cmode = self._color_setup(source_colors)
-        for _ in range(n_iter):
-            o = self.neural_points.query_sdf(src, self.sdf_mlp, query_locally=self.reg_local_map, need_grad=True,
-                                             transform=T_dev, want_xyz=True, color_decoder=cdec, color_grad=cgrad,
-                                             out=self._out)
-            self._gn(o["xyz"], o, source_normals, source_sdf, cfg.reg_min_grad_norm, cfg.reg_max_grad_norm,
-                     cfg.reg_GM_dist_m if cfg.reg_GM_dist_m > 0 else None,
-                     cfg.reg_GM_grad if cfg.reg_GM_grad > 0 else None, cfg.reg_lm_lambda, T_dev, source_colors, cmode)
+        self._iterate(src, T_dev, n_iter, source_normals, source_sdf, source_colors, cdec, cgrad, cmode)
         return T_dev, self._result

@@ -10,9 +10,32 @@ loop.step(0, timed=False, map_iters=60)
 for f in range(1, 4):
     loop.step(f)
 torch.cuda.synchronize()
+
+
+def _ranged(fn, name):
+    def wrapped(*a, **k):
+        with torch.profiler.record_function(name):
+            return fn(*a, **k)
+    return wrapped
+
+
+loop.mapper.mapping = _ranged(loop.mapper.mapping, "mapping")
+loop.tracker.track_fixed = _ranged(loop.tracker.track_fixed, "tracker")
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for f in range(4, 7):
         loop.step(f)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
 print(loop.times[-3:])
+# kernel timeline of the last profiled frame (gpurun_out/frame_timeline.json): [name, start_us, dur_us]
+os.makedirs("gpurun_out", exist_ok=True)
+prof.export_chrome_trace("gpurun_out/frame_trace.json")
+import json
+tr = json.load(open("gpurun_out/frame_trace.json"))
+ev = [(e["name"], e["ts"], e["dur"]) for e in tr["traceEvents"]
+      if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+ev.sort(key=lambda x: x[1])
+rng = [(e["name"], e["ts"], e["dur"]) for e in tr["traceEvents"]
+       if e.get("ph") == "X" and e.get("cat") in ("user_annotation", "gpu_user_annotation")]
+json.dump({"kernels": ev, "ranges": rng}, open("gpurun_out/frame_timeline.json", "w"))
+os.remove("gpurun_out/frame_trace.json")
