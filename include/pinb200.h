@@ -224,9 +224,16 @@ typedef struct pinb200_gn_opts {
   const float* sdf_label;  /* [N] or NULL */
   const float* normals;    /* [N,3] or NULL */
   const float* color_obs;  /* [N,Cc] or NULL */
-  int32_t color_channels, color_mode;
+  int32_t color_channels;
+  int32_t color_mode;
   int32_t min_nn;
-  float min_grad_norm, max_grad_norm, max_sdf_std, gm_dist, gm_grad, lm_lambda, w_photo;
+  float min_grad_norm;
+  float max_grad_norm;
+  float max_sdf_std;
+  float gm_dist;
+  float gm_grad;
+  float lm_lambda;
+  float w_photo;
   double* sums;   /* [64] */
   double* result; /* [32] */
 } pinb200_gn_opts;

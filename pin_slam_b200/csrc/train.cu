@@ -358,6 +358,12 @@ __global__ void __launch_bounds__(TILE, PINB_K2_MIN_CTAS) train_bwd_kernel(const
   }
 }
 
+}  // namespace pinb
+
+#include "train_mma.cuh"
+
+namespace pinb {
+
 template <int H, int DP>
 static int launch_train(TrainParams& p, cudaStream_t stream) {
   TrainLayout l{};
@@ -462,6 +468,11 @@ extern "C" int pinb200_train_backward(const pinb200_map_view* map, const pinb200
   p.grad_dec = grad_dec;
   const int D = dec->in_dim;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    bool handled = false;  // tensor-core kernel for the common decoder shapes, SIMT kernel otherwise
+    const int rc = dispatch_train_mma(p, st, &handled);
+    if (handled) return rc;
+  }
   if (D <= 12) return launch_train<64, 12>(p, st);
   if (D <= 20) return launch_train<64, 20>(p, st);
   if (D <= 36) return launch_train<64, 36>(p, st);

@@ -6,6 +6,7 @@ Only `tracker` (T3-T2) and `mapping` (T6-T5) are timed, like the reference's `ti
 frames/s metric is defined on; preprocessing and `Mapper.process_frame` (map growth,
 sampling: section 8 f1/f2 "next" rows) run untimed between them.
 """
+import time
 import types
 
 import numpy as np
@@ -36,6 +37,7 @@ class FrameLoop:
         self.travel = [0.0]
         self.poses = []
         self.times = []  # (tracker_ms, mapping_ms) per frame
+        self.host_issue_times = []
 
     def preprocess(self, frame_id):
         """Synthetic scan -> voxel(0.08) + range crop -> map points; voxel(0.6) -> registration source."""
@@ -53,7 +55,7 @@ class FrameLoop:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         if frame_id == 0:
             pose = gt.to(self.dev)
-            trk_ms = 0.0
+            trk_ms = trk_cpu_ms = 0.0
         else:
             # constant-velocity initial guess (pin_slam.py: uniform motion model); the very first motion
             # estimate comes from the synthetic trajectory (a real run starts from rest)
@@ -63,7 +65,9 @@ class FrameLoop:
             else:
                 guess = last @ torch.linalg.inv(self.poses[-2]) @ last
             ev[0].record()
+            c0 = time.perf_counter()
             pose, _ = self.tracker.track_fixed(source, guess, self.n_track_iter)
+            trk_cpu_ms = (time.perf_counter() - c0) * 1e3
             ev[1].record()
             pose = pose.clone()
         self.poses.append(pose)
@@ -77,7 +81,9 @@ class FrameLoop:
         self.mapper.process_frame(scan, None, pose, frame_id)
         n_iter = self.n_map_iter if map_iters is None else map_iters
         ev[2].record()
+        c0 = time.perf_counter()
         self.mapper.mapping(n_iter)
+        map_cpu_ms = (time.perf_counter() - c0) * 1e3
         ev[3].record()
         torch.cuda.synchronize()
         if frame_id > 0:
@@ -85,6 +91,7 @@ class FrameLoop:
         map_ms = ev[2].elapsed_time(ev[3])
         if timed:
             self.times.append((trk_ms, map_ms))
+            self.host_issue_times.append((trk_cpu_ms, map_cpu_ms))  # host time to ISSUE the launches (no sync)
         err = float((pose[:3, 3].cpu() - gt[:3, 3]).norm())
         return {"frame": frame_id, "tracker_ms": trk_ms, "mapping_ms": map_ms, "n_source": int(source.shape[0]),
                 "n_scan": int(scan.shape[0]), "local_points": npm.local_count(), "pool": self.mapper.pool_sample_count,

@@ -7,9 +7,11 @@ from pin_slam_b200.frame_loop import FrameLoop
 
 loop = FrameLoop(device="cuda")
 loop.step(0, timed=False, map_iters=60)
-for f in range(1, 4):
+for f in range(1, 10):
     loop.step(f)
 torch.cuda.synchronize()
+print("device ms (tracker, mapping):", [tuple(round(x, 3) for x in t) for t in loop.times[-5:]])
+print("host issue ms (tracker, mapping):", [tuple(round(x, 3) for x in t) for t in loop.host_issue_times[-5:]])
 
 
 def _ranged(fn, name):
@@ -22,7 +24,7 @@ def _ranged(fn, name):
 loop.mapper.mapping = _ranged(loop.mapper.mapping, "mapping")
 loop.tracker.track_fixed = _ranged(loop.tracker.track_fixed, "tracker")
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    for f in range(4, 7):
+    for f in range(10, 13):
         loop.step(f)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))

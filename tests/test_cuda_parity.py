@@ -60,6 +60,20 @@ def assert_rel_close(got, ref, tol, floor, ref64=None, kink_rows=0):
     assert not bad.any(), f"max err {err.max():.3e} (bound {bound.min():.3e}); {int(bad.sum())} bad"
 
 
+def assert_decoder_grad_close(got, ref, ref64):
+    """Decoder gradients are sums over ALL sample rows, so one ReLU kink flip (see assert_rel_close) shifts every
+    entry a little instead of one row a lot: tight bound first, else the kink-level bound 5e-3 of the largest
+    entry on the maximum and 1e-3 on the median (a wrong kernel is off by O(1))."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max()
+    try:
+        assert_rel_close(got, ref, 1e-4, scale * 5e-2, ref64)
+    except AssertionError:
+        err = np.abs(got - ref)
+        assert err.max() <= 5e-3 * scale and np.median(err) <= 1e-3 * scale, \
+            f"decoder gradient: max err {err.max():.3e}, median {np.median(err):.3e}, scale {scale:.3e}"
+
+
 def oracle64(m, dec, q, k, wf, ref32, **kw):
     """fp64 run of the oracle; rows whose neighbour set differs from the fp32 run (a query within one ulp
     of a voxel boundary) fall back to the fp32 values."""
@@ -364,6 +378,53 @@ def test_train_backward_matches_autograd(name):
     np.testing.assert_allclose(mh.keep["certainty"].cpu().numpy(), m.local_point_certainties.numpy(), rtol=1e-5,
                                atol=1e-5)
     assert np.array_equal(mh.keep["ts_update"].cpu().numpy(), m.local_point_ts_update.numpy())
+
+
+@pytest.mark.parametrize("F,K,L,wf,oc,pgo", [(8, 6, 1, False, 1, False), (8, 6, 1, True, 1, False),
+                                               (4, 4, 1, True, 1, True), (16, 5, 2, False, 1, False),
+                                               (32, 8, 2, True, 1, False), (64, 8, 1, False, 1, True),
+                                               (64, 3, 2, True, 3, False), (8, 6, 2, False, 3, False),
+                                               (16, 6, 3, True, 1, False)])
+def test_train_backward_vs_autograd_synthetic(F, K, L, wf, oc, pgo):
+    """K2 on every tensor-core instantiation (1-2 hidden layers) and the SIMT fallback (3 layers): gradients of
+    sum(out * dl) w.r.t. the feature table and the decoder, against fp32/fp64 autograd through the oracle."""
+    m = synthetic_map(n_surface=30000, seed=F + K + L, resolution=0.4, buffer_size=200003, feature_dim=F,
+                      after_pgo=pgo, local_radius=14.0, diff_td=3.0)
+    sig = oc > 1
+    dec = po.make_decoder(F + 3, 64, L, oc, 0.044, seed=L)
+    n = 7001  # not a multiple of the tile size
+    q = queries_near(m, n, seed=9)
+    q[:5] = torch.tensor([300.0, -200.0, 50.0])  # no neighbours
+    dl = torch.randn(n, oc, generator=torch.Generator().manual_seed(1))
+
+    def reference(mm, dd, qq, dll):
+        mm.local_geo_features.requires_grad_(True)
+        dd.requires_grad_(True)
+        vec, _, w, _, _ = po.query_feature(mm, qq, None, K, wf, training_mode=False)
+        if wf:
+            out = po.decoder_color(dd, vec) if sig else po.decoder_sdf(dd, vec).unsqueeze(1)
+        else:
+            flat = vec.reshape(-1, F + 3)
+            o = po.decoder_color(dd, flat) if sig else po.decoder_sdf(dd, flat).unsqueeze(1)
+            out = (o.view(qq.shape[0], K, oc) * w).sum(1)
+        (out * dll).sum().backward()
+        return mm.local_geo_features.grad, torch.cat([p.grad.reshape(-1) for p in dd.tensors()])
+
+    gf_ref, gd_ref = reference(m.clone(), dec.clone(), q, dl)
+    gf64, gd64 = reference(m.clone().double(), dec.double(), q.double(), dl.double())
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec, sigmoid_out=sig)
+    idx, _, w, _ = ops().knn_search(mh, q.cuda(), K)[:4]
+    gfeat = torch.zeros_like(mh.keep["geo_feat"])
+    gdec = torch.zeros(dh.param_count(), device="cuda")
+    ops().train_backward(mh, dh, mh.keep["geo_feat"], q.cuda(), idx, w, dl.cuda(), wf, gfeat, gdec)
+    # 3xTF32 keeps ~21 mantissa bits per product: bound = 1e-4 relative with a floor of 5 % of the largest entry
+    # (5e-6 of the gradient scale), plus the fp32 reference's own distance to fp64; ReLU kink rows as documented
+    assert_rel_close(gfeat.cpu(), gf_ref, 1e-4, float(gf_ref.abs().max()) * 5e-2, gf64, kink_rows=8)
+    assert_decoder_grad_close(gdec.cpu(), gd_ref, gd64)
+    # second call accumulates
+    ops().train_backward(mh, dh, mh.keep["geo_feat"], q.cuda(), idx, w, dl.cuda(), wf, gfeat, gdec)
+    assert_decoder_grad_close(0.5 * gdec.cpu(), gd_ref, gd64)
 
 
 def test_adam_matches_torch():
