@@ -248,6 +248,52 @@ int pinb200_track_iterations(const pinb200_map_view* map, const pinb200_decoder_
                              const pinb200_query_opts* opts, const pinb200_query_out* out,
                              const pinb200_gn_opts* gn, int32_t n_iter, void* stream);
 
+/* The geometry-only training loop of Mapper.mapping (utils/mapper.py:600-844) issued by ONE host call. */
+typedef struct pinb200_map_train_opts {
+  /* sample pool (utils/mapper.py:482-503) and the pre-drawn batch indices [n_iter, bs] (torch.randint stream) */
+  const float* coord_pool;
+  const float* label_pool;
+  const int32_t* ts_pool;
+  const float* weight_pool;
+  const int64_t* index;
+  int64_t bs;
+  int32_t decimation; /* every decimation-th sample gets the 6 numerical-gradient copies; 0 = no Eikonal term */
+  float eik_eps;
+  /* loss (pinb200_mapping_loss) */
+  float sigma;
+  float weight_e;
+  int32_t loss_weight_on;
+  /* Adam (pinb200_adam_step); the decoder is stepped only if train_decoder != 0 */
+  double lr;
+  double beta1;
+  double beta2;
+  double eps;
+  double weight_decay;
+  int32_t train_decoder;
+  int32_t first_step; /* 1-based Adam step of the first iteration */
+  /* workspaces, rows = bs + 6*ceil(bs/decimation) */
+  float* rows;       /* [rows,3] */
+  float* label;      /* [bs] */
+  int32_t* ts;       /* [bs] */
+  float* weight;     /* [bs] */
+  float* dloss;      /* [rows] */
+  float* losses;     /* [2] accumulated bce / eikonal over the iterations */
+  float* feat;       /* [n_nb+1,F] the trained feature table (== map->geo_feat) */
+  float* dec_flat;   /* flat decoder parameter vector the decoder view points into */
+  float* grad_feat;  /* zero on entry, zero on exit */
+  float* grad_dec;   /* zero on entry, zero on exit */
+  float* m_feat;     /* Adam moments */
+  float* v_feat;
+  float* m_dec;
+  float* v_dec;
+} pinb200_map_train_opts;
+
+/* n_iter x [assemble_batch -> query_sdf(training) -> mapping_loss -> train_backward -> adam(decoder) -> adam(features)].
+ * `out` must provide sdf / sdf_std / nn_count / certainty / knn_idx / knn_dist2 / knn_weight / knn_gidx for `rows` rows. */
+int pinb200_map_iterations(const pinb200_map_view* map, const pinb200_decoder_view* dec, int32_t nn_k,
+                           int32_t weighted_first, const pinb200_map_train_opts* t, const pinb200_query_out* out,
+                           int32_t n_iter, void* stream);
+
 /* Colour head of the training loss (utils/mapper.py:804-812, utils/loss.py:31-41): L1 between the predicted and
  * the measured colour on surface samples (|sdf_label| < surface_range), mean over (n_surface x Cc) elements,
  * times weight_i.  n_surface is read from the device (count computed by the caller without a sync).

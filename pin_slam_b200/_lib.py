@@ -55,6 +55,17 @@ class GnOpts(C.Structure):
                 ("result", c_f64p)]
 
 
+class MapTrainOpts(C.Structure):
+    _fields_ = [("coord_pool", c_f32p), ("label_pool", c_f32p), ("ts_pool", c_i32p), ("weight_pool", c_f32p),
+                ("index", C.c_void_p), ("bs", C.c_int64), ("decimation", C.c_int32), ("eik_eps", C.c_float),
+                ("sigma", C.c_float), ("weight_e", C.c_float), ("loss_weight_on", C.c_int32), ("lr", C.c_double),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+                ("train_decoder", C.c_int32), ("first_step", C.c_int32), ("rows", c_f32p), ("label", c_f32p),
+                ("ts", c_i32p), ("weight", c_f32p), ("dloss", c_f32p), ("losses", c_f32p), ("feat", c_f32p),
+                ("dec_flat", c_f32p), ("grad_feat", c_f32p), ("grad_dec", c_f32p), ("m_feat", c_f32p),
+                ("v_feat", c_f32p), ("m_dec", c_f32p), ("v_dec", c_f32p)]
+
+
 # name -> (restype, argtypes); every symbol include/pinb200.h declares
 SIGNATURES = {
     "pinb200_version": (C.c_int, []),
@@ -83,6 +94,8 @@ SIGNATURES = {
     "pinb200_track_iterations": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,
                                            C.c_int64, C.POINTER(QueryOpts), C.POINTER(QueryOut), C.POINTER(GnOpts),
                                            C.c_int32, C.c_void_p]),
+    "pinb200_map_iterations": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.c_int32, C.c_int32,
+                                         C.POINTER(MapTrainOpts), C.POINTER(QueryOut), C.c_int32, C.c_void_p]),
     "pinb200_color_loss": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p]),
 }

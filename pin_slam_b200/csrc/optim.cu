@@ -240,3 +240,57 @@ extern "C" int pinb200_mapping_loss(const float* sdf, const float* sdf_label, co
                                                               loss_weight_on, weight_e, eik_eps, grad_scale, dloss_dsdf, losses);
   return check_launch("mapping_loss_kernel");
 }
+
+
+extern "C" int pinb200_map_iterations(const pinb200_map_view* map, const pinb200_decoder_view* dec, int32_t nn_k,
+                                      int32_t weighted_first, const pinb200_map_train_opts* t,
+                                      const pinb200_query_out* out, int32_t n_iter, void* stream) {
+  if (!map || !dec || !t || !out || !t->index || !t->rows || !t->label || !t->ts || !t->weight || !t->dloss ||
+      !t->losses || !t->feat || !t->dec_flat || !t->grad_feat || !t->grad_dec || !t->m_feat || !t->v_feat ||
+      !t->m_dec || !t->v_dec || !out->sdf || !out->knn_idx || !out->knn_weight) {
+    set_error("map_iterations: null argument");
+    return PINB200_ERR_BAD_ARG;
+  }
+  const int64_t n = t->bs;
+  const int64_t ne = t->decimation > 0 ? (n + t->decimation - 1) / t->decimation : 0;
+  const int64_t rows = n + 6 * ne;
+  const int64_t n_feat = ((int64_t)map->n_nb + 1) * map->feature_dim;
+  const int64_t n_dec = pinb200_decoder_param_count(dec);
+  pinb200_query_opts qo{};
+  qo.nn_k = nn_k;
+  qo.weighted_first = weighted_first;
+  qo.training_mode = 1;
+  qo.need_grad = 0;
+  qo.training_rows = n;
+  qo.transform = nullptr;
+  for (int it = 0; it < n_iter; ++it) {
+    int rc = pinb200_assemble_batch(t->coord_pool, t->label_pool, t->ts_pool, t->weight_pool, nullptr, 0,
+                                    t->index + (int64_t)it * n, n, t->decimation, t->eik_eps, t->rows, t->label, t->ts,
+                                    t->weight, nullptr, stream);
+    if (rc) return rc;
+    rc = pinb200_query_sdf(map, dec, nullptr, t->rows, t->ts, rows, &qo, out, stream);
+    if (rc) return rc;
+    rc = pinb200_mapping_loss(out->sdf, t->label, t->weight, n, ne, t->sigma, t->loss_weight_on,
+                              ne > 0 ? t->weight_e : 0.f, t->eik_eps, 1.0f, t->dloss, t->losses, stream);
+    if (rc) return rc;
+    rc = pinb200_train_backward(map, dec, t->feat, t->rows, out->knn_idx, out->knn_weight, t->dloss, rows, nn_k,
+                                weighted_first, t->grad_feat, t->grad_dec, stream);
+    if (rc) return rc;
+    const int step = t->first_step + it;
+    if (t->train_decoder) {
+      rc = pinb200_adam_step(t->dec_flat, t->grad_dec, t->m_dec, t->v_dec, n_dec, t->lr, t->beta1, t->beta2, t->eps, 0.0,
+                             step, stream);
+      if (rc) return rc;
+    } else {
+      cudaError_t e = cudaMemsetAsync(t->grad_dec, 0, (size_t)n_dec * sizeof(float), (cudaStream_t)stream);
+      if (e != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return PINB200_ERR_CUDA;
+      }
+    }
+    rc = pinb200_adam_step(t->feat, t->grad_feat, t->m_feat, t->v_feat, n_feat, t->lr, t->beta1, t->beta2, t->eps,
+                           t->weight_decay, step, stream);
+    if (rc) return rc;
+  }
+  return PINB200_OK;
+}

@@ -6,7 +6,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import DecoderView, GnOpts, MapView, QueryOpts, QueryOut
+from ._lib import DecoderView, GnOpts, MapTrainOpts, MapView, QueryOpts, QueryOut
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -344,3 +344,44 @@ def assemble_batch(coord_pool, label_pool, ts_pool, weight_pool, color_pool, ind
     _lib.check(rc, "pinb200_assemble_batch")
     _count()
     return rows, label, ts, weight, color, ne
+
+
+def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weighted_first, coord_pool, label_pool,
+                   ts_pool, weight_pool, index, decimation, eik_eps, sigma, weight_e, loss_weight_on, lr, beta1, beta2,
+                   eps, weight_decay, train_decoder, first_step, feat, dec_flat, grad_feat, grad_dec, m_feat, v_feat,
+                   m_dec, v_dec, losses, work: dict):
+    """The geometry-only training loop of Mapper.mapping in ONE host call (pinb200_map_iterations).
+    `index` [n_iter, bs] int64 are the pre-drawn batch indices; scratch buffers live in `work`."""
+    lib = _lib.load()
+    bs = index.shape[1]
+    dev = index.device
+    ne = (bs + decimation - 1) // decimation if decimation > 0 else 0
+    rows = bs + 6 * ne
+
+    def buf(name, shape, dtype=torch.float32):
+        t = work.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            work[name] = t
+        return t
+
+    rows_t = buf("rows", (rows, 3))
+    _, qo, _ = _query_args(rows_t, nn_k, weighted_first, True, False, None, False, None, True, False, bs, work)
+    t = MapTrainOpts()
+    t.coord_pool, t.label_pool = _ptr(coord_pool, torch.float32), _ptr(label_pool, torch.float32)
+    t.ts_pool, t.weight_pool = _ptr(ts_pool, torch.int32), _ptr(weight_pool, torch.float32)
+    t.index, t.bs, t.decimation, t.eik_eps = _ptr(index, torch.int64), bs, int(decimation), float(eik_eps)
+    t.sigma, t.weight_e, t.loss_weight_on = float(sigma), float(weight_e), int(bool(loss_weight_on))
+    t.lr, t.beta1, t.beta2, t.eps, t.weight_decay = float(lr), float(beta1), float(beta2), float(eps), float(weight_decay)
+    t.train_decoder, t.first_step = int(bool(train_decoder)), int(first_step)
+    t.rows = _ptr(rows_t)
+    t.label, t.ts, t.weight = _ptr(buf("label", (bs,))), _ptr(buf("ts", (bs,), torch.int32)), _ptr(buf("weight", (bs,)))
+    t.dloss, t.losses = _ptr(buf("dl", (rows,))), _ptr(losses, torch.float32)
+    t.feat, t.dec_flat = _ptr(feat, torch.float32), _ptr(dec_flat, torch.float32)
+    t.grad_feat, t.grad_dec = _ptr(grad_feat, torch.float32), _ptr(grad_dec, torch.float32)
+    t.m_feat, t.v_feat = _ptr(m_feat, torch.float32), _ptr(v_feat, torch.float32)
+    t.m_dec, t.v_dec = _ptr(m_dec, torch.float32), _ptr(v_dec, torch.float32)
+    rc = lib.pinb200_map_iterations(C.byref(mh.view), C.byref(dec.view), int(nn_k), int(bool(weighted_first)),
+                                    C.byref(t), C.byref(qo), int(n_iter), _stream())
+    _lib.check(rc, "pinb200_map_iterations")
+    _count(n_iter * 6)

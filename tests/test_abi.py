@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
 
 @pytest.mark.parametrize("cname,pyname", [("pinb200_map_view", "MapView"), ("pinb200_decoder_view", "DecoderView"),
                                           ("pinb200_query_opts", "QueryOpts"), ("pinb200_query_out", "QueryOut"),
-                                          ("pinb200_gn_opts", "GnOpts")])
+                                          ("pinb200_gn_opts", "GnOpts"), ("pinb200_map_train_opts", "MapTrainOpts")])
 def test_ctypes_structs_mirror_header(cname, pyname):
     from pin_slam_b200 import _lib
 
@@ -63,15 +63,15 @@ def test_struct_sizes_match_c_compiler(tmp_path):
     from pin_slam_b200 import _lib
 
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "pinb200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "pinb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(pinb200_map_view),sizeof(pinb200_decoder_view),sizeof(pinb200_query_opts),"
-                   "sizeof(pinb200_query_out),sizeof(pinb200_gn_opts));return 0;}\n")
+                   "sizeof(pinb200_query_out),sizeof(pinb200_gn_opts),sizeof(pinb200_map_train_opts));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).split()
     sizes = [int(x) for x in out]
     assert sizes == [ctypes.sizeof(_lib.MapView), ctypes.sizeof(_lib.DecoderView), ctypes.sizeof(_lib.QueryOpts),
-                     ctypes.sizeof(_lib.QueryOut), ctypes.sizeof(_lib.GnOpts)]
+                     ctypes.sizeof(_lib.QueryOut), ctypes.sizeof(_lib.GnOpts), ctypes.sizeof(_lib.MapTrainOpts)]
 
 
 def test_no_cpu_fallback():
