@@ -271,6 +271,9 @@ typedef struct pinb200_map_train_opts {
   double weight_decay;
   int32_t train_decoder;
   int32_t first_step; /* 1-based Adam step of the first iteration */
+  int32_t stages;     /* bit 0: assemble + forward + loss + backward, bit 1: optimizer; 3 = whole iteration.  Data-parallel
+                         training runs stage 1, all-reduces grad_feat/grad_dec, then runs stage 2 */
+  float grad_scale;   /* 1/world_size when the batch is sharded over GPUs and gradients are summed, else 1 */
   /* workspaces, rows = bs + 6*ceil(bs/decimation) */
   float* rows;       /* [rows,3] */
   float* label;      /* [bs] */

@@ -60,7 +60,8 @@ class MapTrainOpts(C.Structure):
                 ("index", C.c_void_p), ("bs", C.c_int64), ("decimation", C.c_int32), ("eik_eps", C.c_float),
                 ("sigma", C.c_float), ("weight_e", C.c_float), ("loss_weight_on", C.c_int32), ("lr", C.c_double),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
-                ("train_decoder", C.c_int32), ("first_step", C.c_int32), ("rows", c_f32p), ("label", c_f32p),
+                ("train_decoder", C.c_int32), ("first_step", C.c_int32), ("stages", C.c_int32),
+                ("grad_scale", C.c_float), ("rows", c_f32p), ("label", c_f32p),
                 ("ts", c_i32p), ("weight", c_f32p), ("dloss", c_f32p), ("losses", c_f32p), ("feat", c_f32p),
                 ("dec_flat", c_f32p), ("grad_feat", c_f32p), ("grad_dec", c_f32p), ("m_feat", c_f32p),
                 ("v_feat", c_f32p), ("m_dec", c_f32p), ("v_dec", c_f32p)]

@@ -263,19 +263,24 @@ extern "C" int pinb200_map_iterations(const pinb200_map_view* map, const pinb200
   qo.need_grad = 0;
   qo.training_rows = n;
   qo.transform = nullptr;
+  const bool do_fb = (t->stages & 1) != 0, do_opt = (t->stages & 2) != 0;
   for (int it = 0; it < n_iter; ++it) {
-    int rc = pinb200_assemble_batch(t->coord_pool, t->label_pool, t->ts_pool, t->weight_pool, nullptr, 0,
-                                    t->index + (int64_t)it * n, n, t->decimation, t->eik_eps, t->rows, t->label, t->ts,
-                                    t->weight, nullptr, stream);
-    if (rc) return rc;
-    rc = pinb200_query_sdf(map, dec, nullptr, t->rows, t->ts, rows, &qo, out, stream);
-    if (rc) return rc;
-    rc = pinb200_mapping_loss(out->sdf, t->label, t->weight, n, ne, t->sigma, t->loss_weight_on,
-                              ne > 0 ? t->weight_e : 0.f, t->eik_eps, 1.0f, t->dloss, t->losses, stream);
-    if (rc) return rc;
-    rc = pinb200_train_backward(map, dec, t->feat, t->rows, out->knn_idx, out->knn_weight, t->dloss, rows, nn_k,
-                                weighted_first, t->grad_feat, t->grad_dec, stream);
-    if (rc) return rc;
+    int rc = PINB200_OK;
+    if (do_fb) {
+      rc = pinb200_assemble_batch(t->coord_pool, t->label_pool, t->ts_pool, t->weight_pool, nullptr, 0,
+                                  t->index + (int64_t)it * n, n, t->decimation, t->eik_eps, t->rows, t->label, t->ts,
+                                  t->weight, nullptr, stream);
+      if (rc) return rc;
+      rc = pinb200_query_sdf(map, dec, nullptr, t->rows, t->ts, rows, &qo, out, stream);
+      if (rc) return rc;
+      rc = pinb200_mapping_loss(out->sdf, t->label, t->weight, n, ne, t->sigma, t->loss_weight_on,
+                                ne > 0 ? t->weight_e : 0.f, t->eik_eps, t->grad_scale, t->dloss, t->losses, stream);
+      if (rc) return rc;
+      rc = pinb200_train_backward(map, dec, t->feat, t->rows, out->knn_idx, out->knn_weight, t->dloss, rows, nn_k,
+                                  weighted_first, t->grad_feat, t->grad_dec, stream);
+      if (rc) return rc;
+    }
+    if (!do_opt) continue;
     const int step = t->first_step + it;
     if (t->train_decoder) {
       rc = pinb200_adam_step(t->dec_flat, t->grad_dec, t->m_dec, t->v_dec, n_dec, t->lr, t->beta1, t->beta2, t->eps, 0.0,

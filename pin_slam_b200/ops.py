@@ -349,7 +349,7 @@ def assemble_batch(coord_pool, label_pool, ts_pool, weight_pool, color_pool, ind
 def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weighted_first, coord_pool, label_pool,
                    ts_pool, weight_pool, index, decimation, eik_eps, sigma, weight_e, loss_weight_on, lr, beta1, beta2,
                    eps, weight_decay, train_decoder, first_step, feat, dec_flat, grad_feat, grad_dec, m_feat, v_feat,
-                   m_dec, v_dec, losses, work: dict):
+                   m_dec, v_dec, losses, work: dict, stages: int = 3, grad_scale: float = 1.0):
     """The geometry-only training loop of Mapper.mapping in ONE host call (pinb200_map_iterations).
     `index` [n_iter, bs] int64 are the pre-drawn batch indices; scratch buffers live in `work`."""
     lib = _lib.load()
@@ -374,6 +374,7 @@ def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weig
     t.sigma, t.weight_e, t.loss_weight_on = float(sigma), float(weight_e), int(bool(loss_weight_on))
     t.lr, t.beta1, t.beta2, t.eps, t.weight_decay = float(lr), float(beta1), float(beta2), float(eps), float(weight_decay)
     t.train_decoder, t.first_step = int(bool(train_decoder)), int(first_step)
+    t.stages, t.grad_scale = int(stages), float(grad_scale)
     t.rows = _ptr(rows_t)
     t.label, t.ts, t.weight = _ptr(buf("label", (bs,))), _ptr(buf("ts", (bs,), torch.int32)), _ptr(buf("weight", (bs,)))
     t.dloss, t.losses = _ptr(buf("dl", (rows,))), _ptr(losses, torch.float32)
@@ -384,4 +385,4 @@ def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weig
     rc = lib.pinb200_map_iterations(C.byref(mh.view), C.byref(dec.view), int(nn_k), int(bool(weighted_first)),
                                     C.byref(t), C.byref(qo), int(n_iter), _stream())
     _lib.check(rc, "pinb200_map_iterations")
-    _count(n_iter * 6)
+    _count(n_iter * ((4 if stages & 1 else 0) + (2 if stages & 2 else 0)))

@@ -353,18 +353,27 @@ class Mapper:
         out = self._work
         stock_batches = (type(self).get_batch is Mapper.get_batch and "get_batch" not in self.__dict__
                          and not self.ba_done_flag)
-        if stock_batches and not dist_on and not color_on:
-            # the whole loop from ONE host call: the batch indices are drawn up front (same torch.randint calls in
-            # the same order as the reference, nothing else consumes the RNG in between)
+        if stock_batches and not color_on:
+            # the loop from ONE host call (two per iteration when the gradients are all-reduced in between): the
+            # batch indices are drawn up front -- same torch.randint calls in the same order as the reference,
+            # nothing else consumes the RNG in between
             index = torch.stack([self.draw_batch_index() for _ in range(iter_count)])
-            ops.map_iterations(
-                npm.map_handle(True), self.sdf_mlp.handle(), iter_count, nn_k=cfg.query_nn_k,
-                weighted_first=cfg.weighted_first, coord_pool=self.global_coord_pool, label_pool=self.sdf_label_pool,
-                ts_pool=self.time_pool, weight_pool=self.weight_pool, index=index,
-                decimation=dec_step if eik_on else 0, eik_eps=eps_num, sigma=self.sdf_scale, weight_e=cfg.weight_e,
-                loss_weight_on=cfg.loss_weight_on, lr=cfg.lr, beta1=0.9, beta2=0.99, eps=cfg.adam_eps,
-                weight_decay=cfg.weight_decay, train_decoder=train_dec, first_step=1, feat=feat, dec_flat=flat,
-                grad_feat=gfeat, grad_dec=gdec, m_feat=mf, v_feat=vf, m_dec=md, v_dec=vd, losses=losses, work=out)
+            kw = dict(nn_k=cfg.query_nn_k, weighted_first=cfg.weighted_first, coord_pool=self.global_coord_pool,
+                      label_pool=self.sdf_label_pool, ts_pool=self.time_pool, weight_pool=self.weight_pool,
+                      decimation=dec_step if eik_on else 0, eik_eps=eps_num, sigma=self.sdf_scale,
+                      weight_e=cfg.weight_e, loss_weight_on=cfg.loss_weight_on, lr=cfg.lr, beta1=0.9, beta2=0.99,
+                      eps=cfg.adam_eps, weight_decay=cfg.weight_decay, train_decoder=train_dec, feat=feat,
+                      dec_flat=flat, grad_feat=gfeat, grad_dec=gdec, m_feat=mf, v_feat=vf, m_dec=md, v_dec=vd,
+                      losses=losses, work=out)
+            mh, dh = npm.map_handle(True), self.sdf_mlp.handle()
+            if not dist_on:
+                ops.map_iterations(mh, dh, iter_count, index=index, first_step=1, **kw)
+            else:
+                for it in range(iter_count):
+                    ops.map_iterations(mh, dh, 1, index=index[it:it + 1], first_step=it + 1, stages=1,
+                                       grad_scale=1.0 / world, **kw)
+                    allreduce_gradients(red)
+                    ops.map_iterations(mh, dh, 1, index=index[it:it + 1], first_step=it + 1, stages=2, **kw)
             self.total_iter += iter_count
             iter_count = 0
         for it in range(iter_count):

@@ -50,17 +50,16 @@ def _build(device):
 
 
 def _fixed_batches(mapper, cfg, rank, world):
-    """Deterministic batches: iteration i uses pool rows [i*bs, (i+1)*bs); rank r takes every world-th row."""
+    """Deterministic batches: iteration i uses pool rows [i*bs, (i+1)*bs); rank r takes every world-th row.
+    Only the index draw is replaced, so Mapper.mapping stays on its stock (staged, one-call-per-stage) path."""
     state = {"i": 0}
 
-    def get_batch(global_coord=False, bs=None):
+    def draw_batch_index(bs=None):
         i = state["i"]
         state["i"] += 1
-        idx = torch.arange(i * cfg.bs, (i + 1) * cfg.bs, device=mapper.device)[rank::world]
-        return (mapper.global_coord_pool[idx], mapper.sdf_label_pool[idx], mapper.time_pool[idx], None, None, None,
-                mapper.weight_pool[idx])
+        return torch.arange(i * cfg.bs, (i + 1) * cfg.bs, device=mapper.device)[rank::world].contiguous()
 
-    mapper.get_batch = get_batch
+    mapper.draw_batch_index = draw_batch_index
 
 
 def _worker(rank, world, port, q, iters):
