@@ -525,6 +525,42 @@ def query_sdf(
 
 
 # --------------------------------------------------------------------------
+# f3: Mesher.query_points  (utils/mesher.py:40-164) -- dense grid query, global map, no grad
+# --------------------------------------------------------------------------
+def mesher_query_points(
+    m: OracleMap,
+    dec: DecoderParams,
+    coord: torch.Tensor,
+    nn_k: int,
+    weighted_first: bool,
+    color_dec: Optional[DecoderParams] = None,
+    query_locally: bool = False,
+    mask_min_nn_count: int = 4,
+):
+    """(sdf [N], color [N,Cc] or None, mc_mask [N] bool).  Rows without any neighbour keep sdf 0
+    (`batch_sdf[pred_mask] = ...` with pred_mask = nn_count >= 1, mesher.py:118-131); the colour head decodes
+    every row (mesher.py:143-146)."""
+    with torch.no_grad():
+        geo, col, w, nn_count, _ = query_feature(m, coord, None, nn_k, weighted_first, training_mode=False,
+                                                 query_locally=query_locally,
+                                                 query_color_feature=color_dec is not None)
+        pred = nn_count >= 1
+        if weighted_first:
+            sdf = torch.zeros(coord.shape[0], dtype=coord.dtype)
+            sdf[pred] = decoder_sdf(dec, geo[pred])
+        else:
+            s = torch.zeros(coord.shape[0], nn_k, 1, dtype=coord.dtype)
+            s[pred] = decoder_sdf(dec, geo[pred].reshape(-1, geo.shape[-1])).reshape(-1, nn_k, 1)
+            sdf = torch.sum(s * w, dim=1).squeeze(1)
+        color = None
+        if color_dec is not None:
+            color = decoder_color(color_dec, col)
+            if not weighted_first:
+                color = torch.sum(color * w, dim=1)
+        return sdf, color, nn_count >= mask_min_nn_count
+
+
+# --------------------------------------------------------------------------
 # a9/a10: registration step  (utils/tracker.py:367-611, 615-695)
 # --------------------------------------------------------------------------
 def skew(v):

@@ -18,6 +18,7 @@ outputs of the reference functions on the hot path:
   Tracker.query_source_points               utils/tracker.py:227
   Tracker.registration_step / implicit_reg  utils/tracker.py:367,615
   Mapper.mapping                            utils/mapper.py:600
+  Mesher.query_points (dense grid query)    utils/mesher.py:40
 
 Optional reference imports (open3d, gtsam, ...) that are absent here and unused
 by the hot path are stubbed in sys.modules before import.
@@ -358,9 +359,54 @@ def gen_train_fixture(kind, seed, weighted_first, iters=3, bs=2048, color=False,
     print("wrote", name, "iters", len(batches))
 
 
+def gen_mesh_fixture(kind, seed, weighted_first, color=False, name=None):
+    """Mesher.query_points on a regular grid through the global map (utils/mesher.py:40-164)."""
+    from utils.mesher import Mesher
+
+    cfg = make_config(kind)
+    cfg.weighted_first = weighted_first
+    cfg.buffer_size = 40009
+    if color:
+        cfg.color_on = True
+        cfg.color_channel = 3
+    npm, pos = build_reference_map(cfg, seed)
+    torch.manual_seed(seed + 1)
+    sdf_mlp = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    color_mlp = Decoder(cfg, cfg.color_mlp_hidden_dim, cfg.color_mlp_level, cfg.color_channel) if color else None
+    mesher = Mesher(cfg, npm, {"sdf": sdf_mlp, "semantic": None, "color": color_mlp})
+    out = {}
+    out.update(map_state(npm))
+    out.update(dec_state(sdf_mlp, "sdf_mlp"))
+    if color:
+        out.update(dec_state(color_mlp, "color_mlp"))
+    out["cfg.query_nn_k"] = np.int64(cfg.query_nn_k)
+    out["cfg.weighted_first"] = np.bool_(cfg.weighted_first)
+    out["cfg.feature_dim"] = np.int64(cfg.feature_dim)
+    # regular grid around the sensor (spacing 0.35 m: several grid nodes per voxel, many nodes in free space
+    # with fewer than 4 or zero neighbours)
+    ax = torch.arange(-14, 15, dtype=torch.float32) * 0.35
+    az = torch.arange(-4, 5, dtype=torch.float32) * 0.35
+    grid = torch.stack(torch.meshgrid(ax, ax, az, indexing="ij"), -1).reshape(-1, 3) + pos.reshape(1, 3).float()
+    out["grid"] = grid.numpy()
+    sdf, _, col, mask = mesher.query_points(grid.clone(), 1000, query_sdf=True, query_sem=False, query_color=color,
+                                            query_mask=True, query_locally=False, mask_min_nn_count=4)
+    out["mesh.sdf"] = np.asarray(sdf, np.float32)
+    out["mesh.mask"] = np.asarray(mask).astype(np.bool_)
+    if color:
+        out["mesh.color"] = np.asarray(col, np.float32)
+    name = name or f"mesh_{kind}_{'wf' if weighted_first else 'nwf'}{'_color' if color else ''}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "grid", grid.shape[0], "masked-in", int(np.asarray(mask).sum()),
+          "no-neighbour rows", int((np.asarray(sdf) == 0).sum()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "mesh":  # the dense-grid query fixtures only
+        gen_mesh_fixture("kitti", 21, weighted_first=False)
+        gen_mesh_fixture("replica", 22, weighted_first=True, color=True)
+        sys.exit(0)
     if only == "replica_query":  # regenerate a single fixture (the reference's map growth is not bit-reproducible
         gen_query_fixture("replica", 5, weighted_first=True, color=True)  # run to run: duplicate-slot index_put)
         sys.exit(0)
@@ -372,6 +418,8 @@ if __name__ == "__main__":
     gen_train_fixture("kitti", 11, weighted_first=False)
     gen_train_fixture("cfg2", 12, weighted_first=True)
     gen_train_fixture("replica", 13, weighted_first=True, color=True)
+    gen_mesh_fixture("kitti", 21, weighted_first=False)
+    gen_mesh_fixture("replica", 22, weighted_first=True, color=True)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
                 f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

@@ -178,3 +178,19 @@ def test_registration_step_with_colour(mode):
     if mode == "photo":
         close(out["color_residual_mean"], float(fx["reg_color.photo.color_residual"]), 1e-6, 0)
     close(out["T"], fx[f"reg_color.{mode}.T"], 2e-4, 2e-5)
+
+
+@pytest.mark.parametrize("name", ["mesh_kitti_nwf", "mesh_replica_wf_color"])
+def test_mesher_grid_query(name):
+    """Oracle restatement of Mesher.query_points (utils/mesher.py:40-164) against the reference's output."""
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    cdec = decoder_from_fixture(fx, "color_mlp") if "mesh.color" in fx else None
+    sdf, col, mask = po.mesher_query_points(m, dec, t(fx["grid"]), int(fx["cfg.query_nn_k"]),
+                                            bool(fx["cfg.weighted_first"]), color_dec=cdec)
+    assert np.array_equal(mask.numpy(), fx["mesh.mask"])
+    assert np.array_equal(sdf.numpy() == 0, fx["mesh.sdf"] == 0)
+    np.testing.assert_allclose(sdf.numpy(), fx["mesh.sdf"], rtol=1e-5, atol=1e-6 * dec.sdf_scale)
+    if cdec is not None:
+        np.testing.assert_allclose(col.numpy(), fx["mesh.color"], rtol=1e-5, atol=1e-6)
