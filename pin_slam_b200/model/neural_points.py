@@ -360,6 +360,43 @@ class NeuralPoints(nn.Module):
                              color_grad=color_grad, transform=transform, save_knn=save_knn, want_xyz=want_xyz,
                              out=out)
 
+    def query_sdf_host(self, query_host: torch.Tensor, sdf_decoder, host_out: dict, *, chunks: int = 4,
+                       query_locally: bool = True, need_grad: bool = True):
+        """Host-facing fused query: `query_host` [N,3] fp32 in (pinned) host memory in, results written into the
+        (pinned) host tensors of `host_out` (any of sdf [N], grad [N,3], sdf_std [N], nn_count [N] i32,
+        certainty [N]).  The batch is cut into `chunks` pieces that alternate between two CUDA streams, so the
+        host->device copy of piece i+1 and the device->host copies of piece i-1 overlap the kernel of piece i.
+        Stream-ordered with respect to the caller's current stream (results are complete when that stream is)."""
+        n = query_host.shape[0]
+        pipe = self.__dict__.get("_host_pipe")
+        if pipe is None:
+            pipe = self.__dict__["_host_pipe"] = {"streams": [torch.cuda.Stream(self.device) for _ in range(2)],
+                                                  "work": [{}, {}], "q": [None, None]}
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(cur)
+        step = max(32, -(-n // max(1, chunks)))
+        for i, head in enumerate(range(0, n, step)):
+            tail = min(head + step, n)
+            s = pipe["streams"][i % 2]
+            if i < 2:
+                s.wait_event(start)
+            with torch.cuda.stream(s):
+                qd = pipe["q"][i % 2]
+                if qd is None or qd.shape[0] < tail - head:
+                    qd = pipe["q"][i % 2] = torch.empty((step, 3), dtype=torch.float32, device=self.device)
+                qv = qd[: tail - head]
+                qv.copy_(query_host[head:tail], non_blocking=True)
+                o = self.query_sdf(qv, sdf_decoder, query_locally=query_locally, need_grad=need_grad,
+                                   out=pipe["work"][i % 2])
+                for name, h in host_out.items():
+                    h[head:tail].copy_(o[name], non_blocking=True)
+        for s in pipe["streams"]:
+            done = torch.cuda.Event()
+            done.record(s)
+            cur.wait_event(done)
+        return host_out
+
     # ---------------------------------------------------------------- reference-compatible queries
     def radius_neighborhood_search(self, points: torch.Tensor, time_filtering: bool = False):
         """dist2 [N,C], global ids [N,C] (int64 like the reference)."""
@@ -522,6 +559,7 @@ class NeuralPoints(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_handles"] = {}  # raw device pointers never travel
+        state.pop("_host_pipe", None)  # CUDA streams / staging buffers of query_sdf_host
         return state
 
 

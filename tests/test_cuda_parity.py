@@ -657,6 +657,31 @@ def test_dropin_query_feature_matches_fused_path():
         np.testing.assert_allclose(o["certainty"].cpu().numpy(), cert.cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_host_facing_pipelined_query_equals_device_query():
+    """NeuralPoints.query_sdf_host (pinned host in/out, pieces pipelined over two streams) returns exactly what
+    the device-resident call returns, for ragged piece sizes too."""
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import Decoder
+    from pin_slam_b200.synthetic import build_map, surface_queries
+
+    cfg = HotPathConfig.cfg2(device="cuda")
+    npm = build_map(cfg, n_surface=200000, seed=0, extent=40.0)
+    torch.manual_seed(0)
+    dec = Decoder(cfg, 64, 2, 1)
+    for n, chunks in ((50001, 4), (4096, 3), (17, 4)):
+        q = surface_queries(npm, n, seed=n, sigma=0.1)
+        ref = {k: v.clone() for k, v in npm.query_sdf(q, dec, need_grad=True).items()}
+        q_host = q.cpu().pin_memory()
+        host = {"sdf": torch.empty(n).pin_memory(), "grad": torch.empty(n, 3).pin_memory(),
+                "sdf_std": torch.empty(n).pin_memory(), "nn_count": torch.empty(n, dtype=torch.int32).pin_memory(),
+                "certainty": torch.empty(n).pin_memory()}
+        for rep in range(2):  # second call reuses the staging buffers
+            npm.query_sdf_host(q_host, dec, host, chunks=chunks)
+            torch.cuda.current_stream().synchronize()
+            for k, h in host.items():
+                assert torch.equal(h, ref[k].cpu()), (n, chunks, k)
+
+
 def test_dropin_pickles_and_installs_under_reference_module_names(tmp_path):
     """utils/tools.py:295-317 pickles the whole NeuralPoints module after clear_temp(); pin_slam.py:157-165 reloads
     it, reassigns .config and calls recreate_hash.  install() must make `model.neural_points` resolve to the drop-in."""
