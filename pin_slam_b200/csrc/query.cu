@@ -54,7 +54,14 @@ struct QueryParams {
 // issues all of their row loads before consuming any (GQ * K independent 128-byte
 // loads in flight per warp).
 // ---------------------------------------------------------------------------
-constexpr int GQ = 4;   // queries gathered concurrently by one warp
+#ifndef PINB_K1_GQ
+#define PINB_K1_GQ 8
+#endif
+constexpr int GQ_MAX = 8;  // queries gathered concurrently by one warp (4 for the widest rows: register budget)
+template <int FT>
+struct GqOf {
+  static constexpr int value = FT >= 64 ? 4 : PINB_K1_GQ;
+};
 constexpr int WT = 32;  // queries (= threads) per warp tile
 constexpr int WPB = 12; // max warps per CTA (one CTA per SM); fewer if shared memory does not fit
 
@@ -66,8 +73,8 @@ struct FeatMap {
   static constexpr int R = FT >= 32 ? KREG * NJ : (KREG + PER - 1) / PER;  // warp loads per query (K = KREG)
 };
 
-// weighted_first: act[j][ql] = sum_k w_k f_k[j]  for the queries ql0 + 4*g (g < GQ)
-template <int FT, int LDX>
+// weighted_first: act[j][ql] = sum_k w_k f_k[j]  for the queries ql0 + g (g < GQ)
+template <int FT, int LDX, int GQ>
 __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ feat, int K, const int* s_idx,
                                                       const float* s_w, int lane, float* s_act, int ql0, int qpt) {
   using M = FeatMap<FT>;
@@ -112,7 +119,7 @@ __device__ __forceinline__ void gather_weighted_group(const float* __restrict__ 
 }
 
 // decode-every-neighbour: act[j][ql*K + k] = f_k[j] (0 if invalid)
-template <int FT, int LDX>
+template <int FT, int LDX, int GQ>
 __device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
                                                   float* s_act, int ql0, int qpt, int sq0) {
   using M = FeatMap<FT>;
@@ -145,7 +152,7 @@ __device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat
 }
 
 // a_k = <g_xbar[0..F), f_k> for the queries ql0 + 4*g  ->  s_a[ql*K + k]
-template <int FT, int LDX>
+template <int FT, int LDX, int GQ>
 __device__ __forceinline__ void feature_dots_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
                                                    const float* s_act, float* s_a, int ql0, int qpt) {
   using M = FeatMap<FT>;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
   constexpr int KP0 = (FT + 3 + 7) / 8 * 8;        // decoder input width padded to the MMA k-step
   constexpr int KT0 = KP0 / 8;                     // k-steps of layer 0 == n-tiles of the input gradient
   constexpr int LDX = (KP0 > H ? KP0 : H) + 4;     // row-major tile leading dimension (== 4 or 12 mod 32)
+  constexpr int GQ = GqOf<FT>::value;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const pinb200_map_view& m = p.map;
@@ -376,9 +384,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
 
       // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
       if (wf) {
-        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_weighted_group<FT, LDX>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
+        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_weighted_group<FT, LDX, GQ>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
       } else {
-        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_rows_group<FT, LDX>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
+        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_rows_group<FT, LDX, GQ>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
         // neighbour vectors of the (query, k) rows: thread per row
         if (tid < used_rows) {
           const int ql = tid / K, k = tid - ql * K, sq = sq0 + ql;
@@ -489,7 +497,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
         if (wf) {
           // ---- C1: a_k = <g_xbar, f_k> (warp per query, coalesced re-read of the K feature rows)
           if (need_grad) {
-            for (int ql0 = 0; ql0 < qpt; ql0 += GQ) feature_dots_group<FT, LDX>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
+            for (int ql0 = 0; ql0 < qpt; ql0 += GQ) feature_dots_group<FT, LDX, GQ>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
             __syncwarp();
           }
           // ---- C2: thread per query -- chain rule through the IDW weights, outputs
@@ -845,7 +853,7 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     const long long per_warp = (p.n + slots - 1) / slots;
     int wq;
     if (p.opts.weighted_first) {
-      wq = (int)std::min<long long>(WT, std::max<long long>(GQ, (per_warp + GQ - 1) / GQ * GQ));
+      wq = (int)std::min<long long>(WT, std::max<long long>(GQ_MAX, (per_warp + GQ_MAX - 1) / GQ_MAX * GQ_MAX));
     } else {
       const int qpt_rows = WT / p.opts.nn_k;
       wq = (int)std::min<long long>(WT, (per_warp + qpt_rows - 1) / qpt_rows * qpt_rows);
