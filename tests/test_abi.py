@@ -82,3 +82,19 @@ def test_no_cpu_fallback():
 
     with pytest.raises(RuntimeError):
         ops._ptr(torch.zeros(3))
+
+
+def test_install_registers_reference_module_names():
+    """install() makes the reference's import statements resolve to the drop-in classes."""
+    import importlib
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r); import pin_slam_b200.install as i; i.install(tracker_and_mapper=True); "
+            "import importlib as il; "
+            "from model.neural_points import NeuralPoints; from model.decoder import Decoder; "
+            "T = il.import_module('utils.tracker').Tracker; M = il.import_module('utils.mapper').Mapper; "
+            "print(NeuralPoints.__module__, Decoder.__module__, T.__module__, M.__module__)") % ROOT
+    out = subprocess.check_output([sys.executable, "-c", code]).decode().split()
+    assert out == ["pin_slam_b200.model.neural_points", "pin_slam_b200.model.decoder", "pin_slam_b200.utils.tracker",
+                   "pin_slam_b200.utils.mapper"]
