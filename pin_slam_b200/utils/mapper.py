@@ -18,7 +18,6 @@ own sub-batch of its pool shard and the gradients are summed with ONE all-reduce
 (certainty increments / timestamps are reduced once per mapping() call); map, decoder and Adam
 state stay replicated and bit-identical across ranks.
 """
-import math
 
 import torch
 

@@ -1,6 +1,6 @@
-import sys, os
+import sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
-import torch, numpy as np
+import torch
 from helpers import *
 from oracle import pin_oracle as po
 from pin_slam_b200 import ops

@@ -86,7 +86,6 @@ def test_no_cpu_fallback():
 
 def test_install_registers_reference_module_names():
     """install() makes the reference's import statements resolve to the drop-in classes."""
-    import importlib
     import subprocess
     import sys
 
