@@ -194,3 +194,53 @@ def test_mesher_grid_query(name):
     np.testing.assert_allclose(sdf.numpy(), fx["mesh.sdf"], rtol=1e-5, atol=1e-6 * dec.sdf_scale)
     if cdec is not None:
         np.testing.assert_allclose(col.numpy(), fx["mesh.color"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+def test_dropin_reset_local_map_and_write_back(name):
+    """The drop-in NeuralPoints.reset_local_map (index-list gathers, one host sync) reproduces the reference's local
+    map bit for bit -- local_mask, global2local incl. the +1 fill quirk, every local array -- and
+    assign_local_to_global writes the trained rows back where the reference does (model/neural_points.py:424-527).
+    Pure torch host logic: runs on the CPU."""
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import NeuralPoints
+
+    fx = load_npz(name)
+    g = lambda k: fx["map." + k]  # noqa: E731
+    color = "map.color_features" in fx
+    cfg = HotPathConfig.kitti(device="cpu", feature_dim=int(g("geo_features").shape[1]), buffer_size=int(g("buffer_size")),
+                              voxel_size_m=float(g("resolution")), local_map_radius=float(fx["cfg.local_map_radius"]),
+                              color_on=color)
+    npm = NeuralPoints(cfg)
+    npm.neural_points = t(g("neural_points"))
+    npm.point_orientations = t(g("point_orientations"))
+    npm.geo_features = t(g("geo_features")).clone()
+    if color:
+        npm.color_features = t(g("color_features")).clone()
+    npm.point_ts_create = t(g("point_ts_create"))
+    npm.point_ts_update = t(g("point_ts_update")).clone()
+    npm.point_certainties = t(g("point_certainties")).clone()
+    npm.travel_dist = t(g("travel_dist"))
+    npm.diff_travel_dist_local = float(g("diff_travel_dist_local"))
+    npm.temporal_local_map_on = bool(g("temporal_local_map_on"))
+    npm.after_pgo = bool(g("after_pgo"))
+    npm.reset_local_map(t(fx["sensor_pos"]), torch.eye(3), int(g("cur_ts")))
+    assert np.array_equal(npm.local_mask.numpy(), g("local_mask"))
+    assert np.array_equal(npm.global2local.numpy().astype(np.int64), g("global2local").astype(np.int64))
+    for mine, ref in ((npm.local_neural_points, "local_neural_points"),
+                      (npm.local_point_orientations, "local_point_orientations"),
+                      (npm.local_geo_features.data, "local_geo_features"),
+                      (npm.local_point_certainties, "local_point_certainties"),
+                      (npm.local_point_ts_update, "local_point_ts_update")):
+        assert np.array_equal(mine.numpy(), g(ref)), ref
+    if color:
+        assert np.array_equal(npm.local_color_features.data.numpy(), g("local_color_features"))
+    # write-back: what the reference does with boolean-mask assignment (neural_points.py:515-527)
+    ref_geo, ref_cert = t(g("geo_features")).clone(), t(g("point_certainties")).clone()
+    npm.local_geo_features.data += 1.0
+    npm.local_point_certainties += 0.5
+    mask = t(g("local_mask"))
+    ref_geo[mask] = npm.local_geo_features.data
+    ref_cert[mask[:-1]] = npm.local_point_certainties
+    npm.assign_local_to_global()
+    assert torch.equal(npm.geo_features, ref_geo) and torch.equal(npm.point_certainties, ref_cert)
