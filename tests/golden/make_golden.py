@@ -19,6 +19,7 @@ outputs of the reference functions on the hot path:
   Tracker.registration_step / implicit_reg  utils/tracker.py:367,615
   Mapper.mapping                            utils/mapper.py:600
   Mesher.query_points (dense grid query)    utils/mesher.py:40
+  DataSampler.sample (per-ray samples)      utils/data_sampler.py:18
 
 Optional reference imports (open3d, gtsam, ...) that are absent here and unused
 by the hot path are stubbed in sys.modules before import.
@@ -400,9 +401,44 @@ def gen_mesh_fixture(kind, seed, weighted_first, color=False, name=None):
           "no-neighbour rows", int((np.asarray(sdf) == 0).sum()))
 
 
+def gen_sampler_fixture(kind, seed, color=False, n=257, name=None):
+    """DataSampler.sample on seeded sensor-frame points (utils/data_sampler.py:18-260): torch.manual_seed(seed)
+    immediately before the call pins the randn/rand stream."""
+    from utils.data_sampler import DataSampler
+
+    cfg = make_config(kind)
+    g = torch.Generator().manual_seed(seed)
+    direction = torch.randn(n, 3, generator=g)
+    direction = direction / direction.norm(dim=1, keepdim=True)
+    points = direction * (torch.rand(n, 1, generator=g) * 40.0 + 2.0)
+    normals = torch.randn(n, 3, generator=g)
+    colors = torch.rand(n, 3, generator=g) if color else None
+    sampler = DataSampler(cfg)
+    torch.manual_seed(seed)
+    coord, label, normal, _, col, weight = sampler.sample(points.clone(), normals.clone(), None,
+                                                          None if colors is None else colors.clone())
+    out = {"points": points.numpy(), "normals": normals.numpy(), "seed": np.int64(seed),
+           "cfg.ints": np.array([cfg.surface_sample_n, cfg.free_front_n, cfg.free_behind_n], np.int64),
+           "cfg.floats": np.array([cfg.surface_sample_range_m, cfg.free_sample_begin_ratio, cfg.free_sample_end_dist_m,
+                                   cfg.dist_weight_scale, cfg.max_range], np.float64),
+           "cfg.flags": np.array([cfg.dist_weight_on, cfg.behind_dropoff_on], np.bool_),
+           "out.coord": coord.numpy(), "out.label": label.numpy(), "out.normal": normal.numpy(),
+           "out.weight": weight.numpy()}
+    if color:
+        out["colors"] = colors.numpy()
+        out["out.color"] = col.numpy()
+    name = name or f"sampler_{kind}{'_color' if color else ''}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, coord.shape)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "sampler":
+        gen_sampler_fixture("kitti", 31)
+        gen_sampler_fixture("replica", 32, color=True)
+        sys.exit(0)
     if only == "mesh":  # the dense-grid query fixtures only
         gen_mesh_fixture("kitti", 21, weighted_first=False)
         gen_mesh_fixture("replica", 22, weighted_first=True, color=True)
@@ -420,6 +456,8 @@ if __name__ == "__main__":
     gen_train_fixture("replica", 13, weighted_first=True, color=True)
     gen_mesh_fixture("kitti", 21, weighted_first=False)
     gen_mesh_fixture("replica", 22, weighted_first=True, color=True)
+    gen_sampler_fixture("kitti", 31)
+    gen_sampler_fixture("replica", 32, color=True)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
                 f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

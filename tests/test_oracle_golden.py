@@ -244,3 +244,29 @@ def test_dropin_reset_local_map_and_write_back(name):
     ref_cert[mask[:-1]] = npm.local_point_certainties
     npm.assign_local_to_global()
     assert torch.equal(npm.geo_features, ref_geo) and torch.equal(npm.point_certainties, ref_cert)
+
+
+@pytest.mark.parametrize("name", ["sampler_kitti", "sampler_replica_color"])
+def test_dropin_data_sampler_matches_reference(name):
+    """SURVEY.md section 8 row f2 (host side): the drop-in DataSampler.sample consumes the RNG stream exactly like the
+    reference (utils/data_sampler.py:18-260) and returns the same samples, labels and weights."""
+    import types
+
+    from pin_slam_b200.utils.mapper import DataSampler
+
+    fx = load_npz(name)
+    ns, nf, nb = (int(v) for v in fx["cfg.ints"])
+    sr, begin, end, dscale, max_range = (float(v) for v in fx["cfg.floats"])
+    cfg = types.SimpleNamespace(device="cpu", surface_sample_n=ns, free_front_n=nf, free_behind_n=nb,
+                                surface_sample_range_m=sr, free_sample_begin_ratio=begin, free_sample_end_dist_m=end,
+                                dist_weight_scale=dscale, max_range=max_range, dist_weight_on=bool(fx["cfg.flags"][0]),
+                                behind_dropoff_on=bool(fx["cfg.flags"][1]))
+    colors = t(fx["colors"]) if "colors" in fx else None
+    torch.manual_seed(int(fx["seed"]))
+    coord, label, normal, _, col, weight = DataSampler(cfg).sample(t(fx["points"]), t(fx["normals"]), None, colors)
+    np.testing.assert_allclose(coord.numpy(), fx["out.coord"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(label.numpy(), fx["out.label"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(weight.numpy(), fx["out.weight"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(normal.numpy(), fx["out.normal"])
+    if colors is not None:
+        assert np.array_equal(col.numpy(), fx["out.color"])
