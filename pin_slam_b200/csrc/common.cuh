@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "../../include/pinb200.h"
+#include "knn_select.cuh"
 
 namespace pinb {
 
@@ -193,83 +194,24 @@ __device__ __forceinline__ float idw_weight(float d2, bool valid, int nn_count, 
 // loads per dependency level (table -> point/ts/g2l -> travel distance) so that one
 // thread keeps ~8 loads in flight and a 128-thread CTA ~1000.
 // ---------------------------------------------------------------------------
-constexpr int KREG = 8;
 constexpr int PROBE_BATCH = 11;  // 33 probes (the default neighbourhood) = 3 batches
 
-struct KnnRegs {
-  float d2[KREG];
-  int idx[KREG];
-  int gidx[KREG];
-};
-
-__device__ __forceinline__ void knn_regs_init(KnnRegs& L) {
-#pragma unroll
-  for (int i = 0; i < KREG; ++i) {
-    L.d2[i] = INVALID_D2;
-    L.idx[i] = -1;
-    L.gidx[i] = -1;
-  }
-}
-
-// Candidate selection keeps the KREG smallest distances UNSORTED (replace the current worst, then find the new
-// worst: ~30 predicated instructions per accepted candidate instead of a sorted insertion) and sorts once at the
-// end with a 19-comparator network.  Ties: a candidate equal to the current worst is rejected (earlier probe
-// wins, like the reference's stable behaviour on duplicates); the final order among exactly equal distances is
-// unspecified, as it is for torch.sort.
-struct KnnSel {
-  float worst;
-  int wpos;
-};
-
-__device__ __forceinline__ void knn_sel_replace(KnnRegs& L, KnnSel& S, float d2, int li, int gi) {
-#pragma unroll
-  for (int i = 0; i < KREG; ++i)
-    if (i == S.wpos) {
-      L.d2[i] = d2;
-      L.idx[i] = li;
-      L.gidx[i] = gi;
-    }
-  S.worst = L.d2[0];
-  S.wpos = 0;
-#pragma unroll
-  for (int i = 1; i < KREG; ++i)
-    if (L.d2[i] > S.worst) {  // first maximum: with several empty (9e3) slots the lowest index is refilled first
-      S.worst = L.d2[i];
-      S.wpos = i;
-    }
-}
-
-__device__ __forceinline__ void knn_cswap(KnnRegs& L, int a, int b) {
-  if (L.d2[b] < L.d2[a]) {
-    const float td = L.d2[a];
-    L.d2[a] = L.d2[b];
-    L.d2[b] = td;
-    const int ti = L.idx[a];
-    L.idx[a] = L.idx[b];
-    L.idx[b] = ti;
-    const int tg = L.gidx[a];
-    L.gidx[a] = L.gidx[b];
-    L.gidx[b] = tg;
-  }
-}
-
-// optimal 19-comparator sorting network for 8 keys (ascending)
-__device__ __forceinline__ void knn_sort8(KnnRegs& L) {
-  knn_cswap(L, 0, 1); knn_cswap(L, 2, 3); knn_cswap(L, 4, 5); knn_cswap(L, 6, 7);
-  knn_cswap(L, 0, 2); knn_cswap(L, 1, 3); knn_cswap(L, 4, 6); knn_cswap(L, 5, 7);
-  knn_cswap(L, 1, 2); knn_cswap(L, 5, 6); knn_cswap(L, 0, 4); knn_cswap(L, 3, 7);
-  knn_cswap(L, 1, 5); knn_cswap(L, 2, 6);
-  knn_cswap(L, 1, 4); knn_cswap(L, 3, 6);
-  knn_cswap(L, 2, 4); knn_cswap(L, 3, 5);
-  knn_cswap(L, 3, 4);
-}
-
+// `scratch` (PINB_K1_SMEM_SELECT builds only): 2 x KREG x 32 ints of per-warp shared memory, see knn_select.cuh
 __device__ __forceinline__ int knn_search_thread(const pinb200_map_view& m, const uint32_t* s_delta, float qx, float qy,
-                                                 float qz, KnnRegs& L) {
+                                                 float qz, KnnRegs& L, int* scratch = nullptr) {
+#ifdef PINB_K1_SMEM_SELECT
+  const int sel_lane = threadIdx.x & 31;
+  int* sc_l = scratch;
+  int* sc_g = scratch + KREG * 32;
+  KnnKeys S;
+  knn_keys_init(S, sc_l, sc_g, sel_lane);
+#else
+  (void)scratch;
   knn_regs_init(L);
   KnnSel S;
   S.worst = INVALID_D2;
   S.wpos = 0;
+#endif
   int count = 0;
   const uint32_t r0 = base_slot(m, qx, qy, qz);
   const bool tf = m.time_filter != 0;
@@ -334,11 +276,19 @@ __device__ __forceinline__ int knn_search_thread(const pinb200_map_view& m, cons
       const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
       if (young && !(dd > m.max_valid_dist2) && li[j] >= 0) {
         ++count;
+#ifdef PINB_K1_SMEM_SELECT
+        if (dd < S.worst) knn_keys_accept(S, dd, li[j], gi[j], sc_l, sc_g, sel_lane);
+#else
         if (dd < S.worst) knn_sel_replace(L, S, dd, li[j], gi[j]);
+#endif
       }
     }
   }
+#ifdef PINB_K1_SMEM_SELECT
+  knn_keys_finish(S, sc_l, sc_g, sel_lane, L);
+#else
   knn_sort8(L);
+#endif
   return count;
 }
 

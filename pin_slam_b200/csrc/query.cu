@@ -283,9 +283,12 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
             }
           cnt = __ldg(p.out.nn_count + qi);
         } else {
-          cnt = knn_search_thread(m, s_delta, qx, qy, qz, Lk);
+          cnt = knn_search_thread(m, s_delta, qx, qy, qz, Lk, reinterpret_cast<int*>(s_act));
         }
       }
+#ifdef PINB_K1_SMEM_SELECT
+      __syncwarp();  // the selection scratch lives in the (idle) activation tile: every lane is done reading it
+#endif
       // normalised inverse-distance weights, summed in neighbour order (model/neural_points.py:665-683)
       float u[KREG], w[KREG], usum = 0.f;
 #pragma unroll
