@@ -20,6 +20,7 @@ outputs of the reference functions on the hot path:
   Mapper.mapping                            utils/mapper.py:600
   Mesher.query_points (dense grid query)    utils/mesher.py:40
   DataSampler.sample (per-ray samples)      utils/data_sampler.py:18
+  NeuralPoints.adjust_map / recreate_hash   model/neural_points.py:791,820 (loop-closure map adjustment)
 
 Optional reference imports (open3d, gtsam, ...) that are absent here and unused
 by the hot path are stubbed in sys.modules before import.
@@ -432,9 +433,60 @@ def gen_sampler_fixture(kind, seed, color=False, n=257, name=None):
     print("wrote", name, coord.shape)
 
 
+def gen_loop_fixture(kind, seed, name=None):
+    """Loop-closure map adjustment: adjust_map with per-frame pose corrections, then
+    recreate_hash (kept_points=True and the duplicate-filtering kept_points=False)."""
+    import copy
+
+    cfg = make_config(kind)
+    cfg.buffer_size = 40009
+    npm, pos = build_reference_map(cfg, seed)
+    out = {}
+    out.update(map_state(npm))
+    out["sensor_pos"] = pos.numpy()
+    out["cfg.local_map_radius"] = np.float64(cfg.local_map_radius)
+    out["cfg.use_mid_ts"] = np.bool_(cfg.use_mid_ts)
+    g = torch.Generator().manual_seed(seed + 3)
+    n_frames = int(npm.travel_dist.shape[0])
+    ang = torch.randn(n_frames, 3, generator=g) * 0.05
+    th = ang.norm(dim=1, keepdim=True).clamp(min=1e-9)
+    ax = ang / th
+    K = torch.zeros(n_frames, 3, 3)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -ax[:, 2], ax[:, 1], ax[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 0], -ax[:, 1], ax[:, 0]
+    R = torch.eye(3).unsqueeze(0) + torch.sin(th).unsqueeze(-1) * K + (1 - torch.cos(th)).unsqueeze(-1) * (K @ K)
+    pose_diff = torch.eye(4).repeat(n_frames, 1, 1)
+    pose_diff[:, :3, :3] = R
+    pose_diff[:, :3, 3] = torch.randn(n_frames, 3, generator=g) * 0.3
+    out["pose_diff"] = pose_diff.numpy()
+    npm.adjust_map(pose_diff)
+    out["adjusted.neural_points"] = npm.neural_points.numpy().copy()
+    out["adjusted.point_orientations"] = npm.point_orientations.numpy().copy()
+    kept = copy.deepcopy(npm)
+    kept.recreate_hash(pos, torch.eye(3), kept_points=True, with_ts=True, cur_ts=int(npm.cur_ts))
+    occ = torch.nonzero(kept.buffer_pt_index >= 0).flatten()
+    out["rehash_kept.table_slots"] = occ.numpy()
+    out["rehash_kept.table_vals"] = kept.buffer_pt_index[occ].numpy()
+    out["rehash_kept.local_mask"] = kept.local_mask.numpy().copy()
+    filt = copy.deepcopy(npm)
+    filt.recreate_hash(pos, torch.eye(3), kept_points=False, with_ts=True, cur_ts=int(npm.cur_ts))
+    occ = torch.nonzero(filt.buffer_pt_index >= 0).flatten()
+    out["rehash_filter.table_slots"] = occ.numpy()
+    out["rehash_filter.table_vals"] = filt.buffer_pt_index[occ].numpy()
+    out["rehash_filter.neural_points"] = filt.neural_points.numpy().copy()
+    out["rehash_filter.geo_features"] = filt.geo_features.numpy().copy()
+    out["rehash_filter.point_ts_create"] = filt.point_ts_create.numpy().copy()
+    name = name or f"loop_{kind}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "points", npm.count(), "after duplicate filter", filt.count())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "loop":
+        gen_loop_fixture("kitti", 41)
+        sys.exit(0)
     if only == "sampler":
         gen_sampler_fixture("kitti", 31)
         gen_sampler_fixture("replica", 32, color=True)
@@ -458,6 +510,7 @@ if __name__ == "__main__":
     gen_mesh_fixture("replica", 22, weighted_first=True, color=True)
     gen_sampler_fixture("kitti", 31)
     gen_sampler_fixture("replica", 32, color=True)
+    gen_loop_fixture("kitti", 41)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
                 f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

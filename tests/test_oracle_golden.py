@@ -270,3 +270,70 @@ def test_dropin_data_sampler_matches_reference(name):
     assert np.array_equal(normal.numpy(), fx["out.normal"])
     if colors is not None:
         assert np.array_equal(col.numpy(), fx["out.color"])
+
+
+def _dropin_from_fixture(fx, color=False):
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import NeuralPoints
+
+    g = lambda k: fx["map." + k]  # noqa: E731
+    cfg = HotPathConfig.kitti(device="cpu", feature_dim=int(g("geo_features").shape[1]), buffer_size=int(g("buffer_size")),
+                              voxel_size_m=float(g("resolution")), local_map_radius=float(fx["cfg.local_map_radius"]),
+                              color_on=color)
+    npm = NeuralPoints(cfg)
+    npm.neural_points = t(g("neural_points")).clone()
+    npm.point_orientations = t(g("point_orientations")).clone()
+    npm.geo_features = t(g("geo_features")).clone()
+    npm.point_ts_create = t(g("point_ts_create")).clone()
+    npm.point_ts_update = t(g("point_ts_update")).clone()
+    npm.point_certainties = t(g("point_certainties")).clone()
+    npm.travel_dist = t(g("travel_dist"))
+    npm.diff_travel_dist_local = float(g("diff_travel_dist_local"))
+    npm.temporal_local_map_on = bool(g("temporal_local_map_on"))
+    npm.cur_ts = int(g("cur_ts"))
+    table = torch.full((int(g("buffer_size")),), -1, dtype=torch.int32)
+    table[t(g("table_slots"))] = t(g("table_vals")).to(torch.int32)
+    npm.buffer_pt_index = table
+    return npm
+
+
+def _assert_same_hash_table(npm, ref_slots, ref_vals):
+    """Same occupied slots; same owner wherever a slot has a single candidate.  Where two voxels collide in the
+    (deliberately small) table the winner of the duplicate-index write is unspecified in torch -- for the reference
+    as well -- so there the owner only has to be one of the colliding points."""
+    table = torch.full((npm.buffer_size,), -1, dtype=torch.int64)
+    table[t(ref_slots)] = t(ref_vals).long()
+    mine = npm.buffer_pt_index.long()
+    assert torch.equal(mine >= 0, table >= 0)
+    differ = torch.nonzero(mine != table).flatten()
+    for s in differ.tolist():
+        a, b = int(mine[s]), int(table[s])
+        assert int(npm._slots(npm.neural_points[a:a + 1])) == s == int(npm._slots(npm.neural_points[b:b + 1]))
+    assert differ.numel() <= 0.02 * int((table >= 0).sum())
+
+
+def test_dropin_loop_closure_map_adjustment_matches_reference():
+    """SURVEY.md section 8 row f4 (host side): adjust_map (per-frame pose corrections incl. the quaternion update) and
+    recreate_hash in both modes reproduce the reference (model/neural_points.py:791-908) on its fixture."""
+    fx = load_npz("loop_kitti")
+    npm = _dropin_from_fixture(fx)
+    npm.config.use_mid_ts = bool(fx["cfg.use_mid_ts"])
+    pos, cur_ts = t(fx["sensor_pos"]), int(fx["map.cur_ts"])
+    npm.adjust_map(t(fx["pose_diff"]))
+    assert npm.after_pgo
+    np.testing.assert_allclose(npm.neural_points.numpy(), fx["adjusted.neural_points"], rtol=1e-6, atol=1e-6)
+    q, qr = npm.point_orientations.numpy(), fx["adjusted.point_orientations"]
+    sign = np.sign((q * qr).sum(1, keepdims=True))  # q and -q are the same rotation
+    np.testing.assert_allclose(q * sign, qr, rtol=1e-5, atol=1e-6)
+    import copy
+
+    kept = copy.deepcopy(npm)
+    kept.recreate_hash(pos, torch.eye(3), kept_points=True, with_ts=True, cur_ts=cur_ts)
+    _assert_same_hash_table(kept, fx["rehash_kept.table_slots"], fx["rehash_kept.table_vals"])
+    assert np.array_equal(kept.local_mask.numpy(), fx["rehash_kept.local_mask"])
+    filt = copy.deepcopy(npm)
+    filt.recreate_hash(pos, torch.eye(3), kept_points=False, with_ts=True, cur_ts=cur_ts)
+    np.testing.assert_allclose(filt.neural_points.numpy(), fx["rehash_filter.neural_points"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(filt.geo_features.numpy(), fx["rehash_filter.geo_features"])
+    assert np.array_equal(filt.point_ts_create.numpy(), fx["rehash_filter.point_ts_create"])
+    _assert_same_hash_table(filt, fx["rehash_filter.table_slots"], fx["rehash_filter.table_vals"])
