@@ -21,6 +21,7 @@ outputs of the reference functions on the hot path:
   Mesher.query_points (dense grid query)    utils/mesher.py:40
   DataSampler.sample (per-ray samples)      utils/data_sampler.py:18
   NeuralPoints.adjust_map / recreate_hash   model/neural_points.py:791,820 (loop-closure map adjustment)
+  NeuralPoints.update (map growth)          model/neural_points.py:311
 
 Optional reference imports (open3d, gtsam, ...) that are absent here and unused
 by the hot path are stubbed in sys.modules before import.
@@ -481,9 +482,39 @@ def gen_loop_fixture(kind, seed, name=None):
     print("wrote", name, "points", npm.count(), "after duplicate filter", filt.count())
 
 
+def gen_growth_fixture(kind, seed, n_frames=3, name=None):
+    """Map growth through NeuralPoints.update (model/neural_points.py:311-422) with a table large enough that no two
+    voxels collide (collision winners are unspecified in torch), non-zero feature init so the RNG stream is pinned."""
+    cfg = make_config(kind)
+    cfg.buffer_size = 2000003
+    cfg.feature_std = 0.05
+    cfg.local_map_radius = 9.0
+    torch.manual_seed(seed)
+    npm = NeuralPoints(cfg)
+    npm.diff_travel_dist_local = 4.5
+    npm.travel_dist = torch.tensor([0.0, 2.0, 4.0, 6.0, 8.0][: n_frames + 1])
+    out = {"seed": np.int64(seed), "n_frames": np.int64(n_frames), "cfg.feature_std": np.float64(cfg.feature_std),
+           "cfg.local_map_radius": np.float64(cfg.local_map_radius)}
+    for f in range(n_frames):
+        pts = scene_points(6000, seed * 10 + f)
+        pts[:, 0] += 1.5 * f
+        pos = torch.tensor([1.5 * f, 0.0, 1.0])
+        out[f"frame{f}.points"] = pts.numpy().copy()
+        out[f"frame{f}.pos"] = pos.numpy().copy()
+        npm.update(pts, pos, torch.eye(3), f)
+        out[f"frame{f}.count"] = np.int64(npm.count())
+    out.update(map_state(npm))
+    name = name or f"growth_{kind}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "points", npm.count())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "growth":
+        gen_growth_fixture("kitti", 51)
+        sys.exit(0)
     if only == "loop":
         gen_loop_fixture("kitti", 41)
         sys.exit(0)
@@ -511,6 +542,7 @@ if __name__ == "__main__":
     gen_sampler_fixture("kitti", 31)
     gen_sampler_fixture("replica", 32, color=True)
     gen_loop_fixture("kitti", 41)
+    gen_growth_fixture("kitti", 51)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
                 f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

@@ -337,3 +337,33 @@ def test_dropin_loop_closure_map_adjustment_matches_reference():
     assert np.array_equal(filt.geo_features.numpy(), fx["rehash_filter.geo_features"])
     assert np.array_equal(filt.point_ts_create.numpy(), fx["rehash_filter.point_ts_create"])
     _assert_same_hash_table(filt, fx["rehash_filter.table_slots"], fx["rehash_filter.table_vals"])
+
+
+def test_dropin_map_growth_matches_reference():
+    """SURVEY.md section 8 row f1 (host side): three frames of NeuralPoints.update on the drop-in grow the same map as
+    the reference (model/neural_points.py:311-422): same points in the same order, same timestamps, same hash table,
+    the same randn feature initialisation (RNG stream), and the same local map after the built-in reset."""
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import NeuralPoints
+
+    fx = load_npz("growth_kitti")
+    g = lambda k: fx["map." + k]  # noqa: E731
+    cfg = HotPathConfig.kitti(device="cpu", buffer_size=int(g("buffer_size")), feature_std=float(fx["cfg.feature_std"]),
+                              local_map_radius=float(fx["cfg.local_map_radius"]))
+    torch.manual_seed(int(fx["seed"]))
+    npm = NeuralPoints(cfg)
+    npm.diff_travel_dist_local = float(g("diff_travel_dist_local"))
+    npm.travel_dist = t(g("travel_dist"))
+    for f in range(int(fx["n_frames"])):
+        npm.update(t(fx[f"frame{f}.points"]), t(fx[f"frame{f}.pos"]), torch.eye(3), f)
+        assert npm.count() == int(fx[f"frame{f}.count"])
+    assert np.array_equal(npm.neural_points.numpy(), g("neural_points"))
+    assert np.array_equal(npm.point_ts_create.numpy(), g("point_ts_create"))
+    assert np.array_equal(npm.point_ts_update.numpy(), g("point_ts_update"))
+    assert np.array_equal(npm.geo_features.numpy(), g("geo_features"))
+    table = torch.full((npm.buffer_size,), -1, dtype=torch.int64)
+    table[t(g("table_slots"))] = t(g("table_vals")).long()
+    assert torch.equal(npm.buffer_pt_index.long(), table)
+    assert np.array_equal(npm.local_mask.numpy(), g("local_mask"))
+    assert np.array_equal(npm.global2local.numpy().astype(np.int64), g("global2local").astype(np.int64))
+    assert np.array_equal(npm.local_geo_features.data.numpy(), g("local_geo_features"))
