@@ -22,6 +22,7 @@ outputs of the reference functions on the hot path:
   DataSampler.sample (per-ray samples)      utils/data_sampler.py:18
   NeuralPoints.adjust_map / recreate_hash   model/neural_points.py:791,820 (loop-closure map adjustment)
   NeuralPoints.update (map growth)          model/neural_points.py:311
+  Mapper.process_frame (sampling + pool)    utils/mapper.py:162
 
 Optional reference imports (open3d, gtsam, ...) that are absent here and unused
 by the hot path are stubbed in sys.modules before import.
@@ -509,9 +510,62 @@ def gen_growth_fixture(kind, seed, n_frames=3, name=None):
     print("wrote", name, "points", npm.count())
 
 
+def gen_frame_fixture(kind, seed, n_frames=3, name=None):
+    """Mapper.process_frame over a few frames (utils/mapper.py:162-449): per-ray sampling, map growth, replay-pool
+    append + window filter, and the new-sample selection through query_certainty.  Collision-free table; the RNG is
+    re-seeded before every frame so that the sampler / pool-filter draws are pinned."""
+    cfg = make_config(kind)
+    cfg.buffer_size = 2000003
+    cfg.local_map_radius = 9.0
+    cfg.pool_filter_freq = 2       # exercise the window filter on frame 1
+    cfg.window_radius = 12.0
+    cfg.adaptive_iters = True
+    torch.manual_seed(seed)
+    npm = NeuralPoints(cfg)
+    npm.diff_travel_dist_local = 4.5
+    npm.travel_dist = torch.tensor([0.0, 2.0, 4.0, 6.0, 8.0][: n_frames + 1])
+    sdf_mlp = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    poses = np.tile(np.eye(4), (n_frames, 1, 1))
+    poses[:, 0, 3] = 1.5 * np.arange(n_frames)
+    poses[:, 2, 3] = 1.0
+    dataset = types.SimpleNamespace(processed_frame=0, lose_track=False, stop_status=False, gt_pose_provided=False,
+                                    odom_poses=poses.copy(), pgo_poses=None, gt_poses=None, static_mask=None)
+    mapper = Mapper(cfg, dataset, npm, {"sdf": sdf_mlp, "semantic": None, "color": None})
+    out = {"seed": np.int64(seed), "n_frames": np.int64(n_frames), "poses": poses,
+           "cfg.local_map_radius": np.float64(cfg.local_map_radius), "cfg.window_radius": np.float64(cfg.window_radius),
+           "cfg.pool_filter_freq": np.int64(cfg.pool_filter_freq), "cfg.max_range": np.float64(cfg.max_range),
+           "travel_dist": npm.travel_dist.numpy().copy()}
+    for f in range(n_frames):
+        world = scene_points(3000, seed * 10 + f)
+        world[:, 0] += 1.5 * f
+        pose = torch.tensor(poses[f], dtype=torch.float64)
+        sensor = (world - pose[:3, 3].float())  # identity rotation
+        dataset.processed_frame = f
+        out[f"frame{f}.points"] = sensor.numpy().copy()
+        torch.manual_seed(seed * 100 + f)
+        mapper.process_frame(sensor.clone(), None, pose, f)
+        out[f"frame{f}.pool_sample_count"] = np.int64(mapper.pool_sample_count)
+        out[f"frame{f}.cur_sample_count"] = np.int64(mapper.cur_sample_count)
+        out[f"frame{f}.map_count"] = np.int64(npm.count())
+        out[f"frame{f}.new_idx"] = mapper.new_idx.numpy().copy()
+        out[f"frame{f}.adaptive_iter_offset"] = np.int64(mapper.adaptive_iter_offset)
+    out["pool.coord"] = mapper.coord_pool.numpy().copy()
+    out["pool.global_coord"] = mapper.global_coord_pool.numpy().copy()
+    out["pool.sdf_label"] = mapper.sdf_label_pool.numpy().copy()
+    out["pool.weight"] = mapper.weight_pool.numpy().copy()
+    out["pool.time"] = mapper.time_pool.numpy().copy()
+    name = name or f"frames_{kind}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "pool", mapper.pool_sample_count, "map", npm.count(),
+          "new", [int(out[f"frame{f}.new_idx"].shape[0]) for f in range(n_frames)])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "frames":
+        gen_frame_fixture("kitti", 61)
+        sys.exit(0)
     if only == "growth":
         gen_growth_fixture("kitti", 51)
         sys.exit(0)
@@ -543,6 +597,7 @@ if __name__ == "__main__":
     gen_sampler_fixture("replica", 32, color=True)
     gen_loop_fixture("kitti", 41)
     gen_growth_fixture("kitti", 51)
+    gen_frame_fixture("kitti", 61)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
                 f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

@@ -367,3 +367,64 @@ def test_dropin_map_growth_matches_reference():
     assert np.array_equal(npm.local_mask.numpy(), g("local_mask"))
     assert np.array_equal(npm.global2local.numpy().astype(np.int64), g("global2local").astype(np.int64))
     assert np.array_equal(npm.local_geo_features.data.numpy(), g("local_geo_features"))
+
+
+def test_dropin_process_frame_matches_reference():
+    """SURVEY.md section 8 row f2 (host side): three frames of the drop-in Mapper.process_frame -- per-ray sampling,
+    map growth, replay-pool append + window filter, new-sample selection -- reproduce the reference
+    (utils/mapper.py:162-449).  The one CUDA call on this path (query_certainty) is served by the oracle here, so the
+    host logic runs on the CPU."""
+    import types
+
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import Decoder, NeuralPoints
+    from pin_slam_b200.utils.mapper import Mapper
+
+    fx = load_npz("frames_kitti")
+    n_frames = int(fx["n_frames"])
+    cfg = HotPathConfig.kitti(device="cpu", buffer_size=2000003, local_map_radius=float(fx["cfg.local_map_radius"]),
+                              pool_filter_freq=int(fx["cfg.pool_filter_freq"]), adaptive_iters=True)
+    cfg.window_radius = float(fx["cfg.window_radius"])
+    torch.manual_seed(int(fx["seed"]))
+    npm = NeuralPoints(cfg)
+    npm.diff_travel_dist_local = 4.5
+    npm.travel_dist = t(fx["travel_dist"])
+    dec = Decoder(cfg, 64, 1, 1)
+    poses = fx["poses"]
+    dataset = types.SimpleNamespace(processed_frame=0, lose_track=False, stop_status=False, gt_pose_provided=False,
+                                    odom_poses=poses.copy(), pgo_poses=None, gt_poses=None, static_mask=None)
+    mapper = Mapper(cfg, dataset, npm, {"sdf": dec, "semantic": None, "color": None})
+
+    def oracle_certainty(q):  # stands in for pinb200_query_certainty (CUDA) on this CPU-only run
+        n = npm.count()
+        m = po.OracleMap(resolution=npm.resolution, buffer_size=npm.buffer_size, feature_dim=cfg.feature_dim,
+                         neural_points=npm.neural_points, point_orientations=npm.point_orientations,
+                         geo_features=npm.geo_features, color_features=None, point_ts_create=npm.point_ts_create,
+                         point_ts_update=npm.point_ts_update, point_certainties=npm.point_certainties,
+                         buffer_pt_index=npm.buffer_pt_index.long(), local_neural_points=npm.local_neural_points,
+                         local_point_orientations=npm.local_point_orientations,
+                         local_geo_features=npm.local_geo_features.data, local_color_features=None,
+                         local_point_certainties=npm.local_point_certainties,
+                         local_point_ts_update=npm.local_point_ts_update, local_mask=npm.local_mask,
+                         global2local=npm.global2local.long(), neighbor_dx=npm.neighbor_dx,
+                         max_valid_dist2=npm.max_valid_dist2, travel_dist=npm.travel_dist, cur_ts=npm.cur_ts,
+                         diff_travel_dist_local=npm.diff_travel_dist_local, temporal_local_map_on=True,
+                         after_pgo=False)
+        assert m.neural_points.shape[0] == n
+        return po.query_certainty(m, q)
+
+    npm.query_certainty = oracle_certainty
+    for f in range(n_frames):
+        dataset.processed_frame = f
+        torch.manual_seed(int(fx["seed"]) * 100 + f)
+        mapper.process_frame(t(fx[f"frame{f}.points"]), None, torch.tensor(poses[f], dtype=torch.float64), f)
+        assert npm.count() == int(fx[f"frame{f}.map_count"])
+        assert mapper.pool_sample_count == int(fx[f"frame{f}.pool_sample_count"])
+        assert mapper.cur_sample_count == int(fx[f"frame{f}.cur_sample_count"])
+        assert np.array_equal(mapper.new_idx.numpy(), fx[f"frame{f}.new_idx"])
+        assert mapper.adaptive_iter_offset == int(fx[f"frame{f}.adaptive_iter_offset"])
+    np.testing.assert_allclose(mapper.coord_pool.numpy(), fx["pool.coord"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(mapper.global_coord_pool.numpy(), fx["pool.global_coord"], rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(mapper.sdf_label_pool.numpy(), fx["pool.sdf_label"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mapper.weight_pool.numpy(), fx["pool.weight"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(mapper.time_pool.numpy(), fx["pool.time"])
