@@ -560,9 +560,82 @@ def gen_frame_fixture(kind, seed, n_frames=3, name=None):
           "new", [int(out[f"frame{f}.new_idx"].shape[0]) for f in range(n_frames)])
 
 
+def gen_track_fixture(kind, seed, name=None):
+    """Tracker.tracking (utils/tracker.py:43-225), the full convergence loop, on a briefly trained map: two frames of
+    process_frame + mapping, then the second scan is registered from a perturbed initial pose."""
+    cfg = make_config(kind)
+    cfg.buffer_size = 2000003
+    cfg.local_map_radius = 12.0
+    cfg.bs = 4096
+    torch.manual_seed(seed)
+    npm = NeuralPoints(cfg)
+    npm.diff_travel_dist_local = 6.0
+    npm.travel_dist = torch.tensor([0.0, 1.0, 2.0])
+    sdf_mlp = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    decoders = {"sdf": sdf_mlp, "semantic": None, "color": None}
+    poses = np.tile(np.eye(4), (2, 1, 1))
+    poses[1, 0, 3] = 0.8
+    poses[:, 2, 3] = 1.0
+    dataset = types.SimpleNamespace(processed_frame=0, lose_track=False, stop_status=False, gt_pose_provided=False,
+                                    odom_poses=poses.copy(), pgo_poses=None, gt_poses=None, static_mask=None)
+    mapper = Mapper(cfg, dataset, npm, decoders)
+    tracker = Tracker(cfg, npm, decoders)
+    scans = []
+    for f in range(2):
+        world = scene_points(8000, seed * 10 + f)
+        pose = torch.tensor(poses[f], dtype=torch.float64)
+        sensor = world - pose[:3, 3].float()
+        scans.append(sensor)
+        dataset.processed_frame = f
+        torch.manual_seed(seed * 100 + f)
+        mapper.process_frame(sensor.clone(), None, pose, f)
+        mapper.mapping(40)
+    out = {}
+    out.update(map_state(npm))
+    out.update(dec_state(sdf_mlp, "sdf_mlp"))
+    out["cfg.query_nn_k"] = np.int64(cfg.query_nn_k)
+    out["cfg.weighted_first"] = np.bool_(cfg.weighted_first)
+    out["cfg.local_map_radius"] = np.float64(cfg.local_map_radius)
+    src = scans[1][::7].contiguous()  # ~1100 source points
+    ang = 0.02
+    init = torch.tensor(poses[1], dtype=torch.float64)
+    init[:3, :3] = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    init[:3, 3] += torch.tensor([0.12, -0.08, 0.03], dtype=torch.float64)
+    out["source"] = src.numpy().copy()
+    out["init_pose"] = init.numpy().copy()
+    calls = []
+    orig = tracker.registration_step
+
+    def counted(*a, **k):
+        r = orig(*a, **k)
+        calls.append((float(r[5]), int(r[4].shape[0])))
+        return r
+
+    tracker.registration_step = counted
+    T, cov, _, valid = tracker.tracking(src.clone(), init.clone(), cur_ts=1)
+    out["result.T"] = T.numpy().copy()
+    out["result.valid"] = np.bool_(valid)
+    out["result.n_iter"] = np.int64(len(calls))
+    out["result.residual_cm"] = np.array([c[0] for c in calls])
+    out["result.valid_count"] = np.array([c[1] for c in calls])
+    cfg_floats = [cfg.reg_min_grad_norm, cfg.reg_max_grad_norm, cfg.reg_GM_dist_m, cfg.reg_GM_grad, cfg.reg_lm_lambda,
+                  cfg.reg_term_thre_deg, cfg.reg_term_thre_m, cfg.surface_sample_range_m,
+                  cfg.final_residual_ratio_thre, cfg.max_sdf_std_ratio, cfg.eigenvalue_ratio_thre]
+    out["cfg.reg_floats"] = np.array(cfg_floats, np.float64)
+    out["cfg.reg_ints"] = np.array([cfg.reg_iter_n, cfg.track_mask_query_nn_k], np.int64)
+    name = name or f"track_{kind}"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    err = np.linalg.norm(T.numpy()[:3, 3] - poses[1][:3, 3])
+    print("wrote", name, "iters", len(calls), "valid", valid, "residual_cm", [round(c[0], 2) for c in calls][:12],
+          "final translation error %.3f m (init 0.147)" % err)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "track":
+        gen_track_fixture("kitti", 71)
+        sys.exit(0)
     if only == "frames":
         gen_frame_fixture("kitti", 61)
         sys.exit(0)
@@ -598,6 +671,7 @@ if __name__ == "__main__":
     gen_loop_fixture("kitti", 41)
     gen_growth_fixture("kitti", 51)
     gen_frame_fixture("kitti", 61)
+    gen_track_fixture("kitti", 71)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from /root/reference (PRBonn/PIN_SLAM)\n"
                 f"torch {torch.__version__} cpu fp32, numpy {np.__version__}\n")

@@ -428,3 +428,53 @@ def test_dropin_process_frame_matches_reference():
     np.testing.assert_allclose(mapper.sdf_label_pool.numpy(), fx["pool.sdf_label"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(mapper.weight_pool.numpy(), fx["pool.weight"], rtol=1e-6, atol=1e-7)
     assert np.array_equal(mapper.time_pool.numpy(), fx["pool.time"])
+
+
+def test_dropin_tracking_loop_matches_reference():
+    """The host-side convergence loop of the drop-in Tracker.tracking (iteration count, residual / valid-point checks,
+    termination thresholds, final pose) against the reference's Tracker.tracking (utils/tracker.py:43-225) on a
+    briefly trained map.  The per-iteration CUDA call (pinb200_track_iterations: K1 + K4) is served by the oracle's
+    query + registration step here, in the result layout of include/pinb200.h, so the loop runs on the CPU."""
+    import types
+
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.utils.tracker import Tracker
+
+    fx = load_npz("track_kitti")
+    m = map_from_fixture(fx)
+    dec = decoder_from_fixture(fx, "sdf_mlp")
+    k, wf = int(fx["cfg.query_nn_k"]), bool(fx["cfg.weighted_first"])
+    (min_g, max_g, gm_d, gm_g, lm, term_deg, term_m, surf_range, final_ratio, std_ratio,
+     eig_thre) = (float(v) for v in fx["cfg.reg_floats"])
+    iter_n, min_nn = (int(v) for v in fx["cfg.reg_ints"])
+    cfg = HotPathConfig.kitti(device="cpu")
+    cfg.reg_min_grad_norm, cfg.reg_max_grad_norm, cfg.reg_GM_dist_m, cfg.reg_GM_grad = min_g, max_g, gm_d, gm_g
+    cfg.reg_lm_lambda, cfg.reg_term_thre_deg, cfg.reg_term_thre_m = lm, term_deg, term_m
+    cfg.surface_sample_range_m, cfg.final_residual_ratio_thre, cfg.max_sdf_std_ratio = surf_range, final_ratio, std_ratio
+    cfg.eigenvalue_ratio_thre, cfg.reg_iter_n, cfg.track_mask_query_nn_k = eig_thre, iter_n, min_nn
+    tracker = Tracker(cfg, types.SimpleNamespace(), {"sdf": None, "semantic": None, "color": None})
+    log = []
+
+    def oracle_iterate(src, t_dev, n_iter, normals, sdf_label, colors, cdec, cgrad, cmode):
+        assert n_iter == 1 and cmode == 0
+        xyz = po.transform_points(src, t_dev)
+        q = po.query_sdf(m, dec, xyz, k, wf, query_locally=True, need_grad=True)
+        r = po.registration_step(xyz, q["sdf"], q["grad"], q["sdf_std"], q["nn_count"],
+                                 torch.zeros(src.shape[0]) if sdf_label is None else sdf_label, min_nn, min_g, max_g,
+                                 surf_range * std_ratio, gm_d if gm_d > 0 else None, gm_g if gm_g > 0 else None, lm,
+                                 normals=normals)
+        res = torch.zeros(32, dtype=torch.float64)  # layout of pinb200_gn_step's `result`
+        res[:16] = r["T"].reshape(-1)
+        res[16] = r["valid_count"]
+        res[17] = r["residual_cm"]
+        t_dev.copy_(r["T"] @ t_dev)  # T <- dT @ T on the "device"
+        log.append((float(res[17]), int(res[16])))
+        return None, res, torch.zeros(64, dtype=torch.float64)
+
+    tracker._iterate = oracle_iterate
+    T, cov, _, valid = tracker.tracking(t(fx["source"]), t(fx["init_pose"]).double(), cur_ts=1)
+    assert valid == bool(fx["result.valid"])
+    assert len(log) == int(fx["result.n_iter"])
+    np.testing.assert_allclose([x[0] for x in log], fx["result.residual_cm"], rtol=2e-3, atol=2e-3)
+    assert np.abs(np.array([x[1] for x in log]) - fx["result.valid_count"]).max() <= 2
+    np.testing.assert_allclose(T.numpy(), fx["result.T"], rtol=0, atol=2e-4)
