@@ -284,6 +284,8 @@ def _dropin_from_fixture(fx, color=False):
     npm.neural_points = t(g("neural_points")).clone()
     npm.point_orientations = t(g("point_orientations")).clone()
     npm.geo_features = t(g("geo_features")).clone()
+    if color:
+        npm.color_features = t(g("color_features")).clone()
     npm.point_ts_create = t(g("point_ts_create")).clone()
     npm.point_ts_update = t(g("point_ts_update")).clone()
     npm.point_certainties = t(g("point_certainties")).clone()
@@ -478,3 +480,44 @@ def test_dropin_tracking_loop_matches_reference():
     np.testing.assert_allclose([x[0] for x in log], fx["result.residual_cm"], rtol=2e-3, atol=2e-3)
     assert np.abs(np.array([x[1] for x in log]) - fx["result.valid_count"]).max() <= 2
     np.testing.assert_allclose(T.numpy(), fx["result.T"], rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("name", QUERY_FIXTURES)
+@pytest.mark.parametrize("local", [True, False])
+def test_dropin_query_feature_assembly_matches_reference(name, local, monkeypatch):
+    """The reference-signature hot call of the drop-in (NeuralPoints.query_feature, differentiable torch assembly on top
+    of the kNN ids) against the reference's outputs.  The kNN search itself (pinb200_knn_search on the GPU) is served
+    by the oracle here, so the assembly -- global->local quirk, neighbour vectors, IDW weights, certainty,
+    weighted-first reduction -- is checked on the CPU."""
+    from pin_slam_b200 import ops
+
+    fx = load_npz(name)
+    m = map_from_fixture(fx)
+    color = "map.color_features" in fx
+    npm = _dropin_from_fixture(fx, color=color)
+    npm.config.weighted_first = bool(fx["cfg.weighted_first"])
+    npm.config.query_nn_k = int(fx["cfg.query_nn_k"])
+    npm.after_pgo = bool(fx["map.after_pgo"])
+    npm.reset_local_map(t(fx["sensor_pos"]), torch.eye(3), int(fx["map.cur_ts"]))
+    npm.map_handle = lambda query_locally=True: ("oracle", bool(query_locally))
+
+    def oracle_knn(handle, q, k, want_gidx=False):
+        loc = handle[1]
+        d2, gidx = po.radius_search(m, q, time_filtering=m.temporal_local_map_on and loc)
+        idx = m.global2local[gidx] if loc else gidx.clone()
+        cnt = (idx >= 0).sum(-1)
+        d2 = d2.clone()
+        d2[idx == -1] = 9e3
+        sd, order = torch.sort(d2, dim=1)
+        idx, gidx = idx.gather(1, order)[:, :k], gidx.gather(1, order)[:, :k]
+        gidx = torch.where(idx >= 0, gidx, torch.full_like(gidx, -1))
+        return idx.int(), sd[:, :k], None, cnt.int(), gidx.int()
+
+    monkeypatch.setattr(ops, "knn_search", oracle_knn)
+    q = t(fx["q"])
+    geo, _, w, cnt, cert = npm.query_feature(q, training_mode=False, query_locally=local)
+    tag = "qf_local" if local else "qf_global"
+    assert np.array_equal(cnt.numpy(), fx[tag + ".nn_counts"])
+    np.testing.assert_allclose(w.numpy(), fx[tag + ".weight"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(geo.detach().numpy(), fx[tag + ".geo"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(cert.numpy(), fx[tag + ".certainty"], rtol=1e-5, atol=1e-6)
