@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PINB200_VERSION 100 /* round 1 */
+#define PINB200_VERSION 200 /* round 2: probe index (probe_words / probe_rec / probe_gid) replaces search_rec */
 #define PINB200_MAX_HIDDEN_LAYERS 4
 #define PINB200_MAX_K 8 /* neighbours kept in registers by the fused search; the reference uses 6 (default) / 8 */
 
@@ -38,6 +38,8 @@ extern "C" {
 #define PINB200_ERR_BAD_ARG (-1)
 #define PINB200_ERR_UNSUPPORTED (-2)
 #define PINB200_ERR_CUDA (-3)
+
+#define PINB200_REC_REMAP (1 << 30) /* flag bit of the id word of a probe record, see pinb200_map_view.probe_rec */
 
 /* State of a neural point map as the kernels see it.
  * Mirrors NeuralPoints' tensors, model/neural_points.py:82-136. */
@@ -70,13 +72,24 @@ typedef struct pinb200_map_view {
   int32_t cur_ts;
   float diff_travel_dist_local;
   int32_t after_pgo;           /* rotate neighbour vectors by the point quaternion (:645) */
-  /* Optional packed search records, one 32-byte sector per global point (B200 layout: a probe hit costs one
-   * sector and one dependent load level instead of three arrays and two levels):
-   *   [n_global, 8] f32 = { x, y, z, travel_dist[ts_create], bit-cast int32 id in the queried index space
-   *                         (global2local[i], or i when global2local is NULL), 0, 0, 0 }
-   * Built by the host wrapper whenever the map / local map / travel distance changes; NULL => the kernels
-   * read points / ts_create / travel_dist / global2local separately. */
-  const float* search_rec;
+  /* Probe index (B200 layout, built by pinb200_build_probe_index): a succinct rank structure holding the ANSWERS
+   * of the hash table in L2-resident form.  A probe of the fused query reads one 8-byte word and, on a hit, one
+   * 16-byte record, both from arrays of a few MB, instead of walking buffer_pt_index -> neural_points /
+   * point_ts_create -> travel_dist / global2local (model/neural_points.py:963-999,573) in a table of several
+   * hundred MB; the age / local-map tests are folded in when the index is built.
+   *   probe_words [ceil(buffer_size/32), 2] u32 = { occupancy bits of 32 consecutive slots, set bits before the word };
+   *               bit s is set iff slot s is owned by a point this view can return (id >= 0, inside the
+   *               travel-distance window when time_filter)
+   *   probe_rec   [n_rec, 4] f32 = { x, y, z, bit-cast int32 id } in slot (rank) order; id = global2local[i] (or i),
+   *               bit 30 (PINB200_REC_REMAP) set when nb_points[id] is a different point than points[i] (the
+   *               reference's global2local fill value maps points outside the local map to local id 1,
+   *               model/neural_points.py:498)
+   *   probe_gid   [n_rec] i32 = global ids of the same points
+   * Required by pinb200_query_sdf / track_iterations / map_iterations (K1); the search-only entry points
+   * (knn_search, radius_search, query_certainty) read the separate arrays. */
+  const uint32_t* probe_words;
+  const float* probe_rec;
+  const int32_t* probe_gid;
 } pinb200_map_view;
 
 /* Weights of one Decoder (model/decoder.py:43-51), torch nn.Linear layout. */
@@ -306,12 +319,17 @@ int pinb200_color_loss(const float* color_pred, const float* color_label, const 
                        int32_t loss_weight_on, float weight_i, float grad_scale, const float* n_surface,
                        float* dloss_dcolor, float* loss, void* stream);
 
-/* Packed 32-byte search records of the global map (pinb200_map_view.search_rec): one launch writes
- * rec[i] = {x, y, z, travel_dist[ts_create[i]] (0 if travel_dist == NULL), bits(global2local[i]) (i if NULL), 0, 0, 0}.
- * Replaces the separate reads of neural_points / point_ts_create / travel_dist / global2local
- * (model/neural_points.py:538-581) inside the search loop by one 32-byte load per probe hit. */
-int pinb200_build_search_records(const float* points, const int32_t* ts_create, const float* travel_dist,
-                                 const int32_t* global2local, int64_t n_global, float* search_rec, void* stream);
+/* Probe index of a map view (pinb200_map_view.probe_words / probe_rec / probe_gid, layout documented there).
+ * Six stream-ordered operations (clear, mark, 3-step prefix sum over the words, scatter); call it whenever the map
+ * view changes (NeuralPoints.update / reset_local_map / recreate_hash, a new travel_dist or cur_ts).  `map` supplies
+ * slot_table, buffer_size, points, n_global, ts_create, travel_dist, global2local, nb_points, resolution and the
+ * time-filter fields; its probe_* fields are ignored.  Sizes: probe_words = 2 * pinb200_probe_index_words(B) u32,
+ * probe_rec = 4 * n_global f32, probe_gid = n_global i32, scratch = pinb200_probe_index_scratch(B) i32
+ * (scratch[last] receives n_rec). */
+int64_t pinb200_probe_index_words(int64_t buffer_size);
+int64_t pinb200_probe_index_scratch(int64_t buffer_size);
+int pinb200_build_probe_index(const pinb200_map_view* map, uint32_t* probe_words, float* probe_rec,
+                              int32_t* probe_gid, int32_t* scratch, void* stream);
 
 /* Batch assembly of one map-training iteration in ONE launch (utils/mapper.py:482-503 pool gathers +
  * :990-1002 the six +-eps shifted copies of every `decimation`-th sample):

@@ -24,7 +24,7 @@ class MapView(C.Structure):
         ("certainty", c_f32p), ("ts_update", c_i32p), ("n_nb", C.c_int64), ("feature_dim", C.c_int32),
         ("probe_dx", c_i32p), ("n_probe", C.c_int32), ("resolution", C.c_float), ("max_valid_dist2", C.c_float),
         ("time_filter", C.c_int32), ("cur_ts", C.c_int32), ("diff_travel_dist_local", C.c_float),
-        ("after_pgo", C.c_int32), ("search_rec", c_f32p),
+        ("after_pgo", C.c_int32), ("probe_words", C.c_void_p), ("probe_rec", c_f32p), ("probe_gid", c_i32p),
     ]
 
 
@@ -89,7 +89,9 @@ SIGNATURES = {
     "pinb200_gn_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f32p, c_f32p,
                                   c_f32p, C.c_int32, C.c_int32, C.c_float, c_f64p, c_f64p, c_f64p, C.c_void_p]),
-    "pinb200_build_search_records": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int64, c_f32p, C.c_void_p]),
+    "pinb200_probe_index_words": (C.c_int64, [C.c_int64]),
+    "pinb200_probe_index_scratch": (C.c_int64, [C.c_int64]),
+    "pinb200_build_probe_index": (C.c_int, [C.POINTER(MapView), C.c_void_p, c_f32p, c_i32p, c_i32p, C.c_void_p]),
     "pinb200_assemble_batch": (C.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_int32, C.c_float, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_void_p]),
     "pinb200_track_iterations": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,

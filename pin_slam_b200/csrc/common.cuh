@@ -188,110 +188,6 @@ __device__ __forceinline__ float idw_weight(float d2, bool valid, int nn_count, 
   return w;
 }
 
-// ---------------------------------------------------------------------------
-// Thread-per-query search: the K (<= KREG) nearest candidates live in registers
-// as a sorted list; the C probes are issued in batches of PROBE_BATCH independent
-// loads per dependency level (table -> point/ts/g2l -> travel distance) so that one
-// thread keeps ~8 loads in flight and a 128-thread CTA ~1000.
-// ---------------------------------------------------------------------------
-constexpr int PROBE_BATCH = 11;  // 33 probes (the default neighbourhood) = 3 batches
-
-// `scratch` (PINB_K1_SMEM_SELECT builds only): 2 x KREG x 32 ints of per-warp shared memory, see knn_select.cuh
-__device__ __forceinline__ int knn_search_thread(const pinb200_map_view& m, const uint32_t* s_delta, float qx, float qy,
-                                                 float qz, KnnRegs& L, int* scratch = nullptr) {
-#ifdef PINB_K1_SMEM_SELECT
-  const int sel_lane = threadIdx.x & 31;
-  int* sc_l = scratch;
-  int* sc_g = scratch + KREG * 32;
-  KnnKeys S;
-  knn_keys_init(S, sc_l, sc_g, sel_lane);
-#else
-  (void)scratch;
-  knn_regs_init(L);
-  KnnSel S;
-  S.worst = INVALID_D2;
-  S.wpos = 0;
-#endif
-  int count = 0;
-  const uint32_t r0 = base_slot(m, qx, qy, qz);
-  const bool tf = m.time_filter != 0;
-  const float td_cur = tf ? __ldg(m.travel_dist + m.cur_ts) : 0.f;
-  const uint32_t B = (uint32_t)m.buffer_size;
-  const int C = m.n_probe;
-  for (int c0 = 0; c0 < C; c0 += PROBE_BATCH) {
-    int gi[PROBE_BATCH];
-#pragma unroll
-    for (int j = 0; j < PROBE_BATCH; ++j) {
-      gi[j] = -1;
-      if (c0 + j < C) {
-        uint32_t slot = r0 + s_delta[c0 + j];
-        if (slot >= B) slot -= B;
-        gi[j] = __ldg(m.slot_table + slot);
-      }
-    }
-    float px[PROBE_BATCH], py[PROBE_BATCH], pz[PROBE_BATCH], td[PROBE_BATCH];
-    int li[PROBE_BATCH];
-    if (m.search_rec) {
-      // one 32-byte record per hit: a single dependent load level
-#pragma unroll
-      for (int j = 0; j < PROBE_BATCH; ++j) {
-        px[j] = py[j] = pz[j] = 0.f;
-        td[j] = td_cur;
-        li[j] = -1;
-        if (gi[j] >= 0) {
-          const float4* rp = reinterpret_cast<const float4*>(m.search_rec + 8 * (size_t)gi[j]);
-          const float4 a = __ldg(rp);
-          const float b = __ldg(reinterpret_cast<const float*>(rp + 1));
-          px[j] = a.x;
-          py[j] = a.y;
-          pz[j] = a.z;
-          td[j] = a.w;
-          li[j] = __float_as_int(b);
-        }
-      }
-    } else {
-      int ts[PROBE_BATCH];
-#pragma unroll
-      for (int j = 0; j < PROBE_BATCH; ++j) {
-        px[j] = py[j] = pz[j] = 0.f;
-        ts[j] = 0;
-        li[j] = -1;
-        if (gi[j] >= 0) {
-          const float* pp = m.points + 3 * (size_t)gi[j];
-          px[j] = __ldg(pp);
-          py[j] = __ldg(pp + 1);
-          pz[j] = __ldg(pp + 2);
-          if (tf) ts[j] = __ldg(m.ts_create + gi[j]);
-          li[j] = m.global2local ? __ldg(m.global2local + gi[j]) : gi[j];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < PROBE_BATCH; ++j) td[j] = (tf && gi[j] >= 0) ? __ldg(m.travel_dist + ts[j]) : td_cur;
-    }
-#pragma unroll
-    for (int j = 0; j < PROBE_BATCH; ++j) {
-      if (gi[j] < 0) continue;
-      const bool young = !tf || (fabsf(td_cur - td[j]) < m.diff_travel_dist_local);
-      const float dx = __fsub_rn(px[j], qx), dy = __fsub_rn(py[j], qy), dz = __fsub_rn(pz[j], qz);
-      const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      if (young && !(dd > m.max_valid_dist2) && li[j] >= 0) {
-        ++count;
-#ifdef PINB_K1_SMEM_SELECT
-        if (dd < S.worst) knn_keys_accept(S, dd, li[j], gi[j], sc_l, sc_g, sel_lane);
-#else
-        if (dd < S.worst) knn_sel_replace(L, S, dd, li[j], gi[j]);
-#endif
-      }
-    }
-  }
-#ifdef PINB_K1_SMEM_SELECT
-  knn_keys_finish(S, sc_l, sc_g, sel_lane, L);
-#else
-  knn_sort8(L);
-#endif
-  return count;
-}
-
 // Sum K (<= 8) per-lane values over the 32 lanes with 9 shuffles (vs 5 per value):
 // after the call, lane l holds the warp total of value k = 4*bit4(l) + 2*bit3(l) + bit2(l).
 __device__ __forceinline__ float warp_reduce8(float (&p)[8], int lane) {

@@ -137,34 +137,9 @@ __global__ void assemble_batch_kernel(const float* __restrict__ cp, const float*
   }
 }
 
-__global__ void build_search_records_kernel(const float* __restrict__ pts, const int32_t* __restrict__ tsc,
-                                            const float* __restrict__ travel, const int32_t* __restrict__ g2l,
-                                            long long n, float4* __restrict__ rec) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float tr = travel ? travel[tsc[i]] : 0.f;
-    const int id = g2l ? g2l[i] : (int)i;
-    rec[2 * i] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], tr);
-    rec[2 * i + 1] = make_float4(__int_as_float(id), 0.f, 0.f, 0.f);
-  }
-}
-
 }  // namespace pinb
 
 using namespace pinb;
-
-extern "C" int pinb200_build_search_records(const float* points, const int32_t* ts_create, const float* travel_dist,
-                                            const int32_t* global2local, int64_t n_global, float* search_rec,
-                                            void* stream) {
-  if (n_global <= 0) return PINB200_OK;
-  if (!points || !search_rec || (travel_dist && !ts_create)) {
-    set_error("build_search_records: null argument");
-    return PINB200_ERR_BAD_ARG;
-  }
-  const int grid = (int)std::min<long long>((n_global + 255) / 256, (long long)sm_count() * 16);
-  build_search_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, ts_create, travel_dist, global2local,
-                                                                     n_global, reinterpret_cast<float4*>(search_rec));
-  return check_launch("build_search_records_kernel");
-}
 
 extern "C" int pinb200_assemble_batch(const float* coord_pool, const float* label_pool, const int32_t* ts_pool,
                                       const float* weight_pool, const float* color_pool, int32_t color_channels,

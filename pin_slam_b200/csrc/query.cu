@@ -1,18 +1,22 @@
-// K1: fused voxel-hash kNN + IDW interpolation + decoder MLP + analytic d/dq.
+// K1: fused voxel-hash kNN + IDW interpolation + decoder MLP + analytic d/dq  (round-2 rewrite).
 //
-// Every WARP owns an independent tile of 32 queries (no block-wide barriers after the one-off weight
-// staging: 12 de-synchronised warps per SM overlap each other's memory and compute phases):
-//   weighted_first=1 : 32 decoder rows, one per query (features IDW-averaged first)
-//   weighted_first=0 : the 32 queries are decoded in row tiles of floor(32/K) queries x K rows
-// Phase A (warp per query): hash the query's cell, probe the C neighbour cells of
-//   the voxel hash table (one probe per lane, 32 at a time), age/distance filter,
-//   in-register warp top-K, IDW weights, coalesced gather of the neighbour feature
-//   rows (a 32-float row == one 128 B warp load), write the decoder input into the
-//   transposed shared-memory tile.
-// Phase B (thread per row): the tiny MLP forward and, if requested, the backward
-//   pass w.r.t. the decoder input, weights broadcast from shared memory.
-// Phase C (warp per query / thread per query): chain rule through the IDW weights
-//   and the neighbour vectors -> d sdf / d query, sdf std, outputs.
+// Every WARP owns an independent tile of 32 queries (no block-wide barriers after the one-off weight staging: the
+// 12 de-synchronised warps of the one CTA per SM overlap each other's memory and compute phases).  The phases of a
+// tile and the thread mapping each one uses:
+//   A1  thread per query   hash the query's cell; probe the C neighbour cells: ONE 16-byte load per probe from the
+//                          probe index (probe_index.cu); branch-free top-8 selection with sorting
+//                          networks (knn_select.cuh); the 8 winners' records are re-read (L1 hits) for positions and
+//                          ids; IDW weights, certainty, training-mode scatters, kNN outputs; everything later phases
+//                          need is stashed in [k][lane] shared-memory columns (conflict free)
+//   A2  F/4 lanes per row  16-byte coalesced gathers of the K feature rows of 128/F queries at a time (a 128-byte row
+//                          = 8 lanes x LDG.128: one L1 wavefront per row, 4 rows per instruction) and the IDW
+//                          reduction in registers -> decoder input rows in the warp's row-major tile
+//   B   warp MMA           decoder forward + backward to the decoder input on mma.sync 3xTF32 with register-chained
+//                          fragments (mlp_chain.cuh): only layer 0's input and the input gradient touch shared memory
+//   C1  F/4 lanes per row  a_k = <d sdf / d feature part of the input, f_k> (second coalesced pass over the K rows)
+//   C2  thread per query   chain rule through the IDW weights and the neighbour vectors -> d sdf / d q, outputs
+// weighted_first=0 decodes every (query, neighbour) pair: the 32 queries are processed in row tiles of floor(32/K)
+// queries x K rows, and C combines the K per-neighbour values (IDW mean / std, utils/tracker.py:313-328).
 //
 // Replaces model/neural_points.py:530-746,950-1009, model/decoder.py:61-85,112,
 // utils/tools.py:247-260, utils/tracker.py:313-328 of the reference.
@@ -21,14 +25,38 @@
 #include <vector>
 
 #include "mlp.cuh"
-#include "mlp_mma.cuh"
+#include "mlp_chain.cuh"
 
 namespace pinb {
 
+constexpr int WT = 32;   // queries (= threads) per warp tile
+constexpr int WPB = 12;  // warps per CTA (one CTA per SM): 12 x 32 threads x 168 registers fill the register file
+constexpr int REMAP = PINB200_REC_REMAP;
+
 struct QueryLayout {  // float offsets into dynamic smem
-  MmaDecSmem dec;
-  int delta, warp0, warp_stride, n_warps;  // CTA-shared part, then n_warps per-warp blocks
-  int act, knn_idx, knn_gidx, knn_d2, knn_w, knn_a, q, out, dv, nn, mask, total;  // offsets inside a warp block
+  ChainDecSmem dec;
+  int delta, warp0, n_warps, total;  // CTA-shared part, then n_warps per-warp blocks (WarpLay<FT>)
+};
+
+// Per-warp tile state, compile-time offsets (floats) so that every access is base + immediate.
+template <int FT>
+struct WarpLay {
+  static constexpr int KP0 = (FT + 3 + 7) / 8 * 8;
+  static constexpr int LDX = KP0 <= 8 ? 8 : ((KP0 - 8 + 31) / 32) * 32 + 8;
+  static constexpr int x = 0;                      // [32][LDX] decoder input rows / input gradient
+  static constexpr int li = x + WT * LDX;          // [K][32] neighbour id | REMAP (-1 invalid)
+  static constexpr int w = li + WT * 8;            // [K][32] IDW weight
+  static constexpr int dx = w + WT * 8;            // [K][32] q - p_k (the point dist2 was measured to)
+  static constexpr int dy = dx + WT * 8;
+  static constexpr int dz = dy + WT * 8;
+  static constexpr int a = dz + WT * 8;            // [K][32] <g_xbar, f_k>
+  static constexpr int q = a + WT * 8;             // [3][32] query
+  static constexpr int usum = q + WT * 3;          // [32] sum of the unnormalised weights
+  static constexpr int out = usum + WT;            // [32][<=4] decoder outputs
+  static constexpr int dv = out + WT * 4;          // [32][4] d out / d pre-activation
+  static constexpr int nn = dv + WT * 4;           // [32] nn_count
+  static constexpr int mask = nn + WT;             // [<=4 layers][32] 64-bit ReLU masks
+  static constexpr int stride = mask + 2 * WT * PINB200_MAX_HIDDEN_LAYERS;
 };
 
 struct QueryParams {
@@ -40,166 +68,283 @@ struct QueryParams {
   const int32_t* query_ts;
   const float* feat;  // feature table decoded by `dec` (geo or colour)
   long long n;
-  int use_saved_knn;  // 1: take kNN from out.knn_idx / out.knn_dist2 (decode-only launch, e.g. colour head)
+  int use_saved_knn;  // 1: take kNN from out.knn_idx / knn_gidx / knn_dist2 (decode-only launch, e.g. colour head)
   int is_color;       // outputs go to out.color / out.color_grad instead of sdf / grad
   int n_tiles;
-  int qpt;  // queries per tile
+  int qpt;  // queries per warp tile
   QueryLayout lay;
 };
 
-// ---------------------------------------------------------------------------
-// warp-per-query feature movement.  The feature dimension FT is a template
-// parameter so that the (neighbour, column) of every load is a compile-time
-// function of the unrolled loop indices; each warp works on GQ queries at once and
-// issues all of their row loads before consuming any (GQ * K independent 128-byte
-// loads in flight per warp).
-// ---------------------------------------------------------------------------
-#ifndef PINB_K1_GQ
-#define PINB_K1_GQ 8
-#endif
-constexpr int GQ_MAX = 8;  // queries gathered concurrently by one warp (4 for the widest rows: register budget)
-template <int FT>
-struct GqOf {
-  static constexpr int value = FT >= 64 ? 4 : PINB_K1_GQ;
-};
-constexpr int WT = 32;  // queries (= threads) per warp tile
-constexpr int WPB = 12; // max warps per CTA (one CTA per SM); fewer if shared memory does not fit
+// squared distance with the reference's arithmetic: sum((p - q)^2) in fp32, no contraction (:990-994)
+__device__ __forceinline__ float dist2_rn(float px, float py, float pz, float qx, float qy, float qz) {
+  const float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
 
-// FT >= 32: a neighbour row is FT/32 coalesced warp loads; FT < 32: 32/FT neighbour rows per warp load.
-template <int FT>
-struct FeatMap {
-  static constexpr int NJ = FT >= 32 ? FT / 32 : 1;     // warp loads per neighbour row
-  static constexpr int PER = FT >= 32 ? 1 : 32 / FT;    // neighbour rows per warp load
-  static constexpr int R = FT >= 32 ? KREG * NJ : (KREG + PER - 1) / PER;  // warp loads per query (K = KREG)
-};
+__device__ __forceinline__ uint32_t probe_slot(uint32_t r0, uint32_t delta, uint32_t B) {
+  uint32_t s = r0 + delta;
+  if (s >= B) s -= B;
+  return s;
+}
 
-// weighted_first: act[j][ql] = sum_k w_k f_k[j]  for the queries ql0 + g (g < GQ)
-template <int FT, int LDX, int GQ>
-__device__ __forceinline__ void gather_weighted_group(const float* __restrict__ feat, int K, const int* s_idx,
-                                                      const float* s_w, int lane, float* s_act, int ql0, int qpt) {
-  using M = FeatMap<FT>;
-  float v[GQ][M::R], w[GQ][M::R];
+// ---------------------------------------------------------------------------
+// A1: thread-per-query search over the probe index (pinb200_map_view.probe_words / probe_rec).  Returns nn_count;
+// T holds the 8 best (distance, record rank) pairs, ascending.  Per 32 probes: one round of 8-byte word loads
+// (occupancy + rank), then the records of the occupied slots 16 at a time (two sorting-network batches per round
+// trip).  The odd last probe of an 8n+1 neighbourhood (33, 57, 81) is issued with the first round and inserted last.
+// ---------------------------------------------------------------------------
+constexpr int PROBE_SUPER = 32;
+constexpr int PROBE_ROUND = 16;
+
+__device__ __forceinline__ int probe_rank(uint2 w, uint32_t slot) {
+  const uint32_t b = slot & 31u;
+  return ((w.x >> b) & 1u) ? (int)(w.y + __popc(w.x & ((1u << b) - 1u))) : -1;
+}
+
+__device__ __forceinline__ int knn_search_lane(const pinb200_map_view& m, const uint32_t* s_delta, bool live, uint32_t r0,
+                                               float qx, float qy, float qz, KnnTop& T) {
+  knn_top_init(T);
+  int count = 0;
+  const uint32_t B = (uint32_t)m.buffer_size;
+  const int C = m.n_probe;
+  const uint2* __restrict__ words = reinterpret_cast<const uint2*>(m.probe_words);
+  const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(m.probe_rec);
+  const float inf = __int_as_float(0x7f800000);
+  const float maxd2 = m.max_valid_dist2;
+  const bool odd = C > KREG && (C & (KREG - 1)) == 1;
+  const int Cb = odd ? C - 1 : C;
+  int rk_last = -1;
+  if (odd && live) {
+    const uint32_t slot = probe_slot(r0, s_delta[C - 1], B);
+    rk_last = probe_rank(__ldg(words + (slot >> 5)), slot);
+  }
+#pragma unroll 1
+  for (int c0 = 0; c0 < Cb; c0 += PROBE_SUPER) {
+    const int nb = Cb - c0;
+    int rk[PROBE_SUPER];
+    {
+      uint32_t slot[PROBE_SUPER];
+      uint2 wv[PROBE_SUPER];
 #pragma unroll
-  for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + g;
+      for (int j = 0; j < PROBE_SUPER; ++j) {
+        slot[j] = 0u;
+        wv[j] = make_uint2(0u, 0u);
+        if (live && j < nb) {
+          slot[j] = probe_slot(r0, s_delta[c0 + j], B);
+          wv[j] = __ldg(words + (slot[j] >> 5));
+        }
+      }
 #pragma unroll
-    for (int r = 0; r < M::R; ++r) {
-      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
-      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
-      v[g][r] = 0.f;
-      w[g][r] = 0.f;
-      if (k < K && ql < qpt) {
-        const int lk = s_idx[ql * K + k];
-        w[g][r] = s_w[ql * K + k];
-        v[g][r] = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * FT + col);
+      for (int j = 0; j < PROBE_SUPER; ++j) rk[j] = probe_rank(wv[j], slot[j]);
+    }
+#pragma unroll
+    for (int h = 0; h < PROBE_SUPER / PROBE_ROUND; ++h) {
+      if (h * PROBE_ROUND < nb) {
+        float4 r[PROBE_ROUND];
+#pragma unroll
+        for (int j = 0; j < PROBE_ROUND; ++j) {
+          r[j] = make_float4(inf, inf, inf, 0.f);
+          if (rk[h * PROBE_ROUND + j] >= 0) r[j] = __ldg(rec4 + rk[h * PROBE_ROUND + j]);
+        }
+#pragma unroll
+        for (int b = 0; b < PROBE_ROUND / KREG; ++b) {
+          if (h * PROBE_ROUND + b * KREG < nb) {
+            float d[KREG];
+            int pc[KREG];
+#pragma unroll
+            for (int j = 0; j < KREG; ++j) {
+              const float4 rr = r[b * KREG + j];
+              const float dd = dist2_rn(rr.x, rr.y, rr.z, qx, qy, qz);
+              const bool ok = dd <= maxd2;  // unoccupied probes carry +inf; dist2 > max is a hash collision (:999)
+              d[j] = ok ? dd : SEL_INVALID_D2;
+              pc[j] = ok ? rk[h * PROBE_ROUND + b * KREG + j] : -1;
+              count += ok ? 1 : 0;
+            }
+            if (c0 == 0 && h == 0 && b == 0)
+              knn_top_first8(T, d, pc);
+            else
+              knn_top_merge8(T, d, pc);
+          }
+        }
       }
     }
   }
+  if (odd) {
+    float4 rl = make_float4(inf, inf, inf, 0.f);
+    if (rk_last >= 0) rl = __ldg(rec4 + rk_last);
+    const float dd = dist2_rn(rl.x, rl.y, rl.z, qx, qy, qz);
+    const bool ok = dd <= maxd2;
+    count += ok ? 1 : 0;
+    knn_top_insert1(T, ok ? dd : SEL_INVALID_D2, ok ? rk_last : -1);
+  }
+  return count;
+}
+
+// neighbour vector n_k = q - p_k in the frame of the neural point (model/neural_points.py:632-651) from the stashed
+// global difference; `lif` = local id | REMAP flag.  Also returns the point quaternion when after_pgo.
+__device__ __forceinline__ void neighbour_vec(const pinb200_map_view& m, int lif, float dx, float dy, float dz, float qx,
+                                              float qy, float qz, float& nx, float& ny, float& nz, float4& quat) {
+  nx = dx;
+  ny = dy;
+  nz = dz;
+  const int li = lif & ~REMAP;
+  if (lif & REMAP) {  // the local id does not name the point the distance was measured to (reference quirk Q1)
+    const float* pp = m.nb_points + 3 * (size_t)li;
+    nx = __fsub_rn(qx, __ldg(pp));
+    ny = __fsub_rn(qy, __ldg(pp + 1));
+    nz = __fsub_rn(qz, __ldg(pp + 2));
+  }
+  quat = make_float4(1.f, 0.f, 0.f, 0.f);
+  if (m.after_pgo) {
+    quat = __ldg(reinterpret_cast<const float4*>(m.nb_orient) + li);
+    quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, nx, ny, nz, nx, ny, nz);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// A2 / C1: feature-row movement, FT/4 lanes per row (a lane owns 4 consecutive columns of its row)
+// ---------------------------------------------------------------------------
+template <int FT>
+struct RowMap {
+  static constexpr int LPR = FT / 4;    // lanes per feature row
+  static constexpr int RPP = 32 / LPR;  // rows (or queries) per pass
+  static constexpr int U = RPP >= 32 ? 1 : (RPP >= 16 ? 2 : 4);  // passes in flight (<= 32 rows of 16-byte loads per lane)
+};
+
+// weighted_first: x[ql][0..F) = sum_k w_k f_k[.]  for the queries of the warp tile
+template <int FT, int LDX>
+__device__ __forceinline__ void gather_weighted(const float* __restrict__ feat, int K, int WQ, const int* s_li,
+                                                const float* s_w, int lane, float* s_x) {
+  using M = RowMap<FT>;
+  const int sub = lane / M::LPR, c4 = lane % M::LPR;
+  const float4* __restrict__ f4 = reinterpret_cast<const float4*>(feat) + c4;
+#pragma unroll 1
+  for (int q0 = 0; q0 < WQ; q0 += M::U * M::RPP) {
+    float4 v[M::U][KREG];
 #pragma unroll
-  for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + g;
-    if (FT >= 32) {
-      float acc[M::NJ];
+    for (int u = 0; u < M::U; ++u) {
+      const int ql = q0 + u * M::RPP + sub;  // < WT: WQ <= WT and U*RPP divides WT
 #pragma unroll
-      for (int jj = 0; jj < M::NJ; ++jj) acc[jj] = 0.f;
+      for (int k = 0; k < KREG; ++k) {
+        v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          const int lif = s_li[k * WT + ql];
+          if (lif >= 0) v[u][k] = __ldg(f4 + (size_t)(lif & ~REMAP) * M::LPR);
+        }
+      }
+    }
 #pragma unroll
-      for (int r = 0; r < M::R; ++r) acc[r % M::NJ] = fmaf(w[g][r], v[g][r], acc[r % M::NJ]);
-      if (ql < qpt)
+    for (int u = 0; u < M::U; ++u) {
+      const int ql = q0 + u * M::RPP + sub;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int jj = 0; jj < M::NJ; ++jj) s_act[ql * LDX + 32 * jj + lane] = acc[jj];
-    } else {
-      float a = 0.f;
-#pragma unroll
-      for (int r = 0; r < M::R; ++r) a = fmaf(w[g][r], v[g][r], a);
-#pragma unroll
-      for (int off = FT; off < 32; off <<= 1) a += __shfl_xor_sync(FULL, a, off);
-      if (lane < FT && ql < qpt) s_act[ql * LDX + lane] = a;
+      for (int k = 0; k < KREG; ++k)
+        if (k < K) {
+          const float w = s_w[k * WT + ql];  // 0 for invalid neighbours
+          acc.x = fmaf(w, v[u][k].x, acc.x);
+          acc.y = fmaf(w, v[u][k].y, acc.y);
+          acc.z = fmaf(w, v[u][k].z, acc.z);
+          acc.w = fmaf(w, v[u][k].w, acc.w);
+        }
+      *reinterpret_cast<float4*>(s_x + ql * LDX + 4 * c4) = acc;
     }
   }
 }
 
-// decode-every-neighbour: act[j][ql*K + k] = f_k[j] (0 if invalid)
-template <int FT, int LDX, int GQ>
-__device__ __forceinline__ void gather_rows_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
-                                                  float* s_act, int ql0, int qpt, int sq0) {
-  using M = FeatMap<FT>;
-  float v[GQ][M::R];
+// decode-every-neighbour: x[ql*K + k][0..F) = f_k (0 if invalid) for the `qpt` queries of the row tile starting at sq0
+template <int FT, int LDX>
+__device__ __forceinline__ void gather_rows(const float* __restrict__ feat, int K, int used_rows, int sq0, const int* s_li,
+                                            int lane, float* s_x) {
+  using M = RowMap<FT>;
+  const int sub = lane / M::LPR, c4 = lane % M::LPR;
+#pragma unroll 1
+  for (int r0 = 0; r0 < WT; r0 += M::U * M::RPP) {
+    float4 v[M::U];
 #pragma unroll
-  for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + g;
-#pragma unroll
-    for (int r = 0; r < M::R; ++r) {
-      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
-      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
-      v[g][r] = 0.f;
-      if (k < K && ql < qpt) {
-        const int lk = s_idx[(sq0 + ql) * K + k];
-        const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * FT + col);
-        v[g][r] = lk < 0 ? 0.f : x;
+    for (int u = 0; u < M::U; ++u) {
+      const int row = r0 + u * M::RPP + sub;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < used_rows) {
+        const int ql = row / K, k = row - ql * K;
+        const int lif = s_li[k * WT + sq0 + ql];
+        if (lif >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(feat + (size_t)(lif & ~REMAP) * FT) + c4);
       }
     }
-  }
 #pragma unroll
-  for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + g;
-#pragma unroll
-    for (int r = 0; r < M::R; ++r) {
-      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
-      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
-      if (k < K && ql < qpt) s_act[(ql * K + k) * LDX + col] = v[g][r];
+    for (int u = 0; u < M::U; ++u) {
+      const int row = r0 + u * M::RPP + sub;
+      if (row < WT) *reinterpret_cast<float4*>(s_x + row * LDX + 4 * c4) = v[u];  // unused rows stay finite (zero)
     }
   }
 }
 
-// a_k = <g_xbar[0..F), f_k> for the queries ql0 + 4*g  ->  s_a[ql*K + k]
-template <int FT, int LDX, int GQ>
-__device__ __forceinline__ void feature_dots_group(const float* __restrict__ feat, int K, const int* s_idx, int lane,
-                                                   const float* s_act, float* s_a, int ql0, int qpt) {
-  using M = FeatMap<FT>;
-  float v[GQ][M::R];
+// Sum 8 per-lane values over groups of LPR consecutive lanes.  Halving exchange: every step a lane keeps half of its
+// values and adds the partner's partial of those (7 shuffles for LPR = 8 instead of 24).  On return v[0..n_out) are
+// group totals; `first` is the neighbour index k of v[0] (the lane's values are k = first .. first + n_out - 1).
+template <int LPR>
+__device__ __forceinline__ void group_reduce8(float (&v)[KREG], int lane, int& first, int& n_out) {
+  first = 0;
+  int n = KREG;
 #pragma unroll
-  for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + g;
+  for (int o = LPR / 2; o >= 1; o >>= 1) {
+    if (n > 1) {
+      const bool hi = (lane & o) != 0;
+      const int h = n / 2;
 #pragma unroll
-    for (int r = 0; r < M::R; ++r) {
-      const int k = FT >= 32 ? r / M::NJ : r * M::PER + lane / (FT >= 32 ? 1 : FT);
-      const int col = FT >= 32 ? 32 * (r % M::NJ) + lane : lane % (FT >= 32 ? 32 : FT);
-      v[g][r] = 0.f;
-      if (k < K && ql < qpt) {
-        const int lk = s_idx[ql * K + k];
-        const float x = __ldg(feat + (size_t)(lk < 0 ? 0 : lk) * FT + col);
-        v[g][r] = lk < 0 ? 0.f : x;
-      }
+      for (int i = 0; i < KREG / 2; ++i)
+        if (i < h) {
+          const float send = hi ? v[i] : v[i + h];
+          const float keep = hi ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(FULL, send, o);
+        }
+      if (hi) first += h;
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(FULL, v[0], o);
     }
   }
+  n_out = n;
+}
+
+// C1: a[k][ql] = <g_xbar[ql][0..F), f_k>
+template <int FT, int LDX>
+__device__ __forceinline__ void feature_dots(const float* __restrict__ feat, int K, int WQ, const int* s_li, int lane,
+                                             const float* s_x, float* s_a) {
+  using M = RowMap<FT>;
+  const int sub = lane / M::LPR, c4 = lane % M::LPR;
+  const float4* __restrict__ f4 = reinterpret_cast<const float4*>(feat) + c4;
+#pragma unroll 1
+  for (int q0 = 0; q0 < WQ; q0 += M::U * M::RPP) {
+    float4 v[M::U][KREG];
 #pragma unroll
-  for (int g = 0; g < GQ; ++g) {
-    const int ql = ql0 + g;
-    const int qs = ql < qpt ? ql : 0;
-    if (FT >= 32) {
-      float gx[M::NJ];
+    for (int u = 0; u < M::U; ++u) {
+      const int ql = q0 + u * M::RPP + sub;
 #pragma unroll
-      for (int jj = 0; jj < M::NJ; ++jj) gx[jj] = s_act[qs * LDX + 32 * jj + lane];
-      float part[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        part[k] = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < M::NJ; ++jj) part[k] = fmaf(gx[jj], v[g][k * M::NJ + jj], part[k]);
+      for (int k = 0; k < KREG; ++k) {
+        v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          const int lif = s_li[k * WT + ql];
+          if (lif >= 0) v[u][k] = __ldg(f4 + (size_t)(lif & ~REMAP) * M::LPR);
+        }
       }
-      const float tot = warp_reduce8(part, lane);
-      const int k = warp_reduce8_owner(lane);
-      if ((lane & 3) == 0 && k < K && ql < qpt) s_a[ql * K + k] = tot;
-    } else {
-      const float gxj = s_act[qs * LDX + (lane % (FT >= 32 ? 32 : FT))];
+    }
 #pragma unroll
-      for (int r = 0; r < M::R; ++r) {
-        float a = gxj * v[g][r];
+    for (int u = 0; u < M::U; ++u) {
+      const int ql = q0 + u * M::RPP + sub;
+      const float4 g4 = *reinterpret_cast<const float4*>(s_x + ql * LDX + 4 * c4);
+      float part[KREG];
 #pragma unroll
-        for (int off = 1; off < (FT >= 32 ? 1 : FT); off <<= 1) a += __shfl_xor_sync(FULL, a, off);
-        const int k = r * M::PER + lane / (FT >= 32 ? 1 : FT);
-        if ((lane % (FT >= 32 ? 32 : FT)) == 0 && k < K && ql < qpt) s_a[ql * K + k] = a;
-      }
+      for (int k = 0; k < KREG; ++k)
+        part[k] = fmaf(g4.w, v[u][k].w, fmaf(g4.z, v[u][k].z, fmaf(g4.y, v[u][k].y, g4.x * v[u][k].x)));
+      int first, n_out;
+      group_reduce8<M::LPR>(part, lane, first, n_out);
+      // after the exchange steps the lanes of a group hold disjoint k ranges; lanes that only took part in plain
+      // butterfly steps (LPR > 8) hold duplicates: the lowest lane of each duplicate set writes
+      const bool writer = M::LPR <= KREG ? true : (lane % (M::LPR / KREG)) == 0;
+      if (writer)
+#pragma unroll
+        for (int i = 0; i < KREG; ++i)
+          if (i < n_out && first + i < K) s_a[(first + i) * WT + ql] = part[i];
     }
   }
 }
@@ -207,58 +352,57 @@ __device__ __forceinline__ void feature_dots_group(const float* __restrict__ fea
 // ---------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------
-template <int H, int FT>
+template <int FT, bool WF>
 __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constant__ QueryParams p) {
-  static_assert(H == 64, "the tensor-core decoder is written for hidden_dim 64");
-  constexpr int KP0 = (FT + 3 + 7) / 8 * 8;        // decoder input width padded to the MMA k-step
-  constexpr int KT0 = KP0 / 8;                     // k-steps of layer 0 == n-tiles of the input gradient
-  constexpr int LDX = (KP0 > H ? KP0 : H) + 4;     // row-major tile leading dimension (== 4 or 12 mod 32)
-  constexpr int GQ = GqOf<FT>::value;
+  constexpr int H = 64;
+  constexpr int KP0 = (FT + 3 + 7) / 8 * 8;  // decoder input width padded to the MMA k-step
+  constexpr int KT0 = KP0 / 8;               // k-steps of layer 0 == n-tiles of the input gradient
+  constexpr int LDX = ld8mod32(KP0);         // row-major tile leading dimension (== 8 mod 32)
+  constexpr int F = FT, D = FT + 3;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const pinb200_map_view& m = p.map;
   const int K = p.opts.nn_k, L = p.dec.n_hidden;
-  constexpr int F = FT, D = FT + 3;
   const int OC = p.dec.out_dim;
-  const bool wf = p.opts.weighted_first != 0;
   const bool need_grad = p.opts.need_grad != 0;
   const bool leaky = p.dec.leaky_relu != 0;
   const float* __restrict__ feat = p.feat;
 
+  using WL = WarpLay<FT>;
+  static_assert(WL::LDX == LDX && (WL::mask % 2) == 0 && (WL::stride % 4) == 0, "per-warp layout");
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem + p.lay.delta);
-  float* wsm = smem + p.lay.warp0 + warp * p.lay.warp_stride;  // this warp's private tile state
-  float* s_act = wsm + p.lay.act;
-  int* s_idx = reinterpret_cast<int*>(wsm + p.lay.knn_idx);
-  int* s_gidx = reinterpret_cast<int*>(wsm + p.lay.knn_gidx);
-  float* s_d2 = wsm + p.lay.knn_d2;
-  float* s_w = wsm + p.lay.knn_w;
-  float* s_a = wsm + p.lay.knn_a;
-  float* s_q = wsm + p.lay.q;
-  float* s_out = wsm + p.lay.out;
-  float* s_dv = wsm + p.lay.dv;
-  int* s_nn = reinterpret_cast<int*>(wsm + p.lay.nn);
-  uint64_t* s_mask = reinterpret_cast<uint64_t*>(wsm + p.lay.mask);
+  float* wsm = smem + p.lay.warp0 + warp * WL::stride;  // this warp's private tile state
+  float* s_x = wsm + WL::x;
+  int* s_li = reinterpret_cast<int*>(wsm + WL::li);
+  float* s_w = wsm + WL::w;
+  float* s_dx = wsm + WL::dx;
+  float* s_dy = wsm + WL::dy;
+  float* s_dz = wsm + WL::dz;
+  float* s_a = wsm + WL::a;
+  float* s_q = wsm + WL::q;
+  float* s_usum = wsm + WL::usum;
+  float* s_out = wsm + WL::out;
+  float* s_dv = wsm + WL::dv;
+  int* s_nn = reinterpret_cast<int*>(wsm + WL::nn);
+  uint64_t* s_mask = reinterpret_cast<uint64_t*>(wsm + WL::mask);
 
-  stage_mma_decoder(p.dec, p.lay.dec, smem);
+  stage_chain_decoder(p.dec, p.lay.dec, smem);
   if (!p.use_saved_knn) fill_probe_deltas(m, s_delta);
   __syncthreads();
 
-  const int QPT = wf ? WT : WT / K;                   // queries per 32-row decoder tile
-  const int WQ = p.qpt;                               // queries per warp tile (<= WT; small launches use fewer so
-                                                      // that every resident warp gets work: latency, not issue, bound)
-  const int n_rt = wf ? 1 : (WQ + QPT - 1) / QPT;     // row tiles per warp tile
-  const int tid = lane;                               // row / query owned by this thread inside the warp tile
+  const int QPT = WF ? WT : WT / K;                // queries per 32-row decoder tile
+  const int WQ = p.qpt;                            // queries per warp tile (<= WT; small launches use fewer so
+                                                   // that every resident warp gets work: latency, not issue, bound)
+  const int n_rt = WF ? 1 : (WQ + QPT - 1) / QPT;  // row tiles per warp tile
   const int nwarp = blockDim.x >> 5;
+  const uint32_t B = (uint32_t)m.buffer_size;
   for (int st = blockIdx.x * nwarp + warp; st < p.n_tiles; st += gridDim.x * nwarp) {
     const long long q0s = (long long)st * WQ;
 
-    // ============ phase A1: thread per query -- search, IDW weights, side effects ============
+    // ============ phase A1: thread per query -- search, IDW weights, side effects, stash ============
     {
-      const long long qi = q0s + tid;
-      const bool live = tid < WQ && qi < p.n;
-      KnnRegs Lk;
-      knn_regs_init(Lk);
-      int cnt = 0;
+      const long long qi = q0s + lane;
+      const bool live = lane < WQ && qi < p.n;
       float qx = 0.f, qy = 0.f, qz = 0.f;
       if (live) {
         qx = __ldg(p.query_xyz + 3 * qi + 0);
@@ -273,80 +417,111 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
           qy = y;
           qz = z;
         }
-        if (p.use_saved_knn) {
+      }
+      // the K nearest: squared distance, position of the (global) point it was measured to, id | REMAP, global id
+      float d2[KREG], px[KREG], py[KREG], pz[KREG];
+      int lif[KREG], gid[KREG];
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < KREG; ++k) {
+        d2[k] = INVALID_D2;
+        px[k] = py[k] = pz[k] = 0.f;
+        lif[k] = gid[k] = -1;
+      }
+      if (p.use_saved_knn) {
+        if (live) {
+          cnt = __ldg(p.out.nn_count + qi);
 #pragma unroll
           for (int k = 0; k < KREG; ++k)
             if (k < K) {
-              Lk.idx[k] = __ldg(p.out.knn_idx + qi * K + k);
-              Lk.gidx[k] = __ldg(p.out.knn_gidx + qi * K + k);
-              Lk.d2[k] = __ldg(p.out.knn_dist2 + qi * K + k);
+              const int li = __ldg(p.out.knn_idx + qi * K + k);
+              if (li >= 0) {
+                gid[k] = __ldg(p.out.knn_gidx + qi * K + k);
+                d2[k] = __ldg(p.out.knn_dist2 + qi * K + k);
+                const float* pg = m.points + 3 * (size_t)gid[k];
+                const float* pl = m.nb_points + 3 * (size_t)li;
+                px[k] = __ldg(pg);
+                py[k] = __ldg(pg + 1);
+                pz[k] = __ldg(pg + 2);
+                const bool same = __ldg(pl) == px[k] && __ldg(pl + 1) == py[k] && __ldg(pl + 2) == pz[k];
+                lif[k] = same ? li : (li | REMAP);
+              }
             }
-          cnt = __ldg(p.out.nn_count + qi);
-        } else {
-          cnt = knn_search_thread(m, s_delta, qx, qy, qz, Lk, reinterpret_cast<int*>(s_act));
         }
+      } else {
+        const uint32_t r0 = base_slot(m, qx, qy, qz);
+        KnnTop T;
+        cnt = knn_search_lane(m, s_delta, live, r0, qx, qy, qz, T);
+        // re-read the winners (the probe loop kept only distance + record rank through the sorting networks)
+        const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(m.probe_rec);
+        float4 r[KREG];
+#pragma unroll
+        for (int k = 0; k < KREG; ++k) {
+          r[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+          if (k < K && T.p[k] >= 0) {
+            r[k] = __ldg(rec4 + T.p[k]);
+            if (p.out.knn_gidx) gid[k] = __ldg(m.probe_gid + T.p[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KREG; ++k)
+          if (k < K && T.p[k] >= 0) {
+            d2[k] = T.d[k];
+            px[k] = r[k].x;
+            py[k] = r[k].y;
+            pz[k] = r[k].z;
+            lif[k] = __float_as_int(r[k].w);
+          }
       }
-#ifdef PINB_K1_SMEM_SELECT
-      __syncwarp();  // the selection scratch lives in the (idle) activation tile: every lane is done reading it
-#endif
       // normalised inverse-distance weights, summed in neighbour order (model/neural_points.py:665-683)
       float u[KREG], w[KREG], usum = 0.f;
 #pragma unroll
       for (int k = 0; k < KREG; ++k) {
-        const bool v = k < K && Lk.idx[k] >= 0;
-        u[k] = k < K ? (cnt == 0 ? IDW_EPS : (v ? __fdiv_rn(1.0f, Lk.d2[k] + IDW_EPS) : 0.f)) : 0.f;
+        const bool v = k < K && lif[k] >= 0;
+        u[k] = k < K ? (cnt == 0 ? IDW_EPS : (v ? __frcp_rn(d2[k] + IDW_EPS) : 0.f)) : 0.f;
         usum += u[k];
       }
 #pragma unroll
-      for (int k = 0; k < KREG; ++k) w[k] = (k < K && Lk.idx[k] >= 0) ? __fdiv_rn(u[k], usum) : 0.f;
-#pragma unroll
-      for (int k = 0; k < KREG; ++k)
-        if (k < K) {
-          s_idx[tid * K + k] = Lk.idx[k];
-          s_gidx[tid * K + k] = Lk.gidx[k];
-          s_d2[tid * K + k] = Lk.d2[k];
-          s_w[tid * K + k] = w[k];
-        }
-      s_nn[tid] = cnt;
-      s_q[3 * tid + 0] = qx;
-      s_q[3 * tid + 1] = qy;
-      s_q[3 * tid + 2] = qz;
+      for (int k = 0; k < KREG; ++k) w[k] = (k < K && lif[k] >= 0) ? __fdiv_rn(u[k], usum) : 0.f;
       // neighbour vectors n_k = q - p_k (rotated into the point frame after PGO), certainty (:631-651)
       float sx = 0.f, sy = 0.f, sz = 0.f, qc = 0.f;
-      {
-        float px[KREG], py[KREG], pz[KREG], ce[KREG];
+      const bool want_cert = !p.is_color && (p.out.certainty != nullptr);
 #pragma unroll
-        for (int k = 0; k < KREG; ++k) {
-          px[k] = py[k] = pz[k] = ce[k] = 0.f;
-          if (k < K && Lk.idx[k] >= 0) {
-            const float* pp = m.nb_points + 3 * (size_t)Lk.idx[k];
-            px[k] = __ldg(pp);
-            py[k] = __ldg(pp + 1);
-            pz[k] = __ldg(pp + 2);
-            if (!p.is_color) ce[k] = m.certainty[Lk.idx[k]];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < KREG; ++k) {
-          if (k < K && Lk.idx[k] >= 0) {
-            float nx = __fsub_rn(qx, px[k]), ny = __fsub_rn(qy, py[k]), nz = __fsub_rn(qz, pz[k]);
-            if (m.after_pgo) {
-              const float* qq = m.nb_orient + 4 * (size_t)Lk.idx[k];
-              quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
-            }
+      for (int k = 0; k < KREG; ++k) {
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (k < K && lif[k] >= 0) {
+          dx = __fsub_rn(qx, px[k]);
+          dy = __fsub_rn(qy, py[k]);
+          dz = __fsub_rn(qz, pz[k]);
+          if (WF || want_cert) {
+            float nx, ny, nz;
+            float4 quat;
+            neighbour_vec(m, lif[k], dx, dy, dz, qx, qy, qz, nx, ny, nz, quat);
             sx = fmaf(w[k], nx, sx);
             sy = fmaf(w[k], ny, sy);
             sz = fmaf(w[k], nz, sz);
-            qc = fmaf(w[k], ce[k], qc);
+            if (want_cert) qc = fmaf(w[k], m.certainty[lif[k] & ~REMAP], qc);
           }
         }
+        if (k < K) {
+          s_li[k * WT + lane] = lif[k];
+          s_w[k * WT + lane] = w[k];
+          s_dx[k * WT + lane] = dx;
+          s_dy[k * WT + lane] = dy;
+          s_dz[k * WT + lane] = dz;
+        }
       }
-      if (wf) {  // the position part of the IDW-averaged decoder input (this thread's tile row) + zero padding
-        s_act[tid * LDX + F + 0] = sx;
-        s_act[tid * LDX + F + 1] = sy;
-        s_act[tid * LDX + F + 2] = sz;
+      s_nn[lane] = cnt;
+      s_usum[lane] = usum;
+      s_q[0 * WT + lane] = qx;
+      s_q[1 * WT + lane] = qy;
+      s_q[2 * WT + lane] = qz;
+      if (WF) {  // the position part of the IDW-averaged decoder input (this thread's tile row) + zero padding
+        s_x[lane * LDX + F + 0] = sx;
+        s_x[lane * LDX + F + 1] = sy;
+        s_x[lane * LDX + F + 2] = sz;
 #pragma unroll
-        for (int d = D; d < KP0; ++d) s_act[tid * LDX + d] = 0.f;
+        for (int d = D; d < KP0; ++d) s_x[lane * LDX + d] = 0.f;
       }
       if (live && !p.is_color) {
         if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
@@ -354,9 +529,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
           const int ts = (m.ts_update && p.query_ts) ? __ldg(p.query_ts + qi) : 0;
 #pragma unroll
           for (int k = 0; k < KREG; ++k)
-            if (k < K && Lk.idx[k] >= 0) {
-              atomicAdd(m.certainty + Lk.idx[k], w[k]);
-              if (m.ts_update && p.query_ts) atomicMax(m.ts_update + Lk.idx[k], ts);
+            if (k < K && lif[k] >= 0) {
+              atomicAdd(m.certainty + (lif[k] & ~REMAP), w[k]);
+              if (m.ts_update && p.query_ts) atomicMax(m.ts_update + (lif[k] & ~REMAP), ts);
             }
         }
         if (p.out.certainty) p.out.certainty[qi] = qc;
@@ -365,9 +540,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
 #pragma unroll
           for (int k = 0; k < KREG; ++k)
             if (k < K) {
-              if (p.out.knn_idx) p.out.knn_idx[qi * K + k] = Lk.idx[k];
-              if (p.out.knn_gidx) p.out.knn_gidx[qi * K + k] = Lk.gidx[k];
-              if (p.out.knn_dist2) p.out.knn_dist2[qi * K + k] = Lk.d2[k];
+              if (p.out.knn_idx) p.out.knn_idx[qi * K + k] = lif[k] < 0 ? -1 : (lif[k] & ~REMAP);
+              if (p.out.knn_gidx) p.out.knn_gidx[qi * K + k] = gid[k];
+              if (p.out.knn_dist2) p.out.knn_dist2[qi * K + k] = d2[k];
               if (p.out.knn_weight) p.out.knn_weight[qi * K + k] = w[k];
             }
         }
@@ -381,62 +556,61 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
     __syncwarp();
 
     for (int rt = 0; rt < n_rt; ++rt) {
-      const int sq0 = rt * QPT;                              // first query of this row tile inside the super tile
-      const int qpt = min(QPT, WQ - sq0);                  // queries in this row tile
-      const int used_rows = wf ? WT : qpt * K;
+      const int sq0 = rt * QPT;            // first query of this row tile inside the warp tile
+      const int qpt = min(QPT, WQ - sq0);  // queries in this row tile
+      const int used_rows = WF ? WT : qpt * K;
 
-      // ============ phase A2: warp per query -- coalesced feature gathers into the tile ============
-      if (wf) {
-        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_weighted_group<FT, LDX, GQ>(feat, K, s_idx, s_w, lane, s_act, ql0, qpt);
+      // ============ phase A2: F/4 lanes per row -- coalesced feature gathers into the tile ============
+      if (WF) {
+        gather_weighted<FT, LDX>(feat, K, WQ, s_li, s_w, lane, s_x);
       } else {
-        for (int ql0 = 0; ql0 < qpt; ql0 += GQ) gather_rows_group<FT, LDX, GQ>(feat, K, s_idx, lane, s_act, ql0, qpt, sq0);
+        gather_rows<FT, LDX>(feat, K, used_rows, sq0, s_li, lane, s_x);
         // neighbour vectors of the (query, k) rows: thread per row
-        if (tid < used_rows) {
-          const int ql = tid / K, k = tid - ql * K, sq = sq0 + ql;
-          const int lk = s_idx[sq * K + k];
-          float nx = 0.f, ny = 0.f, nz = 0.f;
-          if (lk >= 0) {
-            const float* pp = m.nb_points + 3 * (size_t)lk;
-            nx = __fsub_rn(s_q[3 * sq + 0], __ldg(pp));
-            ny = __fsub_rn(s_q[3 * sq + 1], __ldg(pp + 1));
-            nz = __fsub_rn(s_q[3 * sq + 2], __ldg(pp + 2));
-            if (m.after_pgo) {
-              const float* qq = m.nb_orient + 4 * (size_t)lk;
-              quat_rotate_passive(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), nx, ny, nz, nx, ny, nz);
-            }
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (lane < used_rows) {
+          const int ql = lane / K, k = lane - ql * K, sq = sq0 + ql;
+          const int lif = s_li[k * WT + sq];
+          if (lif >= 0) {
+            float4 quat;
+            neighbour_vec(m, lif, s_dx[k * WT + sq], s_dy[k * WT + sq], s_dz[k * WT + sq], s_q[sq], s_q[WT + sq],
+                          s_q[2 * WT + sq], nx, ny, nz, quat);
           }
-          s_act[tid * LDX + F + 0] = nx;
-          s_act[tid * LDX + F + 1] = ny;
-          s_act[tid * LDX + F + 2] = nz;
-#pragma unroll
-          for (int d = D; d < KP0; ++d) s_act[tid * LDX + d] = 0.f;
-        } else {
-          for (int d = 0; d < KP0; ++d) s_act[tid * LDX + d] = 0.f;  // unused rows stay finite
         }
+        s_x[lane * LDX + F + 0] = nx;
+        s_x[lane * LDX + F + 1] = ny;
+        s_x[lane * LDX + F + 2] = nz;
+#pragma unroll
+        for (int d = D; d < KP0; ++d) s_x[lane * LDX + d] = 0.f;
       }
       __syncwarp();
 
-      // ============ phase B: decoder on the tensor cores (warp-level 3xTF32 MMA) ============
+      // ============ phase B: decoder on the tensor cores (warp-level 3xTF32 MMA, register-chained) ============
       float acc[2][8][4];
-      warp_gemm_3xtf32<KT0, 8, false, LDX>(acc, s_act, smem + p.lay.dec.whi[0], smem + p.lay.dec.wlo[0], p.lay.dec.ldw[0], lane);
-      s_mask[lane] = bias_act_frags<8>(acc, smem + p.lay.dec.b[0], leaky, lane);
+      gemm_from_tile<KT0, LDX>(acc, s_x, smem + p.lay.dec.whi[0], smem + p.lay.dec.wlo[0], p.lay.dec.ldw[0], lane);
+      s_mask[lane] = bias_act_chain<8>(acc, smem + p.lay.dec.b[0], leaky, lane);
       for (int l = 1; l < L; ++l) {
-        __syncwarp();
-        store_frags<8, LDX>(s_act, acc, lane);
-        __syncwarp();
-        warp_gemm_3xtf32<8, 8, false, LDX>(acc, s_act, smem + p.lay.dec.whi[l], smem + p.lay.dec.wlo[l], p.lay.dec.ldw[l], lane);
-        s_mask[l * WT + lane] = bias_act_frags<8>(acc, smem + p.lay.dec.b[l], leaky, lane);
+        float nxt[2][8][4];
+        gemm_chain_fwd(nxt, acc, smem + p.lay.dec.whi[l], smem + p.lay.dec.wlo[l], p.lay.dec.ldw[l], lane);
+        s_mask[l * WT + lane] = bias_act_chain<8>(nxt, smem + p.lay.dec.b[l], leaky, lane);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = nxt[mt][nt][e];
       }
       // output head(s): dot with w_out over the 64 hidden units; 4 lanes share a row
       for (int c = 0; c < OC; ++c) {
         const float* wo = smem + p.lay.dec.wout + c * H;
         float part[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < 8; ++nt) {
+          const float2 w2 = *reinterpret_cast<const float2*>(wo + frag_col(nt, 0, lane));
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) part[mt][e >> 1] = fmaf(acc[mt][nt][e], wo[frag_col(nt, e, lane)], part[mt][e >> 1]);
+            for (int e = 0; e < 4; ++e) part[mt][e >> 1] = fmaf(acc[mt][nt][e], (e & 1) ? w2.y : w2.x, part[mt][e >> 1]);
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -455,7 +629,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
                 val = o * p.dec.out_scale;
                 dv = p.dec.out_scale;
               }
-              s_out[row * OC + c] = val;
+              s_out[row * 4 + c] = val;
               s_dv[row * 4 + c] = dv;
             }
           }
@@ -468,88 +642,75 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
         if (need_grad) {
           const float* wo = smem + p.lay.dec.wout + c * H;
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+          for (int nt = 0; nt < 8; ++nt) {
+            const float2 w2 = *reinterpret_cast<const float2*>(wo + frag_col(nt, 0, lane));
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[mt][nt][e] = wo[frag_col(nt, e, lane)];
-          mask_frags<8>(acc, s_mask[(L - 1) * WT + lane], leaky);
-          for (int l = L - 1; l >= 1; --l) {
-            __syncwarp();
-            store_frags<8, LDX>(s_act, acc, lane);
-            __syncwarp();
-            warp_gemm_3xtf32<8, 8, true, LDX>(acc, s_act, smem + p.lay.dec.whi[l], smem + p.lay.dec.wlo[l], p.lay.dec.ldw[l], lane);
-            mask_frags<8>(acc, s_mask[(l - 1) * WT + lane], leaky);
+              for (int e = 0; e < 4; ++e) acc[mt][nt][e] = (e & 1) ? w2.y : w2.x;
           }
-          __syncwarp();
-          store_frags<8, LDX>(s_act, acc, lane);
-          __syncwarp();
+          mask_chain<8>(acc, s_mask[(L - 1) * WT + lane], leaky);
+          for (int l = L - 1; l >= 1; --l) {
+            float nxt[2][8][4];
+            gemm_chain_bwd<8>(nxt, acc, smem + p.lay.dec.whi[l], smem + p.lay.dec.wlo[l], p.lay.dec.ldw[l], lane);
+            mask_chain<8>(nxt, s_mask[(l - 1) * WT + lane], leaky);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[mt][nt][e] = nxt[mt][nt][e];
+          }
           float gxa[2][KT0][4];
-          warp_gemm_3xtf32<8, KT0, true, LDX>(gxa, s_act, smem + p.lay.dec.whi[0], smem + p.lay.dec.wlo[0], p.lay.dec.ldw[0], lane);
+          gemm_chain_bwd<KT0>(gxa, acc, smem + p.lay.dec.whi[0], smem + p.lay.dec.wlo[0], p.lay.dec.ldw[0], lane);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < KT0; ++nt)
+            for (int hh = 0; hh < 2; ++hh) {
+              const float dv = s_dv[(mt * 16 + (lane >> 2) + 8 * hh) * 4 + c];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) gxa[mt][nt][e] *= s_dv[frag_row(mt, e, lane) * 4 + c];
+              for (int nt = 0; nt < KT0; ++nt) {
+                gxa[mt][nt][2 * hh] *= dv;
+                gxa[mt][nt][2 * hh + 1] *= dv;
+              }
+            }
           __syncwarp();
-          store_frags<KT0, LDX>(s_act, gxa, lane);
+          store_frags<KT0, LDX>(s_x, gxa, lane);
         }
         __syncwarp();
 
-        if (wf) {
-          // ---- C1: a_k = <g_xbar, f_k> (warp per query, coalesced re-read of the K feature rows)
+        if (WF) {
+          // ---- C1: a_k = <g_xbar, f_k> (F/4 lanes per row, coalesced re-read of the K feature rows)
           if (need_grad) {
-            for (int ql0 = 0; ql0 < qpt; ql0 += GQ) feature_dots_group<FT, LDX, GQ>(feat, K, s_idx, lane, s_act, s_a, ql0, qpt);
+            feature_dots<FT, LDX>(feat, K, WQ, s_li, lane, s_x, s_a);
             __syncwarp();
           }
           // ---- C2: thread per query -- chain rule through the IDW weights, outputs
-          const long long qi = q0s + tid;
-          if (tid < WQ && qi < p.n) {
-            const float val = s_out[tid * OC + c];
+          const long long qi = q0s + lane;
+          if (lane < WQ && qi < p.n) {
+            const float val = s_out[lane * 4 + c];
             float gq0 = 0.f, gq1 = 0.f, gq2 = 0.f;
             if (need_grad) {
-              const int nn = s_nn[tid];
-              const float qx = s_q[3 * tid], qy = s_q[3 * tid + 1], qz = s_q[3 * tid + 2];
-              const float gn0 = s_act[tid * LDX + F + 0], gn1 = s_act[tid * LDX + F + 1], gn2 = s_act[tid * LDX + F + 2];
+              const int nn = s_nn[lane];
+              const float usum = s_usum[lane];
+              const float qx = s_q[lane], qy = s_q[WT + lane], qz = s_q[2 * WT + lane];
+              const float gn0 = s_x[lane * LDX + F + 0], gn1 = s_x[lane * LDX + F + 1], gn2 = s_x[lane * LDX + F + 2];
               float ak[KREG], wk[KREG], ck[KREG], dx[KREG], dy[KREG], dz[KREG];
-              float abar = 0.f;
-              // issue every neighbour load first (local position, global position, quaternion), then compute
-              float lpx[KREG], lpy[KREG], lpz[KREG], gpx[KREG], gpy[KREG], gpz[KREG];
-              float4 qt[KREG];
-              int lks[KREG];
-#pragma unroll
-              for (int k = 0; k < KREG; ++k) {
-                lks[k] = k < K ? s_idx[tid * K + k] : -1;
-                const int lk0 = lks[k] < 0 ? 0 : lks[k];
-                const int gk0 = lks[k] < 0 ? 0 : s_gidx[tid * K + k];
-                const float* pp = m.nb_points + 3 * (size_t)lk0;
-                const float* pg = m.points + 3 * (size_t)gk0;
-                lpx[k] = __ldg(pp);
-                lpy[k] = __ldg(pp + 1);
-                lpz[k] = __ldg(pp + 2);
-                gpx[k] = __ldg(pg);
-                gpy[k] = __ldg(pg + 1);
-                gpz[k] = __ldg(pg + 2);
-                qt[k] = m.after_pgo ? __ldg(reinterpret_cast<const float4*>(m.nb_orient) + lk0) : make_float4(1.f, 0.f, 0.f, 0.f);
-              }
 #pragma unroll
               for (int k = 0; k < KREG; ++k) {
                 ak[k] = wk[k] = ck[k] = dx[k] = dy[k] = dz[k] = 0.f;
-                if (lks[k] >= 0) {
-                  const float ux = qx - lpx[k], uy = qy - lpy[k], uz = qz - lpz[k];
-                  dx[k] = qx - gpx[k];  // what dist2 was measured to
-                  dy[k] = qy - gpy[k];
-                  dz[k] = qz - gpz[k];
-                  float nx = ux, ny = uy, nz = uz, r0 = gn0, r1 = gn1, r2 = gn2;
-                  if (m.after_pgo) {
-                    quat_rotate_passive(qt[k].x, qt[k].y, qt[k].z, qt[k].w, ux, uy, uz, nx, ny, nz);
-                    quat_rotate_active(qt[k].x, qt[k].y, qt[k].z, qt[k].w, gn0, gn1, gn2, r0, r1, r2);
-                  }
-                  wk[k] = s_w[tid * K + k];
-                  ak[k] = s_a[tid * K + k] + gn0 * nx + gn1 * ny + gn2 * nz;
-                  abar = fmaf(wk[k], ak[k], abar);
-                  ck[k] = nn > 0 ? -2.f * __fdiv_rn(1.0f, s_d2[tid * K + k] + IDW_EPS) : 0.f;
+                const int lif = k < K ? s_li[k * WT + lane] : -1;
+                if (lif >= 0) {
+                  dx[k] = s_dx[k * WT + lane];  // q - the point dist2 was measured to
+                  dy[k] = s_dy[k * WT + lane];
+                  dz[k] = s_dz[k * WT + lane];
+                  float nx, ny, nz, r0 = gn0, r1 = gn1, r2 = gn2;
+                  float4 quat;
+                  neighbour_vec(m, lif, dx[k], dy[k], dz[k], qx, qy, qz, nx, ny, nz, quat);
+                  if (m.after_pgo) quat_rotate_active(quat.x, quat.y, quat.z, quat.w, gn0, gn1, gn2, r0, r1, r2);
+                  wk[k] = s_w[k * WT + lane];
+                  ak[k] = s_a[k * WT + lane] + gn0 * nx + gn1 * ny + gn2 * nz;
+                  ck[k] = nn > 0 ? -2.f * (wk[k] * usum) : 0.f;  // -2 u_k,  u_k = 1/(d2+eps) = w_k * sum_j u_j
                   gq0 = fmaf(wk[k], r0, gq0);
                   gq1 = fmaf(wk[k], r1, gq1);
                   gq2 = fmaf(wk[k], r2, gq2);
@@ -558,9 +719,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
               // d w_k / d q = w_k (c_k - sum_j w_j c_j),  c_k = -2 u_k (q - p_k).
               // sum_k w_k (a_k - abar) c_k is invariant to a common shift of the a_k; shifting by the nearest
               // neighbour's a_0 first keeps (a_k - abar) exact when neighbours coincide (cancellation-free)
+              float abar = 0.f;
               {
                 const float a0 = ak[0];
-                abar = 0.f;
 #pragma unroll
                 for (int k = 0; k < KREG; ++k) {
                   ak[k] = wk[k] != 0.f ? ak[k] - a0 : 0.f;
@@ -588,7 +749,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
                 if (need_grad) {
                   p.out.color[qi * OC + c] = val;
                 } else {
-                  for (int cc = 0; cc < OC; ++cc) p.out.color[qi * OC + cc] = s_out[tid * OC + cc];
+                  for (int cc = 0; cc < OC; ++cc) p.out.color[qi * OC + cc] = s_out[lane * 4 + cc];
                 }
               }
               if (need_grad && p.out.color_grad) {
@@ -600,43 +761,40 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
           }
         } else {
           // decode-every-neighbour: thread per query combines its K rows (tracker.py:317-323)
-          if (tid < qpt && q0s + sq0 + tid < p.n) {
-            const int ql = tid, sq = sq0 + ql;
+          if (lane < qpt && q0s + sq0 + lane < p.n) {
+            const int ql = lane, sq = sq0 + ql;
             const long long qi = q0s + sq;
             const int nn = s_nn[sq];
-            const float qx = s_q[3 * sq], qy = s_q[3 * sq + 1], qz = s_q[3 * sq + 2];
+            const float usum = s_usum[sq];
             const int n_ch = (need_grad || !p.is_color) ? 1 : OC;
             for (int ch = 0; ch < n_ch; ++ch) {
               const int cc = need_grad ? c : ch;
-              float mean = 0.f, wsum = 0.f, msh = 0.f;
-              const float s0 = s_out[(ql * K) * OC + cc];  // nearest neighbour's value: shift for exact differences
+              float mean = 0.f, msh = 0.f;
+              const float s0 = s_out[(ql * K) * 4 + cc];  // nearest neighbour's value: shift for exact differences
               for (int k = 0; k < K; ++k) {
-                const float wk = s_w[sq * K + k];
-                mean = fmaf(wk, s_out[(ql * K + k) * OC + cc], mean);
-                msh = fmaf(wk, s_out[(ql * K + k) * OC + cc] - s0, msh);
-                wsum += wk;
+                const float wk = s_w[k * WT + sq];
+                mean = fmaf(wk, s_out[(ql * K + k) * 4 + cc], mean);
+                msh = fmaf(wk, s_out[(ql * K + k) * 4 + cc] - s0, msh);
               }
               float var = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
               for (int k = 0; k < K; ++k) {
-                const int lk = s_idx[sq * K + k];
-                if (lk < 0) continue;
-                const float wk = s_w[sq * K + k];
-                const float dm = (s_out[(ql * K + k) * OC + cc] - s0) - msh;  // == s_k - mean, cancellation-free
+                const int lif = s_li[k * WT + sq];
+                if (lif < 0) continue;
+                const float wk = s_w[k * WT + sq];
+                const float dm = (s_out[(ql * K + k) * 4 + cc] - s0) - msh;  // == s_k - mean, cancellation-free
                 var = fmaf(wk * dm, dm, var);
                 if (need_grad) {
                   const int row = ql * K + k;
-                  float r0 = s_act[row * LDX + F + 0], r1 = s_act[row * LDX + F + 1], r2 = s_act[row * LDX + F + 2];
-                  const float* pg = m.points + 3 * (size_t)s_gidx[sq * K + k];  // the point dist2 was measured to
-                  const float dx = qx - __ldg(pg), dy = qy - __ldg(pg + 1), dz = qz - __ldg(pg + 2);
+                  float r0 = s_x[row * LDX + F + 0], r1 = s_x[row * LDX + F + 1], r2 = s_x[row * LDX + F + 2];
                   if (m.after_pgo) {
-                    const float* qq = m.nb_orient + 4 * (size_t)lk;
-                    quat_rotate_active(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3), r0, r1, r2, r0, r1, r2);
+                    const float4 qq = __ldg(reinterpret_cast<const float4*>(m.nb_orient) + (lif & ~REMAP));
+                    quat_rotate_active(qq.x, qq.y, qq.z, qq.w, r0, r1, r2, r0, r1, r2);
                   }
-                  const float uk = nn > 0 ? __fdiv_rn(1.0f, s_d2[sq * K + k] + IDW_EPS) : 0.f;
+                  const float uk = nn > 0 ? wk * usum : 0.f;
                   const float coef = wk * dm * (-2.f * uk);
-                  g0 += fmaf(coef, dx, wk * r0);
-                  g1 += fmaf(coef, dy, wk * r1);
-                  g2 += fmaf(coef, dz, wk * r2);
+                  g0 += fmaf(coef, s_dx[k * WT + sq], wk * r0);
+                  g1 += fmaf(coef, s_dy[k * WT + sq], wk * r1);
+                  g2 += fmaf(coef, s_dz[k * WT + sq], wk * r2);
                 }
               }
               if (!p.is_color) {
@@ -792,55 +950,31 @@ static int validate_map(const pinb200_map_view* m, bool need_feat) {
       set_error("map view: after_pgo needs nb_orient");
       return PINB200_ERR_BAD_ARG;
     }
+    if (m->n_nb >= PINB200_REC_REMAP) {
+      set_error("map view: n_nb %lld >= 2^30 (the id word of a probe record keeps bit 30 as a flag)", (long long)m->n_nb);
+      return PINB200_ERR_UNSUPPORTED;
+    }
   }
   return PINB200_OK;
 }
 
-static QueryLayout plan_layout(const QueryParams& p, int KP0) {
+template <int FT>
+static QueryLayout plan_layout(const QueryParams& p) {
   QueryLayout l{};
-  const int H = p.dec.hidden_dim, K = p.opts.nn_k;
   int o = 0;
   l.delta = o;
   o += align4(p.map.n_probe);
-  l.dec = plan_mma_decoder_smem(p.dec, KP0, o);
+  l.dec = plan_chain_decoder_smem(p.dec, WarpLay<FT>::KP0, o);
   l.warp0 = align4(l.dec.end);
-  // per-warp block
-  int w = 0;
-  const int ldx = (KP0 > H ? KP0 : H) + 4;
-  l.act = w;
-  w += align4(WT * ldx);
-  l.knn_idx = w;
-  w += WT * K;
-  l.knn_gidx = w;
-  w += WT * K;
-  l.knn_d2 = w;
-  w += WT * K;
-  l.knn_w = w;
-  w += WT * K;
-  l.knn_a = w;
-  w += WT * K;
-  l.q = w;
-  w += WT * 3;
-  l.out = w;
-  w += align4(WT * p.dec.out_dim);
-  l.dv = w;
-  w += WT * 4;
-  l.nn = w;
-  w += WT;
-  w = (w + 1) & ~1;  // 8-byte align the 64-bit masks
-  l.mask = w;
-  w += 2 * WT * p.dec.n_hidden;
-  l.warp_stride = align4(w);
-  int nw = (227 * 1024 / 4 - l.warp0) / l.warp_stride;
+  int nw = (227 * 1024 / 4 - l.warp0) / WarpLay<FT>::stride;
   l.n_warps = nw > WPB ? WPB : nw;
-  l.total = l.warp0 + l.n_warps * l.warp_stride;
+  l.total = l.warp0 + l.n_warps * WarpLay<FT>::stride;
   return l;
 }
 
-template <int H, int FT>
+template <int FT, bool WF>
 static int launch_query(QueryParams& p, cudaStream_t stream) {
-  constexpr int KP0 = (FT + 3 + 7) / 8 * 8;
-  p.lay = plan_layout(p, KP0);
+  p.lay = plan_layout<FT>(p);
   const size_t smem_bytes = (size_t)p.lay.total * sizeof(float);
   if (p.lay.n_warps < 1 || smem_bytes > 227 * 1024) {
     set_error("query kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
@@ -855,8 +989,9 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     const long long slots = (long long)sm_count() * nw;
     const long long per_warp = (p.n + slots - 1) / slots;
     int wq;
-    if (p.opts.weighted_first) {
-      wq = (int)std::min<long long>(WT, std::max<long long>(GQ_MAX, (per_warp + GQ_MAX - 1) / GQ_MAX * GQ_MAX));
+    if (WF) {
+      constexpr int G = RowMap<FT>::U * RowMap<FT>::RPP;  // queries per gather pass
+      wq = (int)std::min<long long>(WT, std::max<long long>(G, (per_warp + G - 1) / G * G));
     } else {
       const int qpt_rows = WT / p.opts.nn_k;
       wq = (int)std::min<long long>(WT, (per_warp + qpt_rows - 1) / qpt_rows * qpt_rows);
@@ -866,53 +1001,56 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     const long long per_sm = (p.n_tiles + sm_count() - 1) / sm_count();
     if (per_sm < nw) nw = (int)std::max<long long>(1, per_sm);
   }
-  auto kern = query_kernel<H, FT>;
-  // the attribute / occupancy calls cost a few microseconds each: remember the answer per (device, warps, smem)
+  auto kern = query_kernel<FT, WF>;
+  // the attribute / occupancy calls cost a few microseconds each: remember the answer per (device, kernel)
   struct Cached {
-    int dev, nw, occ;
-    size_t smem;
+    int dev;
+    const void* fn;
   };
   static std::mutex mu;
   static std::vector<Cached> cache;
-  int occ = 0, dev = 0;
+  int dev = 0;
   cudaGetDevice(&dev);
   {
     std::lock_guard<std::mutex> lk(mu);
+    bool known = false;
     for (const Cached& c : cache)
-      if (c.dev == dev && c.nw == nw && c.smem == smem_bytes) occ = c.occ;
-    if (occ == 0) {
+      if (c.dev == dev && c.fn == (const void*)kern) known = true;
+    if (!known) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return PINB200_ERR_CUDA;
       }
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem_bytes);
-      if (occ < 1) occ = 1;
-      cache.push_back({dev, nw, occ, smem_bytes});
+      cache.push_back({dev, (const void*)kern});
     }
   }
   const long long ctas_needed = (p.n_tiles + nw - 1) / nw;
-  const int grid = (int)std::min<long long>(ctas_needed, (long long)sm_count() * occ);
+  const int grid = (int)std::min<long long>(ctas_needed, (long long)sm_count());  // one CTA per SM (launch bounds)
   kern<<<grid, nw * 32, smem_bytes, stream>>>(p);
   return check_launch("query_kernel");
 }
 
+template <bool WF>
+static int dispatch_query_wf(QueryParams& p, cudaStream_t stream) {
+  switch (p.dec.in_dim - 3) {
+    case 4: return launch_query<4, WF>(p, stream);
+    case 8: return launch_query<8, WF>(p, stream);
+    case 16: return launch_query<16, WF>(p, stream);
+    case 32: return launch_query<32, WF>(p, stream);
+    case 64: return launch_query<64, WF>(p, stream);
+    default: break;
+  }
+  set_error("feature_dim %d unsupported (4, 8, 16, 32, 64)", p.dec.in_dim - 3);
+  return PINB200_ERR_UNSUPPORTED;
+}
+
 static int dispatch_query(QueryParams& p, cudaStream_t stream) {
-  const int D = p.dec.in_dim;
   if (p.dec.hidden_dim != 64) {
     set_error("decoder hidden_dim %d unsupported (64)", p.dec.hidden_dim);
     return PINB200_ERR_UNSUPPORTED;
   }
-  switch (D - 3) {
-    case 4: return launch_query<64, 4>(p, stream);
-    case 8: return launch_query<64, 8>(p, stream);
-    case 16: return launch_query<64, 16>(p, stream);
-    case 32: return launch_query<64, 32>(p, stream);
-    case 64: return launch_query<64, 64>(p, stream);
-    default: break;
-  }
-  set_error("feature_dim %d unsupported (4, 8, 16, 32, 64)", D - 3);
-  return PINB200_ERR_UNSUPPORTED;
+  return p.opts.weighted_first ? dispatch_query_wf<true>(p, stream) : dispatch_query_wf<false>(p, stream);
 }
 
 static int validate_decoder(const pinb200_decoder_view* d, int F) {
@@ -952,6 +1090,10 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   }
   rc = validate_decoder(sdf_dec, map->feature_dim);
   if (rc) return rc;
+  if (!map->probe_words || !map->probe_rec || !map->probe_gid) {
+    set_error("query_sdf: the map view has no probe index (pinb200_build_probe_index fills probe_words/rec/gid)");
+    return PINB200_ERR_BAD_ARG;
+  }
   const int K = opts->nn_k;
   if (K < 1 || K > KREG || K > map->n_probe) {
     set_error("nn_k %d out of range (1..%d, <= n_probe %d)", K, KREG, map->n_probe);

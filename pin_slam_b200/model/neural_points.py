@@ -62,21 +62,20 @@ def voxel_down_sample(points: torch.Tensor, voxel_size: float) -> torch.Tensor:
 
 
 def voxel_down_sample_min_value(points: torch.Tensor, voxel_size: float, value: torch.Tensor) -> torch.Tensor:
-    """Index of the point with the smallest `value` in each occupied voxel
-    (utils/tools.py voxel_down_sample_min_value_torch semantics)."""
+    """Index of the point with the smallest `value` in each occupied voxel, `value` quantised to 1000 levels of its
+    maximum and ties broken by the smaller index -- the selection rule of the reference helper
+    (utils/tools.py:629-668 voxel_down_sample_min_value_torch), result ordered by ascending voxel key."""
     origin = torch.floor(points.min(dim=0)[0] / voxel_size).long()
     g = torch.floor(points / voxel_size).long() - origin
     v = g.max()
     key = g[:, 0] + g[:, 1] * v + g[:, 2] * v * v
     uniq, inv = torch.unique(key, return_inverse=True)
     n = points.shape[0]
-    vmin = torch.full((uniq.shape[0],), float("inf"), dtype=value.dtype, device=points.device)
-    vmin.scatter_reduce_(0, inv, value, reduce="amin", include_self=True)
-    is_min = value == vmin[inv]
-    idx = torch.where(is_min, torch.arange(n, device=points.device), torch.full_like(inv, n))
-    best = torch.full((uniq.shape[0],), n, dtype=torch.int64, device=points.device)
-    best.scatter_reduce_(0, inv, idx, reduce="amin", include_self=True)
-    return best
+    q = (value / value.max() * 999).long()
+    packed = q * n + torch.arange(n, device=points.device)  # lexicographic (quantised value, index)
+    best = torch.full((uniq.shape[0],), torch.iinfo(torch.int64).max, dtype=torch.int64, device=points.device)
+    best.scatter_reduce_(0, inv, packed, reduce="amin", include_self=True)
+    return best % n
 
 
 class NeuralPoints(nn.Module):
@@ -134,6 +133,7 @@ class NeuralPoints(nn.Module):
         self.global2local = None
 
         self._handles = {}
+        self._rec_tables = {}  # index space (local / global) -> [buffer_size, 4] probe-record table, reused across frames
         self.set_search_neighborhood(num_nei_cells=config.num_nei_cells, search_alpha=config.search_alpha)
         self.cur_memory_mb = 0.0
         self.memory_footprint = []
@@ -149,8 +149,12 @@ class NeuralPoints(nn.Module):
         self._travel_dist = value
         self._handles = {}
 
-    def _invalidate(self):
+    def _invalidate(self, slots_freed: bool = False):
+        """Drop the cached kernel views.  `slots_freed`: hash slots may have been emptied (rehash / pruning), so the
+        probe-record tables must be cleared before they are rebuilt (ops.MapHandle.ensure_records)."""
         self._handles = {}
+        if slots_freed:
+            self._rec_tables = {}
 
     def is_empty(self):
         return self.neural_points.shape[0] == 0
@@ -343,6 +347,7 @@ class NeuralPoints(nn.Module):
             cur_ts=self.cur_ts,
             diff_travel_dist_local=self.diff_travel_dist_local,
             after_pgo=self.after_pgo,
+            rec_cache=(self._rec_tables, key),
         )
         self._handles[key] = h
         return h
@@ -373,6 +378,10 @@ class NeuralPoints(nn.Module):
             pipe = self.__dict__["_host_pipe"] = {"streams": [torch.cuda.Stream(self.device) for _ in range(2)],
                                                   "work": [{}, {}], "q": [None, None]}
         cur = torch.cuda.current_stream()
+        # build (and cache) the kernel views on the caller's stream BEFORE forking: the probe-record table of a fresh
+        # handle is written by a kernel, and the side streams only wait on `start`
+        self.map_handle(query_locally).ensure_records()
+        sdf_decoder.handle()
         start = torch.cuda.Event()
         start.record(cur)
         step = max(32, -(-n // max(1, chunks)))
@@ -486,7 +495,7 @@ class NeuralPoints(nn.Module):
         self.geo_features = self.geo_features[keep_pad]
         if self.color_features is not None:
             self.color_features = self.color_features[keep_pad]
-        self._invalidate()
+        self._invalidate(slots_freed=True)
         return True
 
     def adjust_map(self, pose_diff_torch):
@@ -532,7 +541,7 @@ class NeuralPoints(nn.Module):
             n = self.neural_points.shape[0]
             self.buffer_pt_index[self._slots(self.neural_points)] = torch.arange(n, dtype=torch.int32,
                                                                                 device=self.device)
-        self._invalidate()
+        self._invalidate(slots_freed=True)
         if sensor_position is not None:
             self.reset_local_map(sensor_position, sensor_orientation, cur_ts)
         if not kept_points:
@@ -551,14 +560,37 @@ class NeuralPoints(nn.Module):
         self._local_idx = None
         self.global2local = None
         self._handles = {}
+        self._rec_tables = {}
         if clean_more:
             self.point_ts_create = None
             self.point_ts_update = None
             self.point_certainties = None
 
+    def __setstate__(self, state):
+        """Also accepts the state of a map pickled by the UPSTREAM class (utils/tools.py:300-309 pickles the whole
+        module after clear_temp()): its plain `travel_dist` attribute becomes `_travel_dist` (a property here), the
+        int64 index tensors become int32, and the fields this class adds get their defaults."""
+        super().__setstate__(state)
+        d = self.__dict__
+        if "travel_dist" in d:
+            d["_travel_dist"] = d.pop("travel_dist")
+        d.setdefault("_travel_dist", None)
+        d["_handles"] = {}
+        d["_rec_tables"] = {}
+        d.setdefault("_local_idx", None)
+        d.setdefault("idx_dtype", torch.int32)
+        d.setdefault("color_on", d.get("color_features") is not None)
+        for name in ("buffer_pt_index", "global2local"):
+            t = d.get(name)
+            if torch.is_tensor(t) and t.dtype != torch.int32:
+                d[name] = t.to(torch.int32)
+        if "_probe_dx32" not in d and torch.is_tensor(d.get("neighbor_dx")):
+            d["_probe_dx32"] = d["neighbor_dx"].to(torch.int32).contiguous()
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_handles"] = {}  # raw device pointers never travel
+        state["_rec_tables"] = {}  # derived data (800 MB per index space at the default buffer_size)
         state.pop("_host_pipe", None)  # CUDA streams / staging buffers of query_sdf_host
         return state
 

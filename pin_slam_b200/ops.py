@@ -41,7 +41,7 @@ class MapHandle:
 
     def __init__(self, *, slot_table, buffer_size, points, ts_create, travel_dist, global2local, nb_points,
                  nb_orient, geo_feat, color_feat, certainty, ts_update, probe_dx, resolution, max_valid_dist2,
-                 time_filter, cur_ts, diff_travel_dist_local, after_pgo):
+                 time_filter, cur_ts, diff_travel_dist_local, after_pgo, rec_cache=None):
         self.keep = dict(slot_table=slot_table, points=points, ts_create=ts_create, travel_dist=travel_dist,
                          global2local=global2local, nb_points=nb_points, nb_orient=nb_orient, geo_feat=geo_feat,
                          color_feat=color_feat, certainty=certainty, ts_update=ts_update, probe_dx=probe_dx)
@@ -72,20 +72,45 @@ class MapHandle:
         v.after_pgo = int(bool(after_pgo))
         if time_filter and (travel_dist is None or cur_ts >= travel_dist.shape[0]):
             raise RuntimeError("time filter needs travel_dist[cur_ts]")
-        # packed 32-byte search records {x, y, z, travel(ts_create), id bits, 0, 0, 0}: one launch
-        n_g = points.shape[0]
-        rec = torch.empty((n_g, 8), dtype=torch.float32, device=points.device)
-        if n_g > 0:
-            rc = _lib.load().pinb200_build_search_records(
-                _ptr(points, torch.float32), _ptr(ts_create, torch.int32),
-                _ptr(travel_dist, torch.float32) if time_filter else None, _ptr(global2local, torch.int32), n_g,
-                _ptr(rec), _stream())
-            _lib.check(rc, "pinb200_build_search_records")
-            _count()
-        self.keep["search_rec"] = rec
-        v.search_rec = _ptr(rec, torch.float32)
+        v.probe_words = None
+        v.probe_rec = None
+        v.probe_gid = None
+        # probe index (built lazily by ensure_records); `rec_cache` = (dict, key) of the map owner, where the
+        # 12.5 MB word array is kept across handles so that it is not re-allocated every frame
+        self._rec_cache = rec_cache
+        self._probe = None
         self.view = v
         self.device = points.device
+
+    def ensure_records(self):
+        """Build the probe index of this view (pinb200_map_view.probe_*) once per handle: K1 needs it."""
+        if self._probe is not None:
+            return self
+        lib = _lib.load()
+        pts = self.keep["points"]
+        dev = pts.device
+        bsz = self.view.buffer_size
+        n_words = int(lib.pinb200_probe_index_words(bsz))
+        n_scr = int(lib.pinb200_probe_index_scratch(bsz))
+        cached = None if self._rec_cache is None else self._rec_cache[0].get(self._rec_cache[1])
+        if cached is not None and cached[0].shape[0] == n_words and cached[0].device == dev:
+            words, scratch = cached
+        else:
+            words = torch.empty((n_words, 2), dtype=torch.int32, device=dev)
+            scratch = torch.empty((n_scr,), dtype=torch.int32, device=dev)
+            if self._rec_cache is not None:
+                self._rec_cache[0][self._rec_cache[1]] = (words, scratch)
+        n_g = max(1, pts.shape[0])
+        rec = torch.empty((n_g, 4), dtype=torch.float32, device=dev)
+        gid = torch.empty((n_g,), dtype=torch.int32, device=dev)
+        _lib.check(lib.pinb200_build_probe_index(C.byref(self.view), _ptr(words), _ptr(rec), _ptr(gid), _ptr(scratch),
+                                                 _stream()), "pinb200_build_probe_index")
+        _count(5)
+        self._probe = (words, rec, gid, scratch)
+        self.view.probe_words = _ptr(words)
+        self.view.probe_rec = _ptr(rec)
+        self.view.probe_gid = _ptr(gid)
+        return self
 
     @property
     def n_nb(self):
@@ -166,6 +191,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
               training_rows: int = 0, out: Optional[dict] = None):
     """K1.  Returns a dict of freshly allocated (or caller-provided `out`) CUDA tensors."""
     lib = _lib.load()
+    mh.ensure_records()
     o, qo, opts = _query_args(xyz, nn_k, weighted_first, training_mode, need_grad, color_dec, color_grad, transform,
                               save_knn, want_xyz, training_rows, out)
     rc = lib.pinb200_query_sdf(C.byref(mh.view), C.byref(dec.view),
@@ -184,6 +210,7 @@ def track_iterations(mh: MapHandle, dec: DecoderHandle, src: torch.Tensor, t_dev
     """`n_iter` x (K1 with the device pose `t_dev` + K4 updating it in place) from ONE host call.
     Returns the K1 output dict of the last iteration; `result`/`sums` hold the last K4 outputs."""
     lib = _lib.load()
+    mh.ensure_records()
     o, qo, opts = _query_args(src, nn_k, weighted_first, False, True, color_dec, color_grad, t_dev, False, True, 0, out)
     g = GnOpts(_ptr(sdf_label, torch.float32), _ptr(normals, torch.float32),
                _ptr(color_obs, torch.float32) if color_mode else None,
@@ -353,6 +380,7 @@ def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weig
     """The geometry-only training loop of Mapper.mapping in ONE host call (pinb200_map_iterations).
     `index` [n_iter, bs] int64 are the pre-drawn batch indices; scratch buffers live in `work`."""
     lib = _lib.load()
+    mh.ensure_records()
     bs = index.shape[1]
     dev = index.device
     ne = (bs + decimation - 1) // decimation if decimation > 0 else 0

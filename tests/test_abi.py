@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/pinb200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.pinb200_version() == 100
+    assert lib.pinb200_version() == 200
 
 
 @pytest.mark.parametrize("cname,pyname", [("pinb200_map_view", "MapView"), ("pinb200_decoder_view", "DecoderView"),
