@@ -116,7 +116,15 @@ typedef struct pinb200_query_opts {
                                gradient rows of a training batch follow the samples and are inference-mode
                                (mapper.py:941) */
   const double* transform;  /* optional device ptr, 4x4 row-major fp64: q = T*p evaluated in fp32 (tools.py:534-553) */
+  void* workspace;          /* optional device scratch of >= pinb200_query_workspace_bytes(N) bytes.  With it, batches
+                               of >= PINB200_SPLIT_MIN_QUERIES queries run as two launches (neighbour search at high
+                               occupancy, then gather + decoder); without it, or for small batches, one fused launch.
+                               Results are identical either way. */
+  int64_t workspace_bytes;
 } pinb200_query_opts;
+
+#define PINB200_SPLIT_MIN_QUERIES 32768
+int64_t pinb200_query_workspace_bytes(int64_t n_queries);
 
 /* Outputs of the fused query; any pointer may be NULL to skip that output. */
 typedef struct pinb200_query_out {

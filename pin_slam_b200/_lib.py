@@ -38,7 +38,8 @@ class DecoderView(C.Structure):
 
 class QueryOpts(C.Structure):
     _fields_ = [("nn_k", C.c_int32), ("weighted_first", C.c_int32), ("training_mode", C.c_int32),
-                ("need_grad", C.c_int32), ("training_rows", C.c_int64), ("transform", c_f64p)]
+                ("need_grad", C.c_int32), ("training_rows", C.c_int64), ("transform", c_f64p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 class QueryOut(C.Structure):
@@ -73,6 +74,7 @@ SIGNATURES = {
     "pinb200_last_error": (C.c_char_p, []),
     "pinb200_query_sdf": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,
                                     c_i32p, C.c_int64, C.POINTER(QueryOpts), C.POINTER(QueryOut), C.c_void_p]),
+    "pinb200_query_workspace_bytes": (C.c_int64, [C.c_int64]),
     "pinb200_knn_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, C.c_int32, c_i32p, c_i32p, c_f32p, c_f32p,
                                      c_i32p, C.c_void_p]),
     "pinb200_radius_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, c_f32p, c_i32p, C.c_void_p]),

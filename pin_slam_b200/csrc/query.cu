@@ -44,18 +44,11 @@ struct WarpLay {
   static constexpr int KP0 = (FT + 3 + 7) / 8 * 8;
   static constexpr int LDX = KP0 <= 8 ? 8 : ((KP0 - 8 + 31) / 32) * 32 + 8;
   static constexpr int x = 0;                      // [32][LDX] decoder input rows / input gradient
-  static constexpr int li = x + WT * LDX;          // [K][32] neighbour id | REMAP (-1 invalid)
-  static constexpr int w = li + WT * 8;            // [K][32] IDW weight
-  static constexpr int dx = w + WT * 8;            // [K][32] q - p_k (the point dist2 was measured to)
-  static constexpr int dy = dx + WT * 8;
-  static constexpr int dz = dy + WT * 8;
-  static constexpr int a = dz + WT * 8;            // [K][32] <g_xbar, f_k>
-  static constexpr int q = a + WT * 8;             // [3][32] query
-  static constexpr int usum = q + WT * 3;          // [32] sum of the unnormalised weights
-  static constexpr int out = usum + WT;            // [32][<=4] decoder outputs
+  static constexpr int stash = x + WT * LDX;       // Stash block (see a1_tile)
+  static constexpr int a = stash + 1536;           // [K][32] <g_xbar, f_k>
+  static constexpr int out = a + WT * 8;           // [32][<=4] decoder outputs
   static constexpr int dv = out + WT * 4;          // [32][4] d out / d pre-activation
-  static constexpr int nn = dv + WT * 4;           // [32] nn_count
-  static constexpr int mask = nn + WT;             // [<=4 layers][32] 64-bit ReLU masks
+  static constexpr int mask = dv + WT * 4;         // [<=4 layers][32] 64-bit ReLU masks
   static constexpr int stride = mask + 2 * WT * PINB200_MAX_HIDDEN_LAYERS;
 };
 
@@ -72,6 +65,7 @@ struct QueryParams {
   int is_color;       // outputs go to out.color / out.color_grad instead of sdf / grad
   int n_tiles;
   int qpt;  // queries per warp tile
+  float* stash;  // split pipeline: [n_tiles][Stash::floats] workspace written by search_kernel, read by the decode launch
   QueryLayout lay;
 };
 
@@ -350,9 +344,206 @@ __device__ __forceinline__ void feature_dots(const float* __restrict__ feat, int
 }
 
 // ---------------------------------------------------------------------------
+// Phase A1 of one 32-query tile: search, IDW weights, certainty, training-mode scatters, kNN outputs, and the "stash"
+// every later phase works from.  The stash is one block of STASH_FLOATS floats in [field][k][lane] order (conflict
+// free columns in shared memory, fully coalesced rows in global memory): the fused kernel keeps it in the warp's
+// shared memory, the split pipeline (search_kernel -> decode) writes it to the workspace.
+// ---------------------------------------------------------------------------
+struct Stash {
+  static constexpr int li = 0;              // [K][32] neighbour id | REMAP (-1 invalid)
+  static constexpr int w = li + WT * 8;     // [K][32] IDW weight
+  static constexpr int dx = w + WT * 8;     // [K][32] q - p_k (the point dist2 was measured to)
+  static constexpr int dy = dx + WT * 8;
+  static constexpr int dz = dy + WT * 8;
+  static constexpr int q = dz + WT * 8;     // [3][32] query
+  static constexpr int usum = q + WT * 3;   // [32] sum of the unnormalised weights
+  static constexpr int nn = usum + WT;      // [32] nn_count
+  static constexpr int pos = nn + WT;       // [3][32] sum_k w_k n_k
+  static constexpr int floats = pos + WT * 3;
+};
+static_assert(Stash::floats % 4 == 0, "stash block is copied with 16-byte accesses");
+
+__device__ __forceinline__ void a1_tile(const QueryParams& p, const uint32_t* s_delta, long long q0s, int WQ, int lane,
+                                        float* stash) {
+  const pinb200_map_view& m = p.map;
+  const int K = p.opts.nn_k;
+  int* s_li = reinterpret_cast<int*>(stash + Stash::li);
+  float* s_w = stash + Stash::w;
+  float* s_dx = stash + Stash::dx;
+  float* s_dy = stash + Stash::dy;
+  float* s_dz = stash + Stash::dz;
+  float* s_q = stash + Stash::q;
+  float* s_usum = stash + Stash::usum;
+  int* s_nn = reinterpret_cast<int*>(stash + Stash::nn);
+  float* s_pos = stash + Stash::pos;
+  const long long qi = q0s + lane;
+  const bool live = lane < WQ && qi < p.n;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) {
+    qx = __ldg(p.query_xyz + 3 * qi + 0);
+    qy = __ldg(p.query_xyz + 3 * qi + 1);
+    qz = __ldg(p.query_xyz + 3 * qi + 2);
+    if (p.opts.transform) {  // q = T p in fp32 (utils/tools.py:534-553)
+      const double* T = p.opts.transform;
+      const float x = fmaf(qz, (float)T[2], fmaf(qy, (float)T[1], qx * (float)T[0])) + (float)T[3];
+      const float y = fmaf(qz, (float)T[6], fmaf(qy, (float)T[5], qx * (float)T[4])) + (float)T[7];
+      const float z = fmaf(qz, (float)T[10], fmaf(qy, (float)T[9], qx * (float)T[8])) + (float)T[11];
+      qx = x;
+      qy = y;
+      qz = z;
+    }
+  }
+  // the K nearest: squared distance, position of the (global) point it was measured to, id | REMAP, global id
+  float d2[KREG], px[KREG], py[KREG], pz[KREG];
+  int lif[KREG], gid[KREG];
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) {
+    d2[k] = INVALID_D2;
+    px[k] = py[k] = pz[k] = 0.f;
+    lif[k] = gid[k] = -1;
+  }
+  if (p.use_saved_knn) {
+    if (live) {
+      cnt = __ldg(p.out.nn_count + qi);
+#pragma unroll
+      for (int k = 0; k < KREG; ++k)
+        if (k < K) {
+          const int li = __ldg(p.out.knn_idx + qi * K + k);
+          if (li >= 0) {
+            gid[k] = __ldg(p.out.knn_gidx + qi * K + k);
+            d2[k] = __ldg(p.out.knn_dist2 + qi * K + k);
+            const float* pg = m.points + 3 * (size_t)gid[k];
+            const float* pl = m.nb_points + 3 * (size_t)li;
+            px[k] = __ldg(pg);
+            py[k] = __ldg(pg + 1);
+            pz[k] = __ldg(pg + 2);
+            const bool same = __ldg(pl) == px[k] && __ldg(pl + 1) == py[k] && __ldg(pl + 2) == pz[k];
+            lif[k] = same ? li : (li | REMAP);
+          }
+        }
+    }
+  } else {
+    const uint32_t r0 = base_slot(m, qx, qy, qz);
+    KnnTop T;
+    cnt = knn_search_lane(m, s_delta, live, r0, qx, qy, qz, T);
+    // re-read the winners (the probe loop kept only distance + record rank through the sorting networks)
+    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(m.probe_rec);
+    float4 r[KREG];
+#pragma unroll
+    for (int k = 0; k < KREG; ++k) {
+      r[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (k < K && T.p[k] >= 0) {
+        r[k] = __ldg(rec4 + T.p[k]);
+        if (p.out.knn_gidx) gid[k] = __ldg(m.probe_gid + T.p[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KREG; ++k)
+      if (k < K && T.p[k] >= 0) {
+        d2[k] = T.d[k];
+        px[k] = r[k].x;
+        py[k] = r[k].y;
+        pz[k] = r[k].z;
+        lif[k] = __float_as_int(r[k].w);
+      }
+  }
+  // normalised inverse-distance weights, summed in neighbour order (model/neural_points.py:665-683)
+  float u[KREG], w[KREG], usum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) {
+    const bool v = k < K && lif[k] >= 0;
+    u[k] = k < K ? (cnt == 0 ? IDW_EPS : (v ? __frcp_rn(d2[k] + IDW_EPS) : 0.f)) : 0.f;
+    usum += u[k];
+  }
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) w[k] = (k < K && lif[k] >= 0) ? __fdiv_rn(u[k], usum) : 0.f;
+  // neighbour vectors n_k = q - p_k (rotated into the point frame after PGO), certainty (:631-651)
+  float sx = 0.f, sy = 0.f, sz = 0.f, qc = 0.f;
+  const bool want_cert = !p.is_color && (p.out.certainty != nullptr);
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) {
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (k < K && lif[k] >= 0) {
+      dx = __fsub_rn(qx, px[k]);
+      dy = __fsub_rn(qy, py[k]);
+      dz = __fsub_rn(qz, pz[k]);
+      {
+        float nx, ny, nz;
+        float4 quat;
+        neighbour_vec(m, lif[k], dx, dy, dz, qx, qy, qz, nx, ny, nz, quat);
+        sx = fmaf(w[k], nx, sx);
+        sy = fmaf(w[k], ny, sy);
+        sz = fmaf(w[k], nz, sz);
+        if (want_cert) qc = fmaf(w[k], m.certainty[lif[k] & ~REMAP], qc);
+      }
+    }
+    if (k < K) {
+      s_li[k * WT + lane] = lif[k];
+      s_w[k * WT + lane] = w[k];
+      s_dx[k * WT + lane] = dx;
+      s_dy[k * WT + lane] = dy;
+      s_dz[k * WT + lane] = dz;
+    }
+  }
+  s_nn[lane] = cnt;
+  s_usum[lane] = usum;
+  s_q[0 * WT + lane] = qx;
+  s_q[1 * WT + lane] = qy;
+  s_q[2 * WT + lane] = qz;
+  s_pos[0 * WT + lane] = sx;  // position part of the IDW-averaged decoder input (weighted_first)
+  s_pos[1 * WT + lane] = sy;
+  s_pos[2 * WT + lane] = sz;
+  if (live && !p.is_color) {
+    if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
+      // certainty scatter_add / ts amax (:685-710); invalid entries add 0 / max with 0 in the reference
+      const int ts = (m.ts_update && p.query_ts) ? __ldg(p.query_ts + qi) : 0;
+#pragma unroll
+      for (int k = 0; k < KREG; ++k)
+        if (k < K && lif[k] >= 0) {
+          atomicAdd(m.certainty + (lif[k] & ~REMAP), w[k]);
+          if (m.ts_update && p.query_ts) atomicMax(m.ts_update + (lif[k] & ~REMAP), ts);
+        }
+    }
+    if (p.out.certainty) p.out.certainty[qi] = qc;
+    if (!p.use_saved_knn) {
+      if (p.out.nn_count) p.out.nn_count[qi] = cnt;
+#pragma unroll
+      for (int k = 0; k < KREG; ++k)
+        if (k < K) {
+          if (p.out.knn_idx) p.out.knn_idx[qi * K + k] = lif[k] < 0 ? -1 : (lif[k] & ~REMAP);
+          if (p.out.knn_gidx) p.out.knn_gidx[qi * K + k] = gid[k];
+          if (p.out.knn_dist2) p.out.knn_dist2[qi * K + k] = d2[k];
+          if (p.out.knn_weight) p.out.knn_weight[qi * K + k] = w[k];
+        }
+    }
+    if (p.out.xyz) {
+      p.out.xyz[3 * qi + 0] = qx;
+      p.out.xyz[3 * qi + 1] = qy;
+      p.out.xyz[3 * qi + 2] = qz;
+    }
+  }
+}
+
+// K1a of the split pipeline: phase A1 alone, at high occupancy (no decoder weights in shared memory, <= 128
+// registers): the probe rounds of ~16 resident warps per SM keep the load/store unit busy, which the fused kernel's
+// 12 warps (most of them in compute phases at any time) cannot.  One warp = one 32-query tile.
+__global__ void __launch_bounds__(128, 4) search_kernel(const __grid_constant__ QueryParams p) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem);
+  fill_probe_deltas(p.map, s_delta);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int st = blockIdx.x * nwarp + warp; st < p.n_tiles; st += gridDim.x * nwarp)
+    a1_tile(p, s_delta, (long long)st * WT, WT, lane, p.stash + (size_t)st * Stash::floats);
+}
+
+// ---------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------
-template <int FT, bool WF>
+// SPLIT = false: fused (phase A1 runs here);  true: decode-only launch of the split pipeline (the stash of every tile
+// was written by search_kernel)
+template <int FT, bool WF, bool SPLIT>
 __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constant__ QueryParams p) {
   constexpr int H = 64;
   constexpr int KP0 = (FT + 3 + 7) / 8 * 8;  // decoder input width padded to the MMA k-step
@@ -369,25 +560,26 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
   const float* __restrict__ feat = p.feat;
 
   using WL = WarpLay<FT>;
-  static_assert(WL::LDX == LDX && (WL::mask % 2) == 0 && (WL::stride % 4) == 0, "per-warp layout");
+  static_assert(WL::LDX == LDX && (WL::mask % 2) == 0 && (WL::stride % 4) == 0 && (WL::stash % 4) == 0 && Stash::floats == 1536, "per-warp layout");
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem + p.lay.delta);
   float* wsm = smem + p.lay.warp0 + warp * WL::stride;  // this warp's private tile state
   float* s_x = wsm + WL::x;
-  int* s_li = reinterpret_cast<int*>(wsm + WL::li);
-  float* s_w = wsm + WL::w;
-  float* s_dx = wsm + WL::dx;
-  float* s_dy = wsm + WL::dy;
-  float* s_dz = wsm + WL::dz;
+  int* s_li = reinterpret_cast<int*>(wsm + WL::stash + Stash::li);
+  float* s_w = wsm + WL::stash + Stash::w;
+  float* s_dx = wsm + WL::stash + Stash::dx;
+  float* s_dy = wsm + WL::stash + Stash::dy;
+  float* s_dz = wsm + WL::stash + Stash::dz;
+  float* s_q = wsm + WL::stash + Stash::q;
+  float* s_usum = wsm + WL::stash + Stash::usum;
+  int* s_nn = reinterpret_cast<int*>(wsm + WL::stash + Stash::nn);
+  float* s_pos = wsm + WL::stash + Stash::pos;
   float* s_a = wsm + WL::a;
-  float* s_q = wsm + WL::q;
-  float* s_usum = wsm + WL::usum;
   float* s_out = wsm + WL::out;
   float* s_dv = wsm + WL::dv;
-  int* s_nn = reinterpret_cast<int*>(wsm + WL::nn);
   uint64_t* s_mask = reinterpret_cast<uint64_t*>(wsm + WL::mask);
 
   stage_chain_decoder(p.dec, p.lay.dec, smem);
-  if (!p.use_saved_knn) fill_probe_deltas(m, s_delta);
+  if (!SPLIT && !p.use_saved_knn) fill_probe_deltas(m, s_delta);
   __syncthreads();
 
   const int QPT = WF ? WT : WT / K;                // queries per 32-row decoder tile
@@ -395,163 +587,28 @@ __global__ void __launch_bounds__(WPB * 32, 1) query_kernel(const __grid_constan
                                                    // that every resident warp gets work: latency, not issue, bound)
   const int n_rt = WF ? 1 : (WQ + QPT - 1) / QPT;  // row tiles per warp tile
   const int nwarp = blockDim.x >> 5;
-  const uint32_t B = (uint32_t)m.buffer_size;
   for (int st = blockIdx.x * nwarp + warp; st < p.n_tiles; st += gridDim.x * nwarp) {
     const long long q0s = (long long)st * WQ;
 
     // ============ phase A1: thread per query -- search, IDW weights, side effects, stash ============
-    {
-      const long long qi = q0s + lane;
-      const bool live = lane < WQ && qi < p.n;
-      float qx = 0.f, qy = 0.f, qz = 0.f;
-      if (live) {
-        qx = __ldg(p.query_xyz + 3 * qi + 0);
-        qy = __ldg(p.query_xyz + 3 * qi + 1);
-        qz = __ldg(p.query_xyz + 3 * qi + 2);
-        if (p.opts.transform) {  // q = T p in fp32 (utils/tools.py:534-553)
-          const double* T = p.opts.transform;
-          const float x = fmaf(qz, (float)T[2], fmaf(qy, (float)T[1], qx * (float)T[0])) + (float)T[3];
-          const float y = fmaf(qz, (float)T[6], fmaf(qy, (float)T[5], qx * (float)T[4])) + (float)T[7];
-          const float z = fmaf(qz, (float)T[10], fmaf(qy, (float)T[9], qx * (float)T[8])) + (float)T[11];
-          qx = x;
-          qy = y;
-          qz = z;
-        }
-      }
-      // the K nearest: squared distance, position of the (global) point it was measured to, id | REMAP, global id
-      float d2[KREG], px[KREG], py[KREG], pz[KREG];
-      int lif[KREG], gid[KREG];
-      int cnt = 0;
+    if (SPLIT) {  // the search launch did it: copy the tile's stash block (coalesced 16-byte accesses)
+      const float4* __restrict__ src = reinterpret_cast<const float4*>(p.stash + (size_t)st * Stash::floats);
+      float4* dst = reinterpret_cast<float4*>(wsm + WL::stash);
+      float4 t[Stash::floats / 128];
 #pragma unroll
-      for (int k = 0; k < KREG; ++k) {
-        d2[k] = INVALID_D2;
-        px[k] = py[k] = pz[k] = 0.f;
-        lif[k] = gid[k] = -1;
-      }
-      if (p.use_saved_knn) {
-        if (live) {
-          cnt = __ldg(p.out.nn_count + qi);
+      for (int i = 0; i < Stash::floats / 128; ++i) t[i] = __ldg(src + i * 32 + lane);
 #pragma unroll
-          for (int k = 0; k < KREG; ++k)
-            if (k < K) {
-              const int li = __ldg(p.out.knn_idx + qi * K + k);
-              if (li >= 0) {
-                gid[k] = __ldg(p.out.knn_gidx + qi * K + k);
-                d2[k] = __ldg(p.out.knn_dist2 + qi * K + k);
-                const float* pg = m.points + 3 * (size_t)gid[k];
-                const float* pl = m.nb_points + 3 * (size_t)li;
-                px[k] = __ldg(pg);
-                py[k] = __ldg(pg + 1);
-                pz[k] = __ldg(pg + 2);
-                const bool same = __ldg(pl) == px[k] && __ldg(pl + 1) == py[k] && __ldg(pl + 2) == pz[k];
-                lif[k] = same ? li : (li | REMAP);
-              }
-            }
-        }
-      } else {
-        const uint32_t r0 = base_slot(m, qx, qy, qz);
-        KnnTop T;
-        cnt = knn_search_lane(m, s_delta, live, r0, qx, qy, qz, T);
-        // re-read the winners (the probe loop kept only distance + record rank through the sorting networks)
-        const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(m.probe_rec);
-        float4 r[KREG];
+      for (int i = 0; i < Stash::floats / 128; ++i) dst[i * 32 + lane] = t[i];
+      __syncwarp();
+    } else {
+      a1_tile(p, s_delta, q0s, WQ, lane, wsm + WL::stash);
+    }
+    if (WF) {  // the position part of the IDW-averaged decoder input (this thread's tile row) + zero padding
+      s_x[lane * LDX + F + 0] = s_pos[0 * WT + lane];
+      s_x[lane * LDX + F + 1] = s_pos[1 * WT + lane];
+      s_x[lane * LDX + F + 2] = s_pos[2 * WT + lane];
 #pragma unroll
-        for (int k = 0; k < KREG; ++k) {
-          r[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-          if (k < K && T.p[k] >= 0) {
-            r[k] = __ldg(rec4 + T.p[k]);
-            if (p.out.knn_gidx) gid[k] = __ldg(m.probe_gid + T.p[k]);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < KREG; ++k)
-          if (k < K && T.p[k] >= 0) {
-            d2[k] = T.d[k];
-            px[k] = r[k].x;
-            py[k] = r[k].y;
-            pz[k] = r[k].z;
-            lif[k] = __float_as_int(r[k].w);
-          }
-      }
-      // normalised inverse-distance weights, summed in neighbour order (model/neural_points.py:665-683)
-      float u[KREG], w[KREG], usum = 0.f;
-#pragma unroll
-      for (int k = 0; k < KREG; ++k) {
-        const bool v = k < K && lif[k] >= 0;
-        u[k] = k < K ? (cnt == 0 ? IDW_EPS : (v ? __frcp_rn(d2[k] + IDW_EPS) : 0.f)) : 0.f;
-        usum += u[k];
-      }
-#pragma unroll
-      for (int k = 0; k < KREG; ++k) w[k] = (k < K && lif[k] >= 0) ? __fdiv_rn(u[k], usum) : 0.f;
-      // neighbour vectors n_k = q - p_k (rotated into the point frame after PGO), certainty (:631-651)
-      float sx = 0.f, sy = 0.f, sz = 0.f, qc = 0.f;
-      const bool want_cert = !p.is_color && (p.out.certainty != nullptr);
-#pragma unroll
-      for (int k = 0; k < KREG; ++k) {
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        if (k < K && lif[k] >= 0) {
-          dx = __fsub_rn(qx, px[k]);
-          dy = __fsub_rn(qy, py[k]);
-          dz = __fsub_rn(qz, pz[k]);
-          if (WF || want_cert) {
-            float nx, ny, nz;
-            float4 quat;
-            neighbour_vec(m, lif[k], dx, dy, dz, qx, qy, qz, nx, ny, nz, quat);
-            sx = fmaf(w[k], nx, sx);
-            sy = fmaf(w[k], ny, sy);
-            sz = fmaf(w[k], nz, sz);
-            if (want_cert) qc = fmaf(w[k], m.certainty[lif[k] & ~REMAP], qc);
-          }
-        }
-        if (k < K) {
-          s_li[k * WT + lane] = lif[k];
-          s_w[k * WT + lane] = w[k];
-          s_dx[k * WT + lane] = dx;
-          s_dy[k * WT + lane] = dy;
-          s_dz[k * WT + lane] = dz;
-        }
-      }
-      s_nn[lane] = cnt;
-      s_usum[lane] = usum;
-      s_q[0 * WT + lane] = qx;
-      s_q[1 * WT + lane] = qy;
-      s_q[2 * WT + lane] = qz;
-      if (WF) {  // the position part of the IDW-averaged decoder input (this thread's tile row) + zero padding
-        s_x[lane * LDX + F + 0] = sx;
-        s_x[lane * LDX + F + 1] = sy;
-        s_x[lane * LDX + F + 2] = sz;
-#pragma unroll
-        for (int d = D; d < KP0; ++d) s_x[lane * LDX + d] = 0.f;
-      }
-      if (live && !p.is_color) {
-        if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
-          // certainty scatter_add / ts amax (:685-710); invalid entries add 0 / max with 0 in the reference
-          const int ts = (m.ts_update && p.query_ts) ? __ldg(p.query_ts + qi) : 0;
-#pragma unroll
-          for (int k = 0; k < KREG; ++k)
-            if (k < K && lif[k] >= 0) {
-              atomicAdd(m.certainty + (lif[k] & ~REMAP), w[k]);
-              if (m.ts_update && p.query_ts) atomicMax(m.ts_update + (lif[k] & ~REMAP), ts);
-            }
-        }
-        if (p.out.certainty) p.out.certainty[qi] = qc;
-        if (!p.use_saved_knn) {
-          if (p.out.nn_count) p.out.nn_count[qi] = cnt;
-#pragma unroll
-          for (int k = 0; k < KREG; ++k)
-            if (k < K) {
-              if (p.out.knn_idx) p.out.knn_idx[qi * K + k] = lif[k] < 0 ? -1 : (lif[k] & ~REMAP);
-              if (p.out.knn_gidx) p.out.knn_gidx[qi * K + k] = gid[k];
-              if (p.out.knn_dist2) p.out.knn_dist2[qi * K + k] = d2[k];
-              if (p.out.knn_weight) p.out.knn_weight[qi * K + k] = w[k];
-            }
-        }
-        if (p.out.xyz) {
-          p.out.xyz[3 * qi + 0] = qx;
-          p.out.xyz[3 * qi + 1] = qy;
-          p.out.xyz[3 * qi + 2] = qz;
-        }
-      }
+      for (int d = D; d < KP0; ++d) s_x[lane * LDX + d] = 0.f;
     }
     __syncwarp();
 
@@ -972,7 +1029,7 @@ static QueryLayout plan_layout(const QueryParams& p) {
   return l;
 }
 
-template <int FT, bool WF>
+template <int FT, bool WF, bool SPLIT>
 static int launch_query(QueryParams& p, cudaStream_t stream) {
   p.lay = plan_layout<FT>(p);
   const size_t smem_bytes = (size_t)p.lay.total * sizeof(float);
@@ -989,7 +1046,9 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     const long long slots = (long long)sm_count() * nw;
     const long long per_warp = (p.n + slots - 1) / slots;
     int wq;
-    if (WF) {
+    if (SPLIT) {
+      wq = WT;  // the stash is written per 32-query tile
+    } else if (WF) {
       constexpr int G = RowMap<FT>::U * RowMap<FT>::RPP;  // queries per gather pass
       wq = (int)std::min<long long>(WT, std::max<long long>(G, (per_warp + G - 1) / G * G));
     } else {
@@ -1001,7 +1060,7 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
     const long long per_sm = (p.n_tiles + sm_count() - 1) / sm_count();
     if (per_sm < nw) nw = (int)std::max<long long>(1, per_sm);
   }
-  auto kern = query_kernel<FT, WF>;
+  auto kern = query_kernel<FT, WF, SPLIT>;
   // the attribute / occupancy calls cost a few microseconds each: remember the answer per (device, kernel)
   struct Cached {
     int dev;
@@ -1031,26 +1090,38 @@ static int launch_query(QueryParams& p, cudaStream_t stream) {
   return check_launch("query_kernel");
 }
 
-template <bool WF>
+template <bool WF, bool SPLIT>
 static int dispatch_query_wf(QueryParams& p, cudaStream_t stream) {
   switch (p.dec.in_dim - 3) {
-    case 4: return launch_query<4, WF>(p, stream);
-    case 8: return launch_query<8, WF>(p, stream);
-    case 16: return launch_query<16, WF>(p, stream);
-    case 32: return launch_query<32, WF>(p, stream);
-    case 64: return launch_query<64, WF>(p, stream);
+    case 4: return launch_query<4, WF, SPLIT>(p, stream);
+    case 8: return launch_query<8, WF, SPLIT>(p, stream);
+    case 16: return launch_query<16, WF, SPLIT>(p, stream);
+    case 32: return launch_query<32, WF, SPLIT>(p, stream);
+    case 64: return launch_query<64, WF, SPLIT>(p, stream);
     default: break;
   }
   set_error("feature_dim %d unsupported (4, 8, 16, 32, 64)", p.dec.in_dim - 3);
   return PINB200_ERR_UNSUPPORTED;
 }
 
-static int dispatch_query(QueryParams& p, cudaStream_t stream) {
+static int dispatch_query(QueryParams& p, cudaStream_t stream, bool split) {
   if (p.dec.hidden_dim != 64) {
     set_error("decoder hidden_dim %d unsupported (64)", p.dec.hidden_dim);
     return PINB200_ERR_UNSUPPORTED;
   }
-  return p.opts.weighted_first ? dispatch_query_wf<true>(p, stream) : dispatch_query_wf<false>(p, stream);
+  if (split)
+    return p.opts.weighted_first ? dispatch_query_wf<true, true>(p, stream) : dispatch_query_wf<false, true>(p, stream);
+  return p.opts.weighted_first ? dispatch_query_wf<true, false>(p, stream) : dispatch_query_wf<false, false>(p, stream);
+}
+
+// K1a launch of the split pipeline
+static int launch_search(QueryParams& p, cudaStream_t stream) {
+  p.qpt = WT;
+  p.n_tiles = (int)((p.n + WT - 1) / WT);
+  const long long ctas = (p.n_tiles + 3) / 4;
+  const int grid = (int)std::min<long long>(ctas, (long long)sm_count() * 4);
+  search_kernel<<<grid, 128, align4(p.map.n_probe) * sizeof(float), stream>>>(p);
+  return check_launch("search_kernel");
 }
 
 static int validate_decoder(const pinb200_decoder_view* d, int F) {
@@ -1119,19 +1190,32 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   p.n = n;
   p.qpt = WT;  // queries per warp tile
   p.n_tiles = (int)((n + WT - 1) / WT);
-  rc = dispatch_query(p, (cudaStream_t)stream);
+  // Large batches run as two launches (search at high occupancy, then decode) through the caller's workspace; small
+  // ones (tracker / mapper sized, latency-bound) stay fused in one launch.
+  const int64_t need = pinb200_query_workspace_bytes(n);
+  const bool split = opts->workspace && opts->workspace_bytes >= need && n >= PINB200_SPLIT_MIN_QUERIES;
+  if (split) {
+    p.stash = reinterpret_cast<float*>(opts->workspace);
+    rc = launch_search(p, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  rc = dispatch_query(p, (cudaStream_t)stream, split);
   if (rc) return rc;
   if (color_dec) {  // second launch: decode the colour features with the kNN the first launch saved
     QueryParams c = p;
     c.dec = *color_dec;
     c.feat = map->color_feat;
-    c.use_saved_knn = 1;
+    c.use_saved_knn = split ? 0 : 1;  // the split pipeline re-uses the stash instead
     c.is_color = 1;
     c.opts.training_mode = 0;
     c.opts.need_grad = (opts->need_grad && out->color_grad) ? 1 : 0;
-    rc = dispatch_query(c, (cudaStream_t)stream);
+    rc = dispatch_query(c, (cudaStream_t)stream, split);
   }
   return rc;
+}
+
+extern "C" int64_t pinb200_query_workspace_bytes(int64_t n) {
+  return n <= 0 ? 0 : ((n + WT - 1) / WT) * (int64_t)Stash::floats * (int64_t)sizeof(float);
 }
 
 extern "C" int pinb200_knn_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, int32_t nn_k,

@@ -8,6 +8,7 @@ import torch
 from . import _lib
 from ._lib import DecoderView, GnOpts, MapTrainOpts, MapView, QueryOpts, QueryOut
 
+SPLIT_MIN_QUERIES = 32768  # == PINB200_SPLIT_MIN_QUERIES
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -179,8 +180,15 @@ def _query_args(xyz, nn_k, weighted_first, training_mode, need_grad, color_dec, 
         qo.color = _ptr(buf("color", (n, cc)))
         if color_grad:
             qo.color_grad = _ptr(buf("color_grad", (n, cc, 3)))
+    ws_ptr, ws_bytes = None, 0
+    if n >= SPLIT_MIN_QUERIES:  # large batch: scratch for the two-launch (search, then decode) pipeline
+        need = int(_lib.load().pinb200_query_workspace_bytes(n))
+        ws = o.get("_workspace")
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = o["_workspace"] = torch.empty((need,), dtype=torch.uint8, device=dev)
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     opts = QueryOpts(int(nn_k), int(bool(weighted_first)), int(bool(training_mode)), int(bool(need_grad)),
-                     int(training_rows), _ptr(transform, torch.float64))
+                     int(training_rows), _ptr(transform, torch.float64), ws_ptr, ws_bytes)
     return o, qo, opts
 
 
@@ -199,7 +207,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
                                _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), xyz.shape[0], C.byref(opts),
                                C.byref(qo), _stream())
     _lib.check(rc, "pinb200_query_sdf")
-    _count(2 if color_dec is not None else 1)
+    _count((2 if color_dec is not None else 1) + (1 if xyz.shape[0] >= SPLIT_MIN_QUERIES else 0))
     return o
 
 
