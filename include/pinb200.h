@@ -118,8 +118,9 @@ typedef struct pinb200_query_opts {
   const double* transform;  /* optional device ptr, 4x4 row-major fp64: q = T*p evaluated in fp32 (tools.py:534-553) */
   void* workspace;          /* optional device scratch of >= pinb200_query_workspace_bytes(N) bytes.  With it, batches
                                of >= PINB200_SPLIT_MIN_QUERIES queries run as two launches (neighbour search at high
-                               occupancy, then gather + decoder); without it, or for small batches, one fused launch.
-                               Results are identical either way. */
+                               occupancy, then gather + decoder on tcgen05 tiles); without it, or for small batches,
+                               one fused launch.  The neighbour search is bit-identical either way; the decoder
+                               outputs agree within the 3xTF32 bound (different accumulation order). */
   int64_t workspace_bytes;
 } pinb200_query_opts;
 

@@ -976,6 +976,12 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ pin
   }
 }
 
+}  // namespace pinb
+
+#include "decode_umma.cuh"
+
+namespace pinb {
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1199,7 +1205,9 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
     rc = launch_search(p, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  rc = dispatch_query(p, (cudaStream_t)stream, split);
+  // decode: tcgen05 tiles of 128 queries where the configuration allows it, else the warp-level mma.sync kernel
+  rc = (split && umma_decode_supported(p)) ? dispatch_decode_umma(p, (cudaStream_t)stream)
+                                           : dispatch_query(p, (cudaStream_t)stream, split);
   if (rc) return rc;
   if (color_dec) {  // second launch: decode the colour features with the kNN the first launch saved
     QueryParams c = p;
@@ -1209,7 +1217,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
     c.is_color = 1;
     c.opts.training_mode = 0;
     c.opts.need_grad = (opts->need_grad && out->color_grad) ? 1 : 0;
-    rc = dispatch_query(c, (cudaStream_t)stream, split);
+    rc = (split && umma_decode_supported(c)) ? dispatch_decode_umma(c, (cudaStream_t)stream)
+                                             : dispatch_query(c, (cudaStream_t)stream, split);
   }
   return rc;
 }

@@ -658,10 +658,13 @@ def test_dropin_query_feature_matches_fused_path():
 
 
 def test_host_facing_pipelined_query_equals_device_query():
-    """NeuralPoints.query_sdf_host (pinned host in/out, pieces pipelined over two streams) returns exactly what
-    the device-resident call returns, for ragged piece sizes too."""
+    """NeuralPoints.query_sdf_host (pinned host in/out, pieces pipelined over two streams) returns what the
+    device-resident call returns, for ragged piece sizes too: bit for bit when both run the same kernels; when the
+    device call is large enough for the split search + tcgen05 decode pipeline while the host pieces are not, the
+    search outputs stay bit-identical and the decoder outputs agree within the 3xTF32 parity bound."""
     from pin_slam_b200.config import HotPathConfig
     from pin_slam_b200.model import Decoder
+    from pin_slam_b200 import ops
     from pin_slam_b200.synthetic import build_map, surface_queries
 
     cfg = HotPathConfig.cfg2(device="cuda")
@@ -678,8 +681,17 @@ def test_host_facing_pipelined_query_equals_device_query():
         for rep in range(2):  # second call reuses the staging buffers
             npm.query_sdf_host(q_host, dec, host, chunks=chunks)
             torch.cuda.current_stream().synchronize()
+            piece = -(-n // chunks)
+            same_kernels = (n >= ops.SPLIT_MIN_QUERIES) == (piece >= ops.SPLIT_MIN_QUERIES)
             for k, h in host.items():
-                assert torch.equal(h, ref[k].cpu()), (n, chunks, k)
+                r = ref[k].cpu()
+                if same_kernels or k in ("nn_count", "certainty", "sdf_std"):
+                    assert torch.equal(h, r), (n, chunks, k)
+                elif k == "sdf":
+                    bound = 1e-5 * torch.maximum(r.abs(), torch.tensor(float(dec.sdf_scale)))
+                    assert bool(((h - r).abs() <= bound).all()), (n, chunks, k, float((h - r).abs().max()))
+                else:
+                    assert float((h - r).abs().max()) <= 1e-4 * float(r.abs().mean()), (n, chunks, k)
 
 
 def test_dropin_pickles_and_installs_under_reference_module_names(tmp_path):
