@@ -16,8 +16,12 @@ analytic d sdf / d x.  One *step* is one pass of the hot path over that batch.
             region
   roofline  achieved algorithmic GB/s of the K1 kernel / measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference
-            the CPU oracle (a restatement of the reference's PyTorch path, oracle/pin_oracle.py) on
-            the host cores over a bounded sample of the same batch
+            the UNMODIFIED reference classes (oracle/_ref, vendored by oracle/make_ref.py) on the host
+            cores, in a process that never loads this repo's CUDA library
+  roofline_variants / mapper_dp / per_frame
+            K1 on maps >> L2 and in decode-every-neighbour mode; BASELINE configs[4] data-parallel
+            training (NCCL all-reduce inside the timed region, every N); configs[2] per-frame loop
+            next to the reference's own Tracker/Mapper in PyTorch-CUDA mode
 N>1: the query path has no exchange step -- every rank runs the same per-GPU batch on its own map
 replica (weak scaling); no collective on the data path.
 """
@@ -133,114 +137,60 @@ def bytes_per_query(c, n_occ, k_v, f):
     return 12 + 4 * c + 16 * n_occ + k_v * (4 * f + 4) + 28
 
 
-def oracle_map_from(npm):
-    """CPU OracleMap holding copies of the NeuralPoints state (baseline legs only)."""
-    from oracle import pin_oracle as po
-
-    c = lambda x: None if x is None else x.detach().cpu().clone()  # noqa: E731
-    m = po.OracleMap(
-        resolution=npm.resolution, buffer_size=npm.buffer_size, feature_dim=npm.geo_feature_dim,
-        neural_points=c(npm.neural_points), point_orientations=c(npm.point_orientations),
-        geo_features=c(npm.geo_features), color_features=c(npm.color_features),
-        point_ts_create=c(npm.point_ts_create), point_ts_update=c(npm.point_ts_update),
-        point_certainties=c(npm.point_certainties), buffer_pt_index=c(npm.buffer_pt_index).long(),
-        local_neural_points=c(npm.local_neural_points), local_point_orientations=c(npm.local_point_orientations),
-        local_geo_features=c(npm.local_geo_features), local_color_features=None,
-        local_point_certainties=c(npm.local_point_certainties), local_point_ts_update=c(npm.local_point_ts_update),
-        local_mask=c(npm.local_mask), global2local=c(npm.global2local).long(), neighbor_dx=c(npm.neighbor_dx),
-        max_valid_dist2=npm.max_valid_dist2, travel_dist=c(npm.travel_dist), cur_ts=npm.cur_ts,
-        diff_travel_dist_local=npm.diff_travel_dist_local, temporal_local_map_on=npm.temporal_local_map_on,
-        after_pgo=npm.after_pgo)
-    return m
-
-
-def oracle_decoder_from(dec):
-    from oracle import pin_oracle as po
-
-    hidden = [(l.weight.detach().cpu().clone(), l.bias.detach().cpu().clone()) for l in dec.layers]
-    return po.DecoderParams(hidden, (dec.lout.weight.detach().cpu().clone(), dec.lout.bias.detach().cpu().clone()),
-                            dec.sdf_scale)
-
-
-def time_cpu_oracle(m, d, q_cpu, k, wf, sample, repeats=1):
-    """Seconds per `sample` queries of the reference algorithm (oracle port) on the host cores."""
-    import torch
-
-    from oracle import pin_oracle as po
-
-    qs = q_cpu[:sample]
-    po.query_sdf(m, d, qs[: min(2000, sample)], k, wf)  # warm the thread pool / allocator
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        po.query_sdf(m, d, qs, k, wf)
-        best = min(best, time.perf_counter() - t0)
-    return best
-
-
-def calibrate_cpu_threads(m, d, q_cpu, k, wf):
-    """The thread count at which the CPU path is fastest on this host.  The path is ~200 small ATen ops per call;
-    with one thread per core on a 128-core host the OpenMP fork/join cost dominates them (measured: 25x slower
-    than 16 threads), so `all cores` would understate the reference.  Returns (threads, {threads: seconds})."""
-    import torch
-
-    from oracle import pin_oracle as po
-
-    ncpu = os.cpu_count() or 1
-    cand = sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu})
-    probe = q_cpu[:4000]
-    timings = {}
-    for t in cand:
-        torch.set_num_threads(t)
-        po.query_sdf(m, d, probe[:1000], k, wf)  # warm the pool at this size
-        t0 = time.perf_counter()
-        po.query_sdf(m, d, probe, k, wf)
-        timings[t] = time.perf_counter() - t0
-    best = min(timings, key=timings.get)
-    torch.set_num_threads(best)
-    return best, timings
+def _ref_subprocess(mode, device, extra, timeout=900):
+    """Run oracle/ref_arm.py (the unmodified reference classes from oracle/_ref) in a clean process: it never imports
+    pin_slam_b200 and never maps libpinb200.so.  Returns the parsed JSON line or {"error": ...}."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_arm.py"), mode, "--device", device] + [str(x) for x in extra]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm for this path on the host CPU (the reference is
-    pure Python/PyTorch and /root/reference does not exist on the GPU box, so the oracle port runs it)."""
-    import torch
-
+    """--impl reference: the reference's own implementation of the path -- the unmodified `NeuralPoints` / `Decoder` /
+    `Tracker.query_source_points` classes vendored into oracle/_ref by oracle/make_ref.py -- on the host CPU, all
+    200 000 queries of BASELINE configs[1] per step.  This process imports neither pin_slam_b200 nor libpinb200.so:
+    the workload (map, decoder, queries) is built with the reference's classes from the same seeded generators."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
-    dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
-    cfg, npm, dec, q = build_workload(dev)
-    from pin_slam_b200 import ops  # stats only (C, N_occ, K_v of the workload)
+    from oracle import ref_arm
 
-    n_occ, k_v, _ = workload_stats(npm, q, cfg.query_nn_k) if dev.type == "cuda" else (11.0, 8.0, 1.0)
-    bq = bytes_per_query(npm.neighbor_K, n_occ, k_v, cfg.feature_dim)
-    m, d = oracle_map_from(npm), oracle_decoder_from(dec)
-    qc = q.cpu()
-    sample = 20000
-    threads, tried = calibrate_cpu_threads(m, d, qc, cfg.query_nn_k, cfg.weighted_first)
-    for _ in range(args.warmup):
-        time_cpu_oracle(m, d, qc, cfg.query_nn_k, cfg.weighted_first, 2000)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        from oracle import pin_oracle as po
-
-        po.query_sdf(m, d, qc[:sample], cfg.query_nn_k, cfg.weighted_first)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = bq * sample / dt / 1e9
+    if not ref_arm.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is missing (oracle/make_ref.py needs the "
+                                                              "reference checkout; run build() in the build container)"}))
+        return
+    a = argparse.Namespace(device="cpu", steps=args.steps, warmup=args.warmup, sample=0, frames=12)
+    r = ref_arm.run_query(a)
+    bq = bytes_per_query(r["n_probe"], r["occupied_probes_mean"], r["valid_knn_mean"], r["feature_dim"])
+    dt = r["s_per_step"]
+    val = bq * r["n_query"] / dt / 1e9
     line = {
         "impl": "reference", "metric": "kNN+MLP fused query throughput (algorithmic bytes)", "value": val, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg, npm, n_occ, k_v, bq, sample=sample),
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port",
-                         "host_cores": os.cpu_count(),
-                         "threads_tried_s_per_4000_queries": {str(t): round(v, 4) for t, v in tried.items()},
-                         "sample": f"{sample} of the {N_QUERY} queries per step, torch CPU ops, at the fastest "
-                                   "thread count of the ones tried"},
+        "config": {
+            "workload": "BASELINE configs[1]: fused kNN+SDF-MLP query, 200k query pts, K=8, F=32, 2x64 decoder, "
+                        "C=33 probes, with d sdf/dx",
+            "n_query": r["n_query"], "nn_k": r["nn_k"], "feature_dim": r["feature_dim"], "decoder": r["decoder"],
+            "weighted_first": r["weighted_first"], "n_probe": r["n_probe"], "map_points": r["map_points"],
+            "local_points": r["local_points"], "buffer_size": r["buffer_size"],
+            "occupied_probes_mean": round(r["occupied_probes_mean"], 3), "valid_knn_mean": round(r["valid_knn_mean"], 3),
+            "bytes_per_query": round(bq, 1), "l2": "n/a (host CPU)",
+            "parallelism": "replicas (no collective on the query path)"},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": r["threads"], "host_cores": r["host_cores"],
+                         "kind": "reference",
+                         "threads_tried_s_per_20000_queries": r["threads_tried_s_per_20000_queries"],
+                         "sample": f"all {r['n_query']} queries per step through the unmodified reference "
+                                   "Tracker.query_source_points (oracle/_ref), torch CPU ops at the fastest thread count "
+                                   "of the ones tried"},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "queries_per_s": sample / dt,
+        "queries_per_s": r["queries_per_s"],
     }
     print(json.dumps(line))
 
@@ -281,68 +231,20 @@ def frame_benchmark(dev, n_frames=12, warm_iters=100):
            "frames_per_s": 1000.0 / (trk + mp), "kernel_launches_per_frame": launches,
            "source_points": info[-1]["n_source"], "scan_points": info[-1]["n_scan"],
            "local_map_points": info[-1]["local_points"], "pool_samples": info[-1]["pool"],
-           "final_translation_error_m": info[-1]["trans_err_m"]}
-    try:
-        out["torch_eager_gpu_baseline"] = frame_baseline_torch(loop, dev)
-        out["speedup_vs_torch_eager_gpu"] = out["frames_per_s"] / out["torch_eager_gpu_baseline"]["frames_per_s"]
-    except Exception as e:  # noqa: BLE001
-        out["torch_eager_gpu_baseline"] = {"error": str(e)[:200]}
+           "final_translation_error_m": info[-1]["trans_err_m"],
+           "translation_error_m_per_frame": [round(i["trans_err_m"], 4) for i in info]}
+    # the >= 10x denominator of north_star: the reference's OWN Tracker / Mapper in PyTorch-CUDA mode on this GPU, same
+    # scans, same preprocessing, 3 registration + 5 training iterations per frame (clean subprocess, oracle/_ref)
+    del loop
+    torch.cuda.empty_cache()
+    ref = _ref_subprocess("frames", "cuda", ["--frames", n_frames])
+    out["reference_cuda_baseline"] = ref
+    if "frames_per_s" in ref:
+        out["speedup_vs_reference_cuda"] = out["frames_per_s"] / ref["frames_per_s"]
     return out
 
 
-def frame_baseline_torch(loop, dev, device=None, reps=3):
-    """The reference's per-frame op sequence (oracle port) on `device` for the current map state:
-    3 x (query_source_points + registration_step) and 5 x one Mapper.mapping iteration."""
-    import torch
-
-    from oracle import pin_oracle as po
-
-    device = device or dev
-    cfg, npm, mapper = loop.cfg, loop.neural_points, loop.mapper
-    m = oracle_map_from(npm).to(device)
-    d = oracle_decoder_from(loop.sdf_mlp).to(device)
-    _, _, source = loop.preprocess(len(loop.poses))
-    source = source.to(device)
-    pose = loop.poses[-1].to(device)
-    sync = (lambda: torch.cuda.synchronize()) if torch.device(device).type == "cuda" else (lambda: None)
-
-    def track():
-        T = pose.clone()
-        for _ in range(3):
-            pts = po.transform_points(source, T)
-            o = po.query_sdf(m, d, pts, cfg.query_nn_k, cfg.weighted_first)
-            r = po.registration_step(pts, o["sdf"], o["grad"], o["sdf_std"], o["nn_count"], torch.zeros_like(o["sdf"]),
-                                     cfg.track_mask_query_nn_k, cfg.reg_min_grad_norm, cfg.reg_max_grad_norm,
-                                     cfg.surface_sample_range_m * cfg.max_sdf_std_ratio, cfg.reg_GM_dist_m,
-                                     cfg.reg_GM_grad, cfg.reg_lm_lambda)
-            T = r["T"] @ T
-
-    def train():
-        mm, dd = m.clone(), d.clone()
-        mm.local_geo_features.requires_grad_(True)
-        dd.requires_grad_(True)
-        opt = po.make_adam([dd.tensors(), [mm.local_geo_features]], cfg.lr, cfg.adam_eps, cfg.weight_decay)
-        for _ in range(5):
-            coord, label, ts, _, _, _, w = mapper.get_batch(global_coord=True)
-            coord, label, ts, w = coord.to(device), label.to(device), ts.to(device), w.to(device)
-            loss, _ = po.mapping_loss(mm, dd, coord, label, ts, w, cfg.query_nn_k, cfg.weighted_first, mapper.sdf_scale,
-                                      cfg.loss_weight_on, cfg.weight_e, cfg.gradient_decimation,
-                                      cfg.voxel_size_m * cfg.num_grad_step_ratio)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()
-
-    track(); train(); sync()
-    tt, tm = [], []
-    for _ in range(reps):
-        t0 = time.perf_counter(); track(); sync(); t1 = time.perf_counter(); train(); sync(); t2 = time.perf_counter()
-        tt.append((t1 - t0) * 1e3); tm.append((t2 - t1) * 1e3)
-    trk, mp = sorted(tt)[len(tt) // 2], sorted(tm)[len(tm) // 2]
-    return {"tracker_ms": trk, "mapping_ms": mp, "frames_per_s": 1000.0 / (trk + mp), "device": str(device),
-            "what": "reference op sequence (oracle port) in PyTorch eager: 3 x (query + GN step), 5 x training iteration"}
-
-
-def mapper_benchmark(args):
+def mapper_benchmark(args, standalone=True):
     """BASELINE configs[4]: mapper-only data-parallel training.  A 2M-sample replay pool sharded over the ranks,
     per-GPU batch 16384 (weak scaling), K1 forward + loss heads + K2 backward + ONE NCCL all-reduce of
     [feature grads | decoder grads | certainty increments] + K3 Adam per iteration.  value = samples/s (all ranks)."""
@@ -362,7 +264,7 @@ def mapper_benchmark(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and standalone:
         dist.init_process_group("nccl", device_id=dev)
     cfg = HotPathConfig.kitti(device=str(dev), feature_std=0.05, bs_new_sample=0, local_map_radius=1e4)
     npm = build_map(cfg, n_surface=2_000_000, seed=0, extent=80.0)   # identical replica on every rank (same seed)
@@ -400,20 +302,23 @@ def mapper_benchmark(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / args.steps
-    if rank == 0:
-        print(json.dumps({
-            "metric": "mapper training throughput (samples/s, all GPUs)", "value": cfg.bs * world / (ms * 1e-3),
-            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[4]: mapper-only, 2M-sample pool sharded over ranks, bs/GPU 16384, "
-                                   "run_kitti.yaml parameters, NCCL all-reduce of feature+decoder grads per iteration",
-                       "local_points": int(npm.local_count()), "pool_per_rank": n,
-                       "allreduce_floats": int(npm.local_geo_features.numel() + dec.flat_parameters().numel()
-                                               + npm.local_count()),
-                       "parallelism": f"dp{world}"},
-            "gpu_launches": ops.launch_count() - l0}))
-    if world > 1:
-        dist.destroy_process_group()
+    res = {
+        "metric": "mapper training throughput (samples/s, all GPUs)", "value": cfg.bs * world / (ms * 1e-3),
+        "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4]: mapper-only, 2M-sample pool sharded over ranks, bs/GPU 16384, "
+                               "run_kitti.yaml parameters, NCCL all-reduce of feature+decoder grads per iteration",
+                   "local_points": int(npm.local_count()), "pool_per_rank": n,
+                   "allreduce_floats": int(mapper.allreduce_floats()) if hasattr(mapper, "allreduce_floats") else
+                   int(npm.local_geo_features.numel() + dec.flat_parameters().numel() + npm.local_count()),
+                   "parallelism": f"dp{world}"},
+        "gpu_launches": ops.launch_count() - l0}
+    if standalone:
+        if rank == 0:
+            print(json.dumps(res))
+        if world > 1:
+            dist.destroy_process_group()
+    return res
 
 
 def main():
@@ -424,6 +329,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true", help="skip the per-frame tracker+mapper measurement")
+    ap.add_argument("--no-variants", action="store_true", help="skip the map >> L2 / decode-every-neighbour K1 variants")
+    ap.add_argument("--no-mapper", action="store_true", help="skip the data-parallel map-training measurement")
     ap.add_argument("--map-scale", type=float, default=1.0,
                     help="query workload only: scale the synthetic map (points ~ scale^2, same density); "
                          "1.55 ~ 250 k points, 3.1 ~ 1 M points (map >> L2).  The default (1.0, 106 k points) is the "
@@ -470,6 +377,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def time_k1(fn, steps):
+        """Per-step CUDA-event times (ms) of `fn` on the launching stream, L2 flushed before every step."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -479,16 +397,10 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ops.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    for a, b in evs:
-        flush.zero_()
-        a.record()
-        step()
-        b.record()
+    step_ms = time_k1(step, args.steps)
     barrier()
     launches = ops.launch_count() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(step_ms)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -498,10 +410,12 @@ def main():
                 [("sdf", (N_QUERY,), torch.float32), ("grad", (N_QUERY, 3), torch.float32),
                  ("sdf_std", (N_QUERY,), torch.float32), ("nn_count", (N_QUERY,), torch.int32),
                  ("certainty", (N_QUERY,), torch.float32)]}
+    E2E_CHUNKS = 2
+
     def e2e_step():
-        # the public host-facing call: pinned host queries in, pinned host results out; the batch is cut into 4
-        # pieces on two streams so that the PCIe copies overlap the kernel (pin_slam_b200/model/neural_points.py)
-        npm.query_sdf_host(q_host, dec, res_host, chunks=4, need_grad=True)
+        # the public host-facing call: pinned host queries in, pinned host results out; the batch is cut into pieces on
+        # two streams so that the PCIe copies overlap the kernels (pin_slam_b200/model/neural_points.py)
+        npm.query_sdf_host(q_host, dec, res_host, chunks=E2E_CHUNKS, need_grad=True)
 
     for _ in range(3):
         e2e_step()
@@ -522,8 +436,11 @@ def main():
     value = bq * N_QUERY * world / (ms_per_step * 1e-3) / 1e9
     e2e_val = bq * N_QUERY * world / (e2e_ms / args.steps * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
-    kernel_ms = sorted(step_ms)[len(step_ms) // 2]  # one K1 launch per step: the step time IS the kernel time
+    kernel_ms = sorted(step_ms)[len(step_ms) // 2]
     achieved = bq * N_QUERY / (ms_per_step * 1e-3) / 1e9
+    split = N_QUERY >= ops.SPLIT_MIN_QUERIES
+    k1_kernels = ("pinb::search_kernel + pinb::decode_umma_kernel<%d>" % cfg.feature_dim) if split else \
+        "pinb::query_kernel<%d,%s,false>" % (cfg.feature_dim, "true" if cfg.weighted_first else "false")
 
     line = None
     if rank == 0:
@@ -536,45 +453,102 @@ def main():
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 12 * N_QUERY,
                     "d2h_bytes_per_step": 28 * N_QUERY, "ms_per_step": e2e_ms / args.steps,
                     "call": "NeuralPoints.query_sdf_host(pinned host queries) -> pinned host sdf/grad/std/nn_count/certainty, "
-                            "4 pieces pipelined over 2 streams"},
+                            "%d pieces pipelined over 2 streams" % E2E_CHUNKS},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pinb::query_kernel<64,36>",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": k1_kernels,
                          "kernel_ms_median": kernel_ms,
-                         "note": "achieved = algorithmic bytes/query x queries / mean CUDA-event time of the K1 launch"},
+                         "note": "K1 = the two launches of the query pipeline (neighbour search, then gather + tcgen05 "
+                                 "decoder); achieved = algorithmic bytes/query x queries / mean CUDA-event time of the "
+                                 "pipeline; traffic = dram bytes of both launches (ncu, profiles/k1_traffic.json)"},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            m, d = oracle_map_from(npm), oracle_decoder_from(dec)
-            sample = 20000
-            threads, tried = calibrate_cpu_threads(m, d, q.cpu(), k, cfg.weighted_first)
-            sec = time_cpu_oracle(m, d, q.cpu(), k, cfg.weighted_first, sample, repeats=3)
-            line["cpu_baseline"] = {"value": bq * sample / sec / 1e9, "unit": "GB/s", "cores": threads,
-                                    "host_cores": os.cpu_count(), "kind": "port", "queries_per_s": sample / sec,
-                                    "threads_tried_s_per_4000_queries": {str(t): round(v, 4) for t, v in tried.items()},
-                                    "sample": f"{sample} of the {N_QUERY} queries, oracle (torch CPU restatement of "
-                                              "the reference path) at the fastest thread count tried, best of 3"}
-            # the reference's own GPU mode = the same PyTorch op sequence on the device (the >=10x denominator)
-            try:
-                mg, dg = m.clone().to(dev), d.to(dev)
-                from oracle import pin_oracle as po
+    # ---- the other regimes of SURVEY.md 8(d): maps >> L2, and decode-every-neighbour against the compute roof
+    if world == 1 and not args.no_variants:
+        variants = []
+        from pin_slam_b200.config import HotPathConfig
+        from pin_slam_b200.model import Decoder
+        from pin_slam_b200.synthetic import build_map, surface_queries
 
-                po.query_sdf(mg, dg, q, k, cfg.weighted_first)  # warm-up at full size (allocator, cuBLAS init)
-                torch.cuda.synchronize()
-                sec_g = float("inf")
+        for scale, wf in ((1.55, True), (3.1, True), (1.0, False)):
+            try:
+                vcfg = HotPathConfig.cfg2(device=str(dev), feature_std=0.1, local_map_radius=1e4)
+                vcfg.weighted_first = wf
+                vnpm = npm if scale == 1.0 else build_map(vcfg, n_surface=int(3_000_000 * scale * scale), seed=0,
+                                                          extent=80.0 * scale)
+                if scale == 1.0:
+                    vnpm.config = vcfg
+                torch.manual_seed(42)
+                vdec = Decoder(vcfg, vcfg.geo_mlp_hidden_dim, vcfg.geo_mlp_level, 1)
+                vq = q if scale == 1.0 else surface_queries(vnpm, N_QUERY, seed=1, sigma=0.1)
+                vo = {}
+                fn = lambda: vnpm.query_sdf(vq, vdec, need_grad=True, out=vo)  # noqa: E731
                 for _ in range(3):
-                    t0 = time.perf_counter()
-                    po.query_sdf(mg, dg, q, k, cfg.weighted_first)
-                    torch.cuda.synchronize()
-                    sec_g = min(sec_g, time.perf_counter() - t0)
-                line["torch_eager_gpu_baseline"] = {
-                    "value": bq * N_QUERY / sec_g / 1e9, "unit": "GB/s", "ms_per_step": sec_g * 1e3,
-                    "what": "reference op sequence (oracle port) in PyTorch eager on the same B200, 200k queries, best of 3"}
+                    fn()
+                ms = sorted(time_k1(fn, 8))[4]
+                vn_occ, vk_v, _ = workload_stats(vnpm, vq, k)
+                vbq = bytes_per_query(vnpm.neighbor_K, vn_occ, vk_v, vcfg.feature_dim)
+                ach = vbq * N_QUERY / (ms * 1e-3) / 1e9
+                v = {"workload": "cfg2 %s, map x%.2f" % ("weighted_first" if wf else "decode-every-neighbour", scale),
+                     "map_points": int(vnpm.count()), "weighted_first": wf, "ms_per_step": ms,
+                     "bytes_per_query": round(vbq, 1),
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+                if not wf:
+                    # dense [N*K, D] x [D, 64] x [64, 64] chain, forward + backward to the input: 2 flops per MAC
+                    D, H = vcfg.feature_dim + 3, 64
+                    flops = 2.0 * (D * H + H * H + H) * k * 2 * N_QUERY
+                    sm_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # fp32 SIMT FMA peak of this part (TFLOP/s)
+                    v["compute_roofline"] = {"bound": "fp32 (3xTF32 on tensor cores counts as fp32 work)",
+                                             "achieved": flops / (ms * 1e-3) / 1e12, "peak": sm_peak, "unit": "TFLOP/s",
+                                             "frac": flops / (ms * 1e-3) / 1e12 / sm_peak}
+                variants.append(v)
+                if scale != 1.0:
+                    del vnpm
+                    torch.cuda.empty_cache()
             except Exception as e:  # noqa: BLE001
-                line["torch_eager_gpu_baseline"] = {"error": str(e)[:200]}
+                variants.append({"workload": "map x%.2f wf=%s" % (scale, wf), "error": repr(e)[:200]})
+        npm.config = cfg
+        if line is not None:
+            line["roofline_variants"] = variants
+    # ---- BASELINE configs[4]: data-parallel map training, every N (the collective is inside the timed region)
+    if not args.no_mapper:
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            md = mapper_benchmark(argparse.Namespace(steps=max(20, args.steps), warmup=args.warmup), standalone=False)
+            if line is not None:
+                line["mapper_dp"] = {"ms_per_iter": md["ms_per_step"], "samples_per_s": md["value"],
+                                     "allreduce_bytes": 4 * md["config"]["allreduce_floats"],
+                                     "bs_per_gpu": 16384, "n_gpus": world, "gpu_launches": md["gpu_launches"],
+                                     "workload": md["config"]["workload"]}
+        except Exception as e:  # noqa: BLE001
+            if line is not None:
+                line["mapper_dp"] = {"error": repr(e)[:300]}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            # the reference itself (unmodified classes, oracle/_ref), clean subprocesses: CPU on the host cores over a
+            # bounded sample, and its own PyTorch-CUDA mode on this GPU over the full batch
+            r = _ref_subprocess("query", "cpu", ["--steps", 2, "--warmup", 1, "--sample", 50000])
+            if "queries_per_s" in r:
+                line["cpu_baseline"] = {"value": bq * r["queries_per_s"] / 1e9, "unit": "GB/s", "cores": r["threads"],
+                                        "host_cores": r["host_cores"], "kind": "reference",
+                                        "queries_per_s": r["queries_per_s"],
+                                        "threads_tried_s_per_20000_queries": r["threads_tried_s_per_20000_queries"],
+                                        "sample": "50000 of the 200000 queries per step, 2 steps, unmodified reference "
+                                                  "Tracker.query_source_points (oracle/_ref) on CPU tensors at the "
+                                                  "fastest thread count tried"}
+            else:
+                line["cpu_baseline"] = r
+            g = _ref_subprocess("query", "cuda", ["--steps", 3, "--warmup", 2])
+            if "queries_per_s" in g:
+                line["reference_cuda_baseline"] = {
+                    "value": bq * g["queries_per_s"] / 1e9, "unit": "GB/s", "ms_per_step": g["s_per_step"] * 1e3,
+                    "what": "unmodified reference Tracker.query_source_points (oracle/_ref) in PyTorch-CUDA mode on this "
+                            "B200, all 200k queries per step"}
+                line["speedup_vs_reference_cuda"] = g["s_per_step"] * 1e3 / ms_per_step
+            else:
+                line["reference_cuda_baseline"] = g
         if world == 1 and not args.no_frame:
-            del flush
-            torch.cuda.empty_cache()
             try:
                 line["per_frame"] = frame_benchmark(dev)
             except Exception as e:  # noqa: BLE001
