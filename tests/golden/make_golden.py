@@ -623,6 +623,31 @@ def gen_track_fixture(kind, seed, name=None):
                   cfg.final_residual_ratio_thre, cfg.max_sdf_std_ratio, cfg.eigenvalue_ratio_thre]
     out["cfg.reg_floats"] = np.array(cfg_floats, np.float64)
     out["cfg.reg_ints"] = np.array([cfg.reg_iter_n, cfg.track_mask_query_nn_k], np.int64)
+    # one explicit registration step with the covariance / eigenvalue outputs switched on (utils/tracker.py:680-693;
+    # consumed by the degeneracy check at :198-223) on the points at the converged pose
+    tracker.registration_step = orig
+    from utils.tools import transform_torch
+    pts_final = transform_torch(src.clone(), T)
+    gm_d = cfg.reg_GM_dist_m if cfg.reg_GM_dist_m > 0 else None
+    gm_g = cfg.reg_GM_grad if cfg.reg_GM_grad > 0 else None
+    rs = tracker.registration_step(pts_final, None, torch.zeros(src.shape[0]), None, cfg.reg_min_grad_norm,
+                                   cfg.reg_max_grad_norm, gm_d, gm_g, cfg.reg_lm_lambda, True)
+    out["regstep.points"] = pts_final.detach().numpy().copy()
+    out["regstep.T"] = rs[0].numpy().copy()
+    out["regstep.cov"] = rs[1].detach().numpy().copy()
+    out["regstep.eig"] = rs[2].detach().numpy().copy()
+    out["regstep.valid_count"] = np.int64(rs[4].shape[0])
+    out["regstep.residual_cm"] = np.float64(rs[5])
+    # Mapper.dynamic_filter (utils/mapper.py:99-137) on the second scan in the world frame, both strategies
+    world_pts = (scans[1] + torch.tensor(poses[1][:3, 3], dtype=torch.float32)).contiguous()
+    dyn = world_pts[::3].clone()
+    mask2 = mapper.dynamic_filter(dyn.clone(), type_2_on=True)
+    mask1 = mapper.dynamic_filter(dyn.clone(), type_2_on=False)
+    out["dyn.points"] = dyn.numpy().copy()
+    out["dyn.mask_type2"] = mask2.numpy().copy()
+    out["dyn.mask_type1"] = mask1.numpy().copy()
+    out["dyn.cfg"] = np.array([cfg.dynamic_certainty_thre, cfg.dynamic_sdf_ratio_thre, cfg.dynamic_min_grad_norm_thre,
+                               cfg.voxel_size_m], np.float64)
     name = name or f"track_{kind}"
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     err = np.linalg.norm(T.numpy()[:3, 3] - poses[1][:3, 3])
