@@ -311,6 +311,13 @@ typedef struct pinb200_map_train_opts {
   float* v_feat;
   float* m_dec;
   float* v_dec;
+  /* data-parallel training (one process per GPU, the batch sharded over the ranks): when nccl_comm != NULL and
+   * stages == 3, every iteration sums reduce_buf[0 .. reduce_count) over the ranks (ncclAllReduce on `stream`) between
+   * the backward kernels and the Adam kernels.  reduce_buf must cover grad_feat and grad_dec (the caller lays the
+   * gradient blocks out contiguously); grad_scale = 1/world makes the sum the global-batch mean gradient. */
+  void* nccl_comm;    /* from pinb200_nccl_init, or NULL */
+  float* reduce_buf;
+  int64_t reduce_count;
 } pinb200_map_train_opts;
 
 /* n_iter x [assemble_batch -> query_sdf(training) -> mapping_loss -> train_backward -> adam(decoder) -> adam(features)].
@@ -318,6 +325,14 @@ typedef struct pinb200_map_train_opts {
 int pinb200_map_iterations(const pinb200_map_view* map, const pinb200_decoder_view* dec, int32_t nn_k,
                            int32_t weighted_first, const pinb200_map_train_opts* t, const pinb200_query_out* out,
                            int32_t n_iter, void* stream);
+
+/* NCCL communicator owned by the library (libnccl is resolved with dlopen at first use; PyTorch has it loaded).
+ * Rank 0 creates the 128-byte unique id, the caller broadcasts it (e.g. torch.distributed), every rank calls
+ * pinb200_nccl_init.  Used by pinb200_map_iterations (pinb200_map_train_opts.nccl_comm) for the per-iteration
+ * gradient all-reduce of data-parallel map training over NVLink / NVSwitch. */
+int pinb200_nccl_unique_id(uint8_t* out128);
+int pinb200_nccl_init(const uint8_t* uid128, int32_t world, int32_t rank, void** comm_out);
+int pinb200_nccl_destroy(void* comm);
 
 /* Colour head of the training loss (utils/mapper.py:804-812, utils/loss.py:31-41): L1 between the predicted and
  * the measured colour on surface samples (|sdf_label| < surface_range), mean over (n_surface x Cc) elements,

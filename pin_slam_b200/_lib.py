@@ -65,7 +65,8 @@ class MapTrainOpts(C.Structure):
                 ("grad_scale", C.c_float), ("rows", c_f32p), ("label", c_f32p),
                 ("ts", c_i32p), ("weight", c_f32p), ("dloss", c_f32p), ("losses", c_f32p), ("feat", c_f32p),
                 ("dec_flat", c_f32p), ("grad_feat", c_f32p), ("grad_dec", c_f32p), ("m_feat", c_f32p),
-                ("v_feat", c_f32p), ("m_dec", c_f32p), ("v_dec", c_f32p)]
+                ("v_feat", c_f32p), ("m_dec", c_f32p), ("v_dec", c_f32p), ("nccl_comm", C.c_void_p),
+                ("reduce_buf", c_f32p), ("reduce_count", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/pinb200.h declares
@@ -101,6 +102,9 @@ SIGNATURES = {
                                            C.c_int32, C.c_void_p]),
     "pinb200_map_iterations": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.c_int32, C.c_int32,
                                          C.POINTER(MapTrainOpts), C.POINTER(QueryOut), C.c_int32, C.c_void_p]),
+    "pinb200_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pinb200_nccl_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pinb200_nccl_destroy": (C.c_int, [C.c_void_p]),
     "pinb200_color_loss": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p]),
 }

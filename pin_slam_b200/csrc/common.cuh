@@ -22,6 +22,7 @@ constexpr float IDW_EPS = 1e-15f;   // model/neural_points.py:665
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
+int nccl_allreduce_sum(void* comm, float* buf, int64_t count, cudaStream_t stream);  // collective.cu
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

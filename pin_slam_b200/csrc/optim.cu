@@ -255,6 +255,14 @@ extern "C" int pinb200_map_iterations(const pinb200_map_view* map, const pinb200
                                   weighted_first, t->grad_feat, t->grad_dec, stream);
       if (rc) return rc;
     }
+    if (do_fb && do_opt && t->nccl_comm) {  // data-parallel: sum the gradient blocks over the ranks, on this stream
+      if (!t->reduce_buf || t->reduce_count <= 0) {
+        set_error("map_iterations: nccl_comm needs reduce_buf / reduce_count");
+        return PINB200_ERR_BAD_ARG;
+      }
+      rc = nccl_allreduce_sum(t->nccl_comm, t->reduce_buf, t->reduce_count, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
     if (!do_opt) continue;
     const int step = t->first_step + it;
     if (t->train_decoder) {

@@ -384,7 +384,8 @@ def assemble_batch(coord_pool, label_pool, ts_pool, weight_pool, color_pool, ind
 def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weighted_first, coord_pool, label_pool,
                    ts_pool, weight_pool, index, decimation, eik_eps, sigma, weight_e, loss_weight_on, lr, beta1, beta2,
                    eps, weight_decay, train_decoder, first_step, feat, dec_flat, grad_feat, grad_dec, m_feat, v_feat,
-                   m_dec, v_dec, losses, work: dict, stages: int = 3, grad_scale: float = 1.0):
+                   m_dec, v_dec, losses, work: dict, stages: int = 3, grad_scale: float = 1.0, nccl_comm=None,
+                   reduce_buf=None):
     """The geometry-only training loop of Mapper.mapping in ONE host call (pinb200_map_iterations).
     `index` [n_iter, bs] int64 are the pre-drawn batch indices; scratch buffers live in `work`."""
     lib = _lib.load()
@@ -418,7 +419,41 @@ def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weig
     t.grad_feat, t.grad_dec = _ptr(grad_feat, torch.float32), _ptr(grad_dec, torch.float32)
     t.m_feat, t.v_feat = _ptr(m_feat, torch.float32), _ptr(v_feat, torch.float32)
     t.m_dec, t.v_dec = _ptr(m_dec, torch.float32), _ptr(v_dec, torch.float32)
+    if nccl_comm is not None:
+        t.nccl_comm, t.reduce_buf, t.reduce_count = nccl_comm.handle, _ptr(reduce_buf, torch.float32), reduce_buf.numel()
     rc = lib.pinb200_map_iterations(C.byref(mh.view), C.byref(dec.view), int(nn_k), int(bool(weighted_first)),
                                     C.byref(t), C.byref(qo), int(n_iter), _stream())
     _lib.check(rc, "pinb200_map_iterations")
     _count(n_iter * ((4 if stages & 1 else 0) + (2 if stages & 2 else 0)))
+
+
+class NcclComm:
+    """A NCCL communicator owned by libpinb200 (pinb200_nccl_init) over the ranks of the default torch.distributed
+    process group, which is only used to hand the 128-byte unique id from rank 0 to the others."""
+
+    _instance = None
+
+    def __init__(self, device):
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            _lib.check(lib.pinb200_nccl_unique_id(C.cast(buf, C.c_void_p)), "pinb200_nccl_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(device) if dist.get_backend() == "nccl" else uid
+        dist.broadcast(uid, src=0)
+        raw = (C.c_uint8 * 128)(*uid.cpu().tolist())
+        comm = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.pinb200_nccl_init(C.cast(raw, C.c_void_p), world, rank, C.byref(comm)), "pinb200_nccl_init")
+        self.handle, self.world, self.rank, self.device = comm, world, rank, torch.device(device)
+
+    @classmethod
+    def get(cls, device):
+        """One communicator per process (one process per GPU)."""
+        if cls._instance is None or cls._instance.device != torch.device(device):
+            cls._instance = cls(device)
+        return cls._instance

@@ -128,6 +128,7 @@ class Mapper:
         self.last_losses = None
         self._work = {}
         self._batch = {}
+        self.fused_allreduce = True  # data-parallel training: NCCL all-reduce issued by the library (one host call)
         self.init_pool()
 
     # ------------------------------------------------------------------ pool
@@ -367,6 +368,12 @@ class Mapper:
             mh, dh = npm.map_handle(True), self.sdf_mlp.handle()
             if not dist_on:
                 ops.map_iterations(mh, dh, iter_count, index=index, first_step=1, **kw)
+            elif torch.distributed.get_backend() == "nccl" and self.fused_allreduce:
+                # data parallel, still ONE host call: the library enqueues the NCCL all-reduce of `red` on the
+                # kernel stream between the backward and the Adam kernels of every iteration
+                comm = ops.NcclComm.get(dev)
+                ops.map_iterations(mh, dh, iter_count, index=index, first_step=1, grad_scale=1.0 / world,
+                                   nccl_comm=comm, reduce_buf=red, **kw)
             else:
                 for it in range(iter_count):
                     ops.map_iterations(mh, dh, 1, index=index[it:it + 1], first_step=it + 1, stages=1,
@@ -440,6 +447,13 @@ class Mapper:
             allreduce_map_statistics(cert_at_start, npm.local_point_certainties, npm.local_point_ts_update)
         self.last_losses = losses
         npm.assign_local_to_global()
+
+    def allreduce_floats(self):
+        """Size of the per-iteration data-parallel exchange (feature + decoder [+ colour] gradient blocks)."""
+        n = self.neural_points.local_geo_features.numel() + self.sdf_mlp.flat_parameters().numel()
+        if self.config.color_on and self.color_mlp is not None:
+            n += self.neural_points.local_color_features.numel() + self.color_mlp.flat_parameters().numel()
+        return n
 
     def bundle_adjustment(self, iter_count, window_size: int = 50, use_lie_group: bool = False):
         raise NotImplementedError("local bundle adjustment (pypose) is outside the B200 hot path (SURVEY.md section 2 #4)")

@@ -7,6 +7,7 @@ import torch
 from oracle import pin_oracle as po
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PARITY_SLACK = []  # filled by tests/test_cuda_parity.py::assert_rel_close, reported by tests/conftest.py
 
 
 def load_npz(name):
