@@ -355,6 +355,19 @@ int64_t pinb200_probe_index_scratch(int64_t buffer_size);
 int pinb200_build_probe_index(const pinb200_map_view* map, uint32_t* probe_words, float* probe_rec,
                               int32_t* probe_gid, int32_t* scratch, void* stream);
 
+/* Voxel down-sampling (utils/tools.py:583-626 voxel_down_sample_torch; with `value` != NULL :629-668
+ * voxel_down_sample_min_value_torch): per occupied voxel the index of the point with the smallest selection value
+ * (distance to the voxel centre, or value[i] >= 0), quantised to 1000 levels of its maximum, ties to the smaller
+ * index.  Writes the (voxel key, winner index) pairs of the occupied voxels to out_key / out_idx in ARBITRARY order
+ * and their number to scalars[7]; the caller sorts the pairs by key (the reference returns ascending key order).
+ * Workspaces: ws_keys / ws_best [table_size] 8-byte words with table_size = pinb200_voxel_table_size(n), scalars
+ * [8] i32, out_key / out_idx [>= number of voxels, n is always enough] i64.  Replaces torch.unique(return_inverse) +
+ * scatter_reduce over the whole frame by a lock-free hash set (one atomicCAS + one atomicMin per point). */
+int64_t pinb200_voxel_table_size(int64_t n);
+int pinb200_voxel_downsample(const float* points, int64_t n, float voxel_size, const float* value, int64_t* ws_keys,
+                             uint64_t* ws_best, int64_t table_size, int32_t* scalars, int64_t* out_key,
+                             int64_t* out_idx, void* stream);
+
 /* Batch assembly of one map-training iteration in ONE launch (utils/mapper.py:482-503 pool gathers +
  * :990-1002 the six +-eps shifted copies of every `decimation`-th sample):
  *   rows  [n + 6*ne, 3] = [ coord_pool[index] | x+e_x | x-e_x | x+e_y | x-e_y | x+e_z | x-e_z ],  ne = ceil(n/decimation)

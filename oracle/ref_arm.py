@@ -188,7 +188,7 @@ def run_frames(args):
     tracker = R.Tracker(cfg, npm, decoders)
     mapper = R.Mapper(cfg, dataset, npm, decoders)
     sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
-    travel, poses, times, errs = [0.0], [], [], []
+    travel, poses, times, errs, preps = [0.0], [], [], [], []
     for f in range(2 + args.frames):
         gt = S.trajectory_pose(f)
         scan = S.lidar_scan(gt, seed=f, device=dev)
@@ -217,20 +217,26 @@ def run_frames(args):
         dataset.processed_frame = f
         dataset.odom_poses = torch.stack(poses).cpu().numpy()
         npm.travel_dist = torch.tensor(travel, device=dev, dtype=cfg.dtype)
+        sync()
+        t0 = time.perf_counter()
         mapper.process_frame(scan, None, pose, f)
         sync()
+        prep_s = time.perf_counter() - t0
         t0 = time.perf_counter()
         mapper.mapping(100 if f == 0 else 5)
         sync()
         map_s = time.perf_counter() - t0
         if f >= 2:
             times.append((trk_s, map_s))
+            preps.append(prep_s)
         errs.append(float((pose[:3, 3].cpu() - gt[:3, 3]).norm()))
     trk = sorted(t for t, _ in times)[len(times) // 2]
     mp = sorted(m for _, m in times)[len(times) // 2]
     return ({
         "mode": "frames", "device": args.device, "frames": args.frames, "tracker_ms_median": trk * 1e3,
-        "mapping_ms_median": mp * 1e3, "frames_per_s": 1.0 / (trk + mp), "source_points": int(source.shape[0]),
+        "mapping_ms_median": mp * 1e3, "frames_per_s": 1.0 / (trk + mp),
+        "prep_ms_median": sorted(preps)[len(preps) // 2] * 1e3,
+        "frames_per_s_with_prep": 1.0 / (trk + mp + sorted(preps)[len(preps) // 2]), "source_points": int(source.shape[0]),
         "scan_points": int(scan.shape[0]), "local_map_points": int(npm.local_neural_points.shape[0]),
         "pool_samples": int(mapper.pool_sample_count), "translation_error_m_per_frame": [round(e, 4) for e in errs],
         "final_translation_error_m": errs[-1], "threads": torch.get_num_threads(), "torch": torch.__version__,

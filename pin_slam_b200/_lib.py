@@ -95,6 +95,9 @@ SIGNATURES = {
     "pinb200_probe_index_words": (C.c_int64, [C.c_int64]),
     "pinb200_probe_index_scratch": (C.c_int64, [C.c_int64]),
     "pinb200_build_probe_index": (C.c_int, [C.POINTER(MapView), C.c_void_p, c_f32p, c_i32p, c_i32p, C.c_void_p]),
+    "pinb200_voxel_table_size": (C.c_int64, [C.c_int64]),
+    "pinb200_voxel_downsample": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_f32p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           c_i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pinb200_assemble_batch": (C.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_int32, C.c_float, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_void_p]),
     "pinb200_track_iterations": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,

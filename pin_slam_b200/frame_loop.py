@@ -37,6 +37,7 @@ class FrameLoop:
         self.travel = [0.0]
         self.poses = []
         self.times = []  # (tracker_ms, mapping_ms) per frame
+        self.prep_times = []  # Mapper.process_frame (sampling, map growth, pool) per frame
         self.host_issue_times = []
 
     def preprocess(self, frame_id):
@@ -52,7 +53,7 @@ class FrameLoop:
     def step(self, frame_id, timed=True, map_iters=None):
         cfg, npm = self.cfg, self.neural_points
         gt, scan, source = self.preprocess(frame_id)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         if frame_id == 0:
             pose = gt.to(self.dev)
             trk_ms = trk_cpu_ms = 0.0
@@ -78,7 +79,9 @@ class FrameLoop:
         self.dataset.processed_frame = frame_id
         self.dataset.odom_poses = torch.stack(self.poses).cpu().numpy()
         npm.travel_dist = torch.tensor(self.travel, device=self.dev, dtype=cfg.dtype)
+        ev[4].record()
         self.mapper.process_frame(scan, None, pose, frame_id)
+        ev[5].record()
         n_iter = self.n_map_iter if map_iters is None else map_iters
         ev[2].record()
         c0 = time.perf_counter()
@@ -89,10 +92,12 @@ class FrameLoop:
         if frame_id > 0:
             trk_ms = ev[0].elapsed_time(ev[1])
         map_ms = ev[2].elapsed_time(ev[3])
+        prep_ms = ev[4].elapsed_time(ev[5])  # "mapping preparation" (T5-T4 of the reference's time_table)
         if timed:
             self.times.append((trk_ms, map_ms))
+            self.prep_times.append(prep_ms)
             self.host_issue_times.append((trk_cpu_ms, map_cpu_ms))  # host time to ISSUE the launches (no sync)
         err = float((pose[:3, 3].cpu() - gt[:3, 3]).norm())
-        return {"frame": frame_id, "tracker_ms": trk_ms, "mapping_ms": map_ms, "n_source": int(source.shape[0]),
+        return {"frame": frame_id, "tracker_ms": trk_ms, "mapping_ms": map_ms, "prep_ms": prep_ms, "n_source": int(source.shape[0]),
                 "n_scan": int(scan.shape[0]), "local_points": npm.local_count(), "pool": self.mapper.pool_sample_count,
                 "trans_err_m": err}

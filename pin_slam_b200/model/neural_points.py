@@ -44,7 +44,11 @@ def voxel_down_sample(points: torch.Tensor, voxel_size: float) -> torch.Tensor:
     Same selection rule and output order as the reference helper
     (utils/tools.py:583-626): voxel key x + y*v + z*v^2 over the offset grid,
     centre distance quantised to 1000 levels, ties broken by the smaller index,
-    result ordered by ascending voxel key."""
+    result ordered by ascending voxel key.  CUDA tensors go through pinb200_voxel_downsample (a lock-free hash set
+    instead of torch.unique over the whole frame: section 8 row f1); the torch formulation below is the CPU form
+    the golden fixtures pin."""
+    if points.is_cuda:
+        return ops.voxel_downsample(points, voxel_size)
     grid = torch.floor(points / voxel_size)
     centre = (grid + 0.5) * voxel_size
     dist = ((points - centre) ** 2).sum(dim=1) ** 0.5
@@ -65,6 +69,8 @@ def voxel_down_sample_min_value(points: torch.Tensor, voxel_size: float, value: 
     """Index of the point with the smallest `value` in each occupied voxel, `value` quantised to 1000 levels of its
     maximum and ties broken by the smaller index -- the selection rule of the reference helper
     (utils/tools.py:629-668 voxel_down_sample_min_value_torch), result ordered by ascending voxel key."""
+    if points.is_cuda:
+        return ops.voxel_downsample(points, voxel_size, value)
     origin = torch.floor(points.min(dim=0)[0] / voxel_size).long()
     g = torch.floor(points / voxel_size).long() - origin
     v = g.max()

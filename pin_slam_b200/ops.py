@@ -427,6 +427,29 @@ def map_iterations(mh: MapHandle, dec: DecoderHandle, n_iter: int, *, nn_k, weig
     _count(n_iter * ((4 if stages & 1 else 0) + (2 if stages & 2 else 0)))
 
 
+def voxel_downsample(points: torch.Tensor, voxel_size: float, value: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Index of the winning point of every occupied voxel, ascending voxel key (pinb200_voxel_downsample + a sort
+    of the few winners).  One host synchronisation (the voxel count), like the reference's torch.unique."""
+    lib = _lib.load()
+    pts = points.contiguous()
+    n, dev = pts.shape[0], pts.device
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=dev)
+    tsz = int(lib.pinb200_voxel_table_size(n))
+    ws = torch.empty((2 * tsz,), dtype=torch.int64, device=dev)
+    scal = torch.empty((8,), dtype=torch.int32, device=dev)
+    outs = torch.empty((2, n), dtype=torch.int64, device=dev)
+    val = None if value is None else value.to(torch.float32).contiguous()
+    rc = lib.pinb200_voxel_downsample(_ptr(pts, torch.float32), n, float(voxel_size), _ptr(val, torch.float32),
+                                      ws.data_ptr(), ws.data_ptr() + 8 * tsz, tsz, _ptr(scal), outs[0].data_ptr(),
+                                      outs[1].data_ptr(), _stream())
+    _lib.check(rc, "pinb200_voxel_downsample")
+    _count(3)
+    m = int(scal[7].item())
+    order = torch.argsort(outs[0, :m])
+    return outs[1, :m][order]
+
+
 class NcclComm:
     """A NCCL communicator owned by libpinb200 (pinb200_nccl_init) over the ranks of the default torch.distributed
     process group, which is only used to hand the 128-byte unique id from rank 0 to the others."""

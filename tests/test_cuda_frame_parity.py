@@ -305,3 +305,23 @@ def test_cuda_radius_search_with_time_filter_matches_reference():
     assert np.array_equal(d2.cpu().numpy(), fx["rs.dist2"])
     _, idxg = npm.radius_neighborhood_search(q, time_filtering=False)
     assert np.array_equal(idxg.cpu().numpy().astype(np.int32), fx["rs_nofilter.idx"])
+
+
+@pytest.mark.parametrize("n,voxel", [(65536, 0.08), (45000, 0.6), (3000, 0.4), (17, 0.4), (200000, 0.05)])
+def test_cuda_voxel_downsample_equals_reference_formulation(n, voxel):
+    """pinb200_voxel_downsample (hash set + compaction + sort of the winners) returns exactly what the reference's
+    unique / scatter-amin formulation returns (utils/tools.py:583-668): same winners, same ascending-key order, for the
+    centre-distance and the min-value variants, with duplicated points (ties -> smaller index)."""
+    from pin_slam_b200 import ops
+    from pin_slam_b200.model import neural_points as npmod
+
+    g = torch.Generator().manual_seed(n)
+    pts = (torch.rand(n, 3, generator=g) * torch.tensor([40.0, 30.0, 6.0]) - torch.tensor([20.0, 15.0, 1.0]))
+    pts[n // 2:n // 2 + n // 10] = pts[:n // 10]  # exact duplicates: ties on the quantised distance
+    val = torch.randint(0, 50, (n,), generator=g).float()
+    cpu_a = npmod.voxel_down_sample(pts, voxel)              # torch formulation (CPU tensors take that path)
+    cpu_b = npmod.voxel_down_sample_min_value(pts, voxel, val)
+    got_a = ops.voxel_downsample(pts.to(DEV), voxel)
+    got_b = ops.voxel_downsample(pts.to(DEV), voxel, val.to(DEV))
+    assert torch.equal(got_a.cpu(), cpu_a)
+    assert torch.equal(got_b.cpu(), cpu_b)
