@@ -368,6 +368,17 @@ int pinb200_voxel_downsample(const float* points, int64_t n, float voxel_size, c
                              uint64_t* ws_best, int64_t table_size, int32_t* scalars, int64_t* out_key,
                              int64_t* out_idx, void* stream);
 
+/* Window filter of the replay pool (utils/mapper.py:404-438): keeps the samples whose global coordinate lies within
+ * sqrt(radius2) of `origin` (device, 3 x fp64; the reference's fp32 - fp64 difference is evaluated in fp64) and writes
+ * them, ORDER PRESERVED, to the o_* arrays (a second arena: the call does not work in place).  counts (device, 2 x i64):
+ * [0] samples kept, [1] samples kept among the last n_tail (the current frame's).  scratch: pinb200_pool_filter_scratch(n)
+ * i32.  Replaces six boolean-mask indexings (six reallocations of multi-million-row tensors per frame). */
+int64_t pinb200_pool_filter_scratch(int64_t n);
+int pinb200_pool_filter(const float* coord, const float* gcoord, const float* label, const float* weight,
+                        const int32_t* ts, const float* color, int32_t color_channels, int64_t n, int64_t n_tail,
+                        const double* origin, double radius2, float* o_coord, float* o_gcoord, float* o_label,
+                        float* o_weight, int32_t* o_ts, float* o_color, int32_t* scratch, int64_t* counts, void* stream);
+
 /* Batch assembly of one map-training iteration in ONE launch (utils/mapper.py:482-503 pool gathers +
  * :990-1002 the six +-eps shifted copies of every `decimation`-th sample):
  *   rows  [n + 6*ne, 3] = [ coord_pool[index] | x+e_x | x-e_x | x+e_y | x-e_y | x+e_z | x-e_z ],  ne = ceil(n/decimation)

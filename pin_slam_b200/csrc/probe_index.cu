@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace pinb {
 
@@ -47,31 +48,6 @@ __global__ void probe_mark_kernel(const __grid_constant__ pinb200_map_view m, ui
     if (view_id_of(m, i, x, y, z, td_cur) < 0) continue;
     atomicOr(words + 2 * (size_t)(slot >> 5), 1u << (slot & 31));
   }
-}
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(FULL, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(FULL, w, o);
-      if (lane >= o) w += t;
-    }
-    s_warp[32 + lane] = w;  // inclusive over warps
-  }
-  __syncthreads();
-  total = s_warp[32 + (blockDim.x >> 5) - 1];
-  const int warp_off = warp == 0 ? 0 : s_warp[32 + warp - 1];
-  return warp_off + inc - v;
 }
 
 __global__ void __launch_bounds__(SCAN_TPB) probe_blocksum_kernel(const uint32_t* __restrict__ words, long long n_words,

@@ -102,6 +102,88 @@ def _transform(points, pose):
     return points @ p[:3, :3].T + p[:3, 3]
 
 
+class _PoolArena:
+    """Fixed-capacity storage behind the replay-pool tensors.  The reference grows the
+    pool with `torch.cat` and filters it with boolean masks: six multi-million-row reallocations per frame.  Here the
+    public pool attributes of `Mapper` are views `[:count]` of one of two arenas: appending copies the new samples in
+    place, the window filter compacts from the active arena into the other one (pinb200_pool_filter) and swaps."""
+
+    FIELDS = (("coord", 3, torch.float32), ("gcoord", 3, torch.float32), ("label", 0, torch.float32),
+              ("weight", 0, torch.float32), ("ts", 0, torch.int32))
+
+    def __init__(self, device, color_channels: int, capacity_hint: int = 0):
+        self.device, self.cc, self.hint = device, int(color_channels), int(capacity_hint)
+        self.bufs, self.cap, self.count, self.cur = [None, None], 0, 0, 0
+        self.scratch = self.counts = None
+
+    def _alloc(self, cap):
+        d = {n: torch.empty((cap, w) if w else (cap,), dtype=dt, device=self.device) for n, w, dt in self.FIELDS}
+        d["color"] = torch.empty((cap, self.cc), dtype=torch.float32, device=self.device) if self.cc else None
+        return d
+
+    def reserve(self, need):
+        if need <= self.cap and self.bufs[0] is not None:
+            return
+        # sized once for the configured pool capacity (config.pool_capacity samples + one frame of new samples: 36-48
+        # bytes per sample, 1.5 GB for the 2e7-sample KITTI pool) so that a run never re-allocates: a cudaMalloc of a
+        # few hundred MB costs ~25 ms, more than a whole frame
+        cap = max(int(need * 1.5), 1 << 20, self.hint)
+        old = self.bufs[self.cur]
+        self.bufs = [self._alloc(cap), self._alloc(cap)]
+        if old is not None and self.count:
+            for n, t in old.items():
+                if t is not None:
+                    self.bufs[0][n][: self.count].copy_(t[: self.count])
+        self.cap, self.cur = cap, 0
+
+    def view(self, name):
+        t = self.bufs[self.cur][name]
+        return None if t is None else t[: self.count]
+
+    def owns(self, name, t):
+        b = None if self.bufs[self.cur] is None else self.bufs[self.cur][name]
+        return b is not None and t is not None and t.data_ptr() == b.data_ptr() and t.shape[0] == self.count
+
+    def load(self, tensors: dict):
+        """Adopt pool tensors that were assigned from outside (tests, checkpoints, transform_data_pool)."""
+        n = tensors["label"].shape[0]
+        self.count = 0
+        self.reserve(n)
+        for name, t in tensors.items():
+            if t is not None and self.bufs[self.cur][name] is not None:
+                self.bufs[self.cur][name][:n].copy_(t)
+        self.count = n
+
+    def append(self, new: dict):
+        n = new["label"].shape[0]
+        self.reserve(self.count + n)
+        for name, t in new.items():
+            if t is not None and self.bufs[self.cur][name] is not None:
+                self.bufs[self.cur][name][self.count: self.count + n].copy_(t)
+        self.count += n
+
+    def filter_window(self, origin64, radius2, n_tail):
+        """Order-preserving compaction into the other arena; returns (kept, kept among the last n_tail) as ints."""
+        lib = ops._lib.load()
+        n = self.count
+        need = int(lib.pinb200_pool_filter_scratch(max(n, 1)))
+        if self.scratch is None or self.scratch.numel() < need:
+            self.scratch = torch.empty((need,), dtype=torch.int32, device=self.device)
+            self.counts = torch.empty((2,), dtype=torch.int64, device=self.device)
+        a, b = self.bufs[self.cur], self.bufs[1 - self.cur]
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        rc = lib.pinb200_pool_filter(p(a["coord"]), p(a["gcoord"]), p(a["label"]), p(a["weight"]), p(a["ts"]), p(a["color"]),
+                                     self.cc, n, int(n_tail), origin64.data_ptr(), float(radius2), p(b["coord"]),
+                                     p(b["gcoord"]), p(b["label"]), p(b["weight"]), p(b["ts"]), p(b["color"]),
+                                     self.scratch.data_ptr(), self.counts.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+        ops._lib.check(rc, "pinb200_pool_filter")
+        ops._count(3)
+        kept, tail = (int(v) for v in self.counts.tolist())  # the one host sync of the filter
+        self.cur, self.count = 1 - self.cur, kept
+        return kept, tail
+
+
 class Mapper:
     def __init__(self, config, dataset, neural_points, decoders: dict):
         self.config = config
@@ -212,20 +294,54 @@ class Mapper:
         self.cur_new_point_ratio = self.neural_points.update(grow_pts, origin, orient, frame_id)
         self.neural_points.record_memory(verbose=(not self.silence))
 
-        self.coord_pool = torch.cat((self.coord_pool, coord), 0)
-        self.weight_pool = torch.cat((self.weight_pool, weight), 0)
-        self.sdf_label_pool = torch.cat((self.sdf_label_pool, label), 0)
-        self.time_pool = torch.cat((self.time_pool, stamps), 0)
-        self.color_pool = torch.cat((self.color_pool, color_label), 0) if color_label is not None else None
         self.determine_used_pose()
-        if self.ba_done_flag:
-            tf = self.used_poses[self.time_pool.long()].to(self.coord_pool)
-            self.global_coord_pool = (tf[:, :3, :3] @ self.coord_pool.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
-            self.ba_done_flag = False
+        on_gpu = coord.is_cuda
+        if on_gpu:
+            # fixed-capacity arenas behind the pool tensors (no per-frame reallocation), pinb200_pool_filter below
+            P = self.__dict__.get("_pool")
+            cc = 0 if color_label is None else color_label.shape[1]
+            if P is None or P.cc != cc:
+                P = self._pool = _PoolArena(self.device, cc, min(int(cfg.pool_capacity), 30_000_000) + 2_000_000)
+            cur = {"coord": self.coord_pool, "gcoord": self.global_coord_pool, "label": self.sdf_label_pool,
+                   "weight": self.weight_pool, "ts": self.time_pool, "color": self.color_pool if cc else None}
+            if not all(P.owns(k, v) for k, v in cur.items() if v is not None and (k != "color" or cc)):
+                P.load(cur)
+            P.append({"coord": coord, "gcoord": _transform(coord, cur_pose_torch), "label": label, "weight": weight,
+                      "ts": stamps, "color": color_label})
+            self._bind_pool(P)
+            if self.ba_done_flag:
+                tf = self.used_poses[self.time_pool.long()].to(self.coord_pool)
+                self.global_coord_pool.copy_((tf[:, :3, :3] @ self.coord_pool.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3])
+                self.ba_done_flag = False
         else:
-            self.global_coord_pool = torch.cat((self.global_coord_pool, _transform(coord, cur_pose_torch)), 0)
+            self.coord_pool = torch.cat((self.coord_pool, coord), 0)
+            self.weight_pool = torch.cat((self.weight_pool, weight), 0)
+            self.sdf_label_pool = torch.cat((self.sdf_label_pool, label), 0)
+            self.time_pool = torch.cat((self.time_pool, stamps), 0)
+            self.color_pool = torch.cat((self.color_pool, color_label), 0) if color_label is not None else None
+            if self.ba_done_flag:
+                tf = self.used_poses[self.time_pool.long()].to(self.coord_pool)
+                self.global_coord_pool = (tf[:, :3, :3] @ self.coord_pool.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+                self.ba_done_flag = False
+            else:
+                self.global_coord_pool = torch.cat((self.global_coord_pool, _transform(coord, cur_pose_torch)), 0)
 
-        if (frame_id + 1) % cfg.pool_filter_freq == 0:
+        if (frame_id + 1) % cfg.pool_filter_freq == 0 and on_gpu:
+            kept, tail = P.filter_window(origin.to(torch.float64).contiguous(), cfg.window_radius**2, self.cur_sample_count)
+            self._bind_pool(P)
+            self.cur_sample_count, self.pool_sample_count = tail, kept
+            if kept > cfg.pool_capacity:  # rare: random down-sampling of an over-full window (mapper.py:418-424)
+                drop = torch.randint(0, kept, (kept - cfg.pool_capacity,), device=self.device)
+                keep = torch.ones(kept, dtype=torch.bool, device=self.device)
+                keep[drop] = False
+                tens = {"coord": self.coord_pool[keep], "gcoord": self.global_coord_pool[keep],
+                        "label": self.sdf_label_pool[keep], "weight": self.weight_pool[keep], "ts": self.time_pool[keep],
+                        "color": self.color_pool[keep] if P.cc else None}
+                self.cur_sample_count = int(keep[-self.cur_sample_count:].sum().item())
+                P.load(tens)
+                self._bind_pool(P)
+                self.pool_sample_count = P.count
+        elif (frame_id + 1) % cfg.pool_filter_freq == 0:
             keep = ((self.global_coord_pool - origin) ** 2).sum(-1) < cfg.window_radius**2
             alive = torch.nonzero(keep).squeeze(-1)
             if alive.shape[0] > cfg.pool_capacity:
@@ -262,6 +378,11 @@ class Mapper:
                     self.adaptive_iter_offset = 5
                     if frame_id > cfg.freeze_after_frame and ratio > cfg.new_sample_ratio_restart:
                         self.adaptive_iter_offset = 10
+
+    def _bind_pool(self, P):
+        self.coord_pool, self.global_coord_pool = P.view("coord"), P.view("gcoord")
+        self.sdf_label_pool, self.weight_pool, self.time_pool = P.view("label"), P.view("weight"), P.view("ts")
+        self.color_pool = P.view("color") if P.cc else None
 
     # ------------------------------------------------------------------ batches
     def draw_batch_index(self, bs=None):
