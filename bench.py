@@ -247,6 +247,71 @@ def frame_benchmark(dev, n_frames=12, warm_iters=100):
     return out
 
 
+def replica_benchmark(dev, n_frames=8, n_track_iter=10, n_map_iter=20):
+    """BASELINE configs[3]: Replica-shaped RGB-D frames (640 x 480 pinhole depth + colour of an analytic room),
+    run_replica.yaml parameters: colour decoder head on, K = 6, F = 8, photometric point-to-implicit registration
+    (fixed `n_track_iter` GN iterations, no host sync) + `n_map_iter` map-training iterations (SDF + colour branches)
+    per frame; and the dense per-pixel query (SDF + colour + both gradients) of a whole frame as a K1 roofline."""
+    import torch
+
+    from pin_slam_b200 import ops
+    from pin_slam_b200.frame_loop import FrameLoop
+
+    loop = FrameLoop(device=dev, rgbd=True, n_track_iter=n_track_iter, n_map_iter=n_map_iter)
+    loop.step(0, timed=False, map_iters=100)
+    loop.step(1, timed=False)
+    l0 = ops.launch_count()
+    info = [loop.step(f) for f in range(2, 2 + n_frames)]
+    launches = (ops.launch_count() - l0) / n_frames
+    med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731
+    trk, mp, prep = med([t for t, _ in loop.times]), med([m for _, m in loop.times]), med(loop.prep_times)
+    out = {"workload": "BASELINE configs[3]: Replica-shaped RGB-D, 640x480 depth + colour, run_replica.yaml (voxel 0.05 m, "
+                       "K=6, F=8, 1x64 SDF + colour decoders, weighted_first, photometric GN x%d + mapper x%d per frame)"
+                       % (n_track_iter, n_map_iter),
+           "frames": n_frames, "frame_pixels": int(loop.last_frame_points), "tracker_ms_median": trk,
+           "mapping_ms_median": mp, "prep_ms_median": prep, "frames_per_s": 1000.0 / (trk + mp),
+           "frames_per_s_with_prep": 1000.0 / (trk + mp + prep), "kernel_launches_per_frame": launches,
+           "source_points": info[-1]["n_source"], "scan_points": info[-1]["n_scan"],
+           "local_map_points": info[-1]["local_points"], "pool_samples": info[-1]["pool"],
+           "translation_error_m_per_frame": [round(i["trans_err_m"], 4) for i in info]}
+    # dense per-pixel query of one frame: SDF + colour heads with both gradients
+    from pin_slam_b200.synthetic import rgbd_frame, rgbd_pose
+
+    npm, cfg = loop.neural_points, loop.cfg
+    gt = rgbd_pose(2 + n_frames)
+    pts, _ = rgbd_frame(gt, seed=99, device=dev)
+    world = (pts @ gt[:3, :3].float().to(dev).T + gt[:3, 3].float().to(dev)).contiguous()
+    n = world.shape[0]
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    o = {}
+    fn = lambda: npm.query_sdf(world, loop.sdf_mlp, need_grad=True, color_decoder=loop.color_mlp, color_grad=True, out=o)  # noqa: E731
+    for _ in range(3):
+        fn()
+    ms = []
+    for _ in range(8):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    t = sorted(ms)[4]
+    _, idx = ops.radius_search(npm.map_handle(False), world[:50000].contiguous())
+    n_occ = float((idx >= 0).sum(1).float().mean())
+    k_v = float(torch.clamp(o["nn_count"], max=cfg.query_nn_k).float().mean())
+    # SURVEY 8(d) with the colour head on: two feature rows per neighbour, colour (3) + colour gradient (9) outputs
+    bq = 12 + 4 * npm.neighbor_K + 16 * n_occ + k_v * (2 * 4 * cfg.feature_dim + 4) + 28 + 4 * (3 + 9)
+    peak, _ = hbm_peak()
+    ach = bq * n / (t * 1e-3) / 1e9
+    out["dense_query"] = {"pixels": n, "ms": t, "bytes_per_query": round(bq, 1), "occupied_probes_mean": round(n_occ, 2),
+                          "valid_knn_mean": round(k_v, 2),
+                          "kernels": "pinb::search_kernel + pinb::decode_umma_kernel<8> (SDF) + pinb::decode_umma_kernel<8> "
+                                     "(colour, 3 backward passes)",
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+    return out
+
+
 def mapper_benchmark(args, standalone=True):
     """BASELINE configs[4]: mapper-only data-parallel training.  A 2M-sample replay pool sharded over the ranks,
     per-GPU batch 16384 (weak scaling), K1 forward + loss heads + K2 backward + ONE NCCL all-reduce of
@@ -563,6 +628,12 @@ def main():
                 line["per_frame"] = frame_benchmark(dev)
             except Exception as e:  # noqa: BLE001
                 line["per_frame"] = {"error": repr(e)[:300]}
+            try:
+                line["per_frame_replica"] = replica_benchmark(dev)
+            except Exception as e:  # noqa: BLE001
+                import traceback
+
+                line["per_frame_replica"] = {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -130,6 +130,20 @@ class HotPathConfig:
         return cls(**d)
 
     @classmethod
+    def replica(cls, **kw):
+        """config/rgbd_slam/run_replica.yaml of the reference: RGB-D, colour head, photometric
+        tracking, weighted_first (default)."""
+        d = dict(voxel_size_m=0.05, weighted_first=True, feature_dim=8, query_nn_k=6, track_mask_query_nn_k=6,
+                 color_on=True, color_channel=3, sigma_sigmoid_m=0.01, weight_e=0.2, surface_sample_range_m=0.03,
+                 surface_sample_n=3, free_front_n=1, free_behind_n=1, free_sample_end_dist_m=0.1, bs_new_sample=4000,
+                 pool_capacity=int(2e7), pool_filter_freq=10, photometric_loss_on=True, photometric_loss_weight=0.01,
+                 eigenvalue_check=False, reg_min_grad_norm=0.4, reg_max_grad_norm=2.5, reg_GM_grad=0.3,
+                 reg_GM_dist_m=0.05, reg_term_thre_deg=1e-3, reg_term_thre_m=1e-4, reg_iter_n=50, iters=20,
+                 max_range=10.0, local_map_radius=12.0, window_radius=10.0)
+        d.update(kw)
+        return cls(**d)
+
+    @classmethod
     def cfg2(cls, **kw):
         """BASELINE.json configs[1]: 32-d features, K=8, 2-layer decoder."""
         d = dict(voxel_size_m=0.4, weighted_first=True, feature_dim=32, query_nn_k=8, track_mask_query_nn_k=8,

@@ -15,19 +15,24 @@ import torch
 from .config import HotPathConfig
 from .model import Decoder, NeuralPoints
 from .model.neural_points import voxel_down_sample
-from .synthetic import lidar_scan, trajectory_pose
+from .synthetic import lidar_scan, rgbd_frame, rgbd_pose, trajectory_pose
 from .utils.mapper import Mapper
 from .utils.tracker import Tracker
 
 
 class FrameLoop:
-    def __init__(self, device="cuda", n_track_iter=3, n_map_iter=5, seed=42, cfg=None):
-        self.cfg = cfg or HotPathConfig.kitti(device=str(device))
+    def __init__(self, device="cuda", n_track_iter=3, n_map_iter=5, seed=42, cfg=None, rgbd=False):
+        """`rgbd`: BASELINE configs[3] -- Replica-shaped 640 x 480 RGB-D frames, run_replica.yaml (colour head,
+        photometric registration); otherwise configs[2] -- 64 x 1024 KITTI-shaped scans, run_kitti.yaml."""
+        self.rgbd = bool(rgbd)
+        self.cfg = cfg or (HotPathConfig.replica(device=str(device)) if rgbd else HotPathConfig.kitti(device=str(device)))
         self.dev = torch.device(device)
         torch.manual_seed(seed)
         self.neural_points = NeuralPoints(self.cfg)
         self.sdf_mlp = Decoder(self.cfg, self.cfg.geo_mlp_hidden_dim, self.cfg.geo_mlp_level, 1)
-        decoders = {"sdf": self.sdf_mlp, "semantic": None, "color": None}
+        self.color_mlp = Decoder(self.cfg, self.cfg.color_mlp_hidden_dim, self.cfg.color_mlp_level,
+                                 self.cfg.color_channel) if self.cfg.color_on else None
+        decoders = {"sdf": self.sdf_mlp, "semantic": None, "color": self.color_mlp}
         self.dataset = types.SimpleNamespace(processed_frame=0, odom_poses=np.zeros((0, 4, 4)), pgo_poses=None,
                                              gt_poses=None, gt_pose_provided=False, lose_track=False,
                                              stop_status=False, static_mask=None)
@@ -41,7 +46,16 @@ class FrameLoop:
         self.host_issue_times = []
 
     def preprocess(self, frame_id):
-        """Synthetic scan -> voxel(0.08) + range crop -> map points; voxel(0.6) -> registration source."""
+        """Synthetic scan -> voxel(0.08) + range crop -> map points; voxel(0.6) -> registration source.
+        RGB-D: voxel(0.02) -> map points [x, y, z, r, g, b]; voxel(0.06) -> source (run_replica.yaml)."""
+        if self.rgbd:
+            gt = rgbd_pose(frame_id)
+            pts, col = rgbd_frame(gt, seed=frame_id, device=self.dev)
+            self.last_frame_points = pts.shape[0]
+            keep = voxel_down_sample(pts, 0.02)
+            scan = torch.cat((pts[keep], col[keep]), 1)
+            source = scan[voxel_down_sample(scan[:, :3].contiguous(), 0.06)]
+            return gt, scan.contiguous(), source.contiguous()
         gt = trajectory_pose(frame_id)
         scan = lidar_scan(gt, seed=frame_id, device=self.dev)
         scan = scan[voxel_down_sample(scan, 0.08)]
@@ -62,12 +76,14 @@ class FrameLoop:
             # estimate comes from the synthetic trajectory (a real run starts from rest)
             last = self.poses[-1]
             if len(self.poses) < 2:
-                guess = (gt @ torch.linalg.inv(trajectory_pose(frame_id - 1))).to(self.dev) @ last
+                prev_gt = rgbd_pose(frame_id - 1) if self.rgbd else trajectory_pose(frame_id - 1)
+                guess = (gt @ torch.linalg.inv(prev_gt)).to(self.dev) @ last
             else:
                 guess = last @ torch.linalg.inv(self.poses[-2]) @ last
             ev[0].record()
             c0 = time.perf_counter()
-            pose, _ = self.tracker.track_fixed(source, guess, self.n_track_iter)
+            pose, _ = self.tracker.track_fixed(source[:, :3].contiguous(), guess, self.n_track_iter,
+                                               source_colors=source[:, 3:].contiguous() if self.rgbd else None)
             trk_cpu_ms = (time.perf_counter() - c0) * 1e3
             ev[1].record()
             pose = pose.clone()

@@ -134,3 +134,62 @@ def surface_queries(npm, n, seed, sigma=0.1):
     sel = torch.randint(0, npm.count(), (n,), generator=g).to(dev)
     off = (sigma * torch.randn(n, 3, generator=g)).to(dev)
     return (npm.neural_points[sel] + off).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[3]: Replica-shaped RGB-D frames (640 x 480 pinhole depth + colour) of an analytic room
+# ---------------------------------------------------------------------------
+ROOM = (6.0, 4.0, 3.0)  # x, y, z extent in metres, origin at the floor centre
+FURNITURE = [(-1.8, -1.0, 0.6, 0.5, 0.8), (1.5, 1.2, 0.8, 0.4, 0.45), (0.3, -1.4, 0.4, 0.4, 1.2),
+             (2.3, -0.9, 0.35, 0.6, 0.9), (-2.2, 1.3, 0.5, 0.45, 0.5)]  # (cx, cy, half_x, half_y, height)
+
+
+def surface_colour(p: torch.Tensor) -> torch.Tensor:
+    """Smooth analytic RGB texture in [0, 1] as a function of the world position."""
+    f = torch.tensor([[1.3, 0.7, 2.1], [0.9, 1.9, 0.5], [2.3, 1.1, 1.7]], device=p.device, dtype=p.dtype)
+    ph = torch.tensor([0.3, 1.1, 2.0], device=p.device, dtype=p.dtype)
+    return 0.5 + 0.45 * torch.sin(p @ f.T + ph)
+
+
+def rgbd_pose(frame: int):
+    """Slow hand-held style trajectory inside the room: camera z forward, looking along +x, slightly down."""
+    T = torch.eye(4, dtype=torch.float64)
+    yaw = 0.02 * frame
+    c, s = math.cos(yaw), math.sin(yaw)
+    # camera axes in world: z_cam = forward (cos yaw, sin yaw, -0.15), x_cam = right, y_cam = down
+    fwd = torch.tensor([c, s, -0.15], dtype=torch.float64)
+    fwd = fwd / fwd.norm()
+    right = torch.linalg.cross(fwd, torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64))
+    right = right / right.norm()
+    down = torch.linalg.cross(fwd, right)
+    T[:3, 0], T[:3, 1], T[:3, 2] = right, down, fwd
+    T[0, 3] = -2.0 + 0.03 * frame
+    T[1, 3] = 0.2 * math.sin(0.1 * frame)
+    T[2, 3] = 1.4
+    return T
+
+
+def rgbd_frame(pose: torch.Tensor, seed: int, width=640, height=480, fx=525.0, fy=525.0, noise=0.002, max_range=10.0,
+               device="cpu"):
+    """Camera-frame points [<= H*W, 3] and colours [.., 3] of one RGB-D frame taken at `pose` (4x4, camera->world)."""
+    dev = torch.device(device)
+    g = torch.Generator().manual_seed(seed)
+    u = torch.arange(width, device=dev, dtype=torch.float32) - (width - 1) / 2
+    v = torch.arange(height, device=dev, dtype=torch.float32) - (height - 1) / 2
+    vv, uu = torch.meshgrid(v, u, indexing="ij")
+    d_c = torch.stack([uu / fx, vv / fy, torch.ones_like(uu)], -1).reshape(-1, 3)  # z = 1 plane: depth = t
+    rot, org = pose[:3, :3].float().to(dev), pose[:3, 3].float().to(dev)
+    d_w = d_c @ rot.T
+    o = org.expand_as(d_w)
+    hx, hy, hz = ROOM[0] / 2, ROOM[1] / 2, ROOM[2]
+    inv = 1.0 / torch.where(d_w.abs() < 1e-9, torch.full_like(d_w, 1e-9), d_w)
+    lo = torch.tensor([-hx, -hy, 0.0], device=dev)
+    hi = torch.tensor([hx, hy, hz], device=dev)
+    t = torch.maximum((lo - o) * inv, (hi - o) * inv).min(dim=1)[0]  # exit of the room box = wall / floor / ceiling
+    for cx, cy, bx, by, bh in FURNITURE:
+        t = torch.minimum(t, _ray_box(o, d_w, torch.tensor([cx - bx, cy - by, 0.0], device=dev),
+                                      torch.tensor([cx + bx, cy + by, bh], device=dev)))
+    ok = torch.isfinite(t) & (t < max_range) & (t > 0.05)
+    depth = t + (noise * torch.randn(t.shape, generator=g)).to(dev)
+    world = o + d_w * t.unsqueeze(1)
+    return (d_c * depth.unsqueeze(1))[ok].contiguous(), surface_colour(world)[ok].contiguous()
