@@ -126,6 +126,17 @@ typedef struct pinb200_query_opts {
 
 #define PINB200_SPLIT_MIN_QUERIES 32768
 int64_t pinb200_query_workspace_bytes(int64_t n_queries);
+/* Run-time tunables of the query path (process-wide; for tests and A/B measurements):
+     "split_min_queries"  batch size from which the two-launch pipeline is used (default PINB200_SPLIT_MIN_QUERIES;
+                          <= 0 restores the default)
+     "decode_variant"     0: phase-synchronous tcgen05 decode with backward MMAs (decode_umma_kernel)
+                          1: warp-specialised forward-mode decode (wsq_decode_kernel; default)
+     "ws_profile"         1: wsq_decode_kernel records per-warp phase cycle counters (pinb200_debug_read)
+   The reference has no equivalent: its decode is model/decoder.py:61-85 + autograd (utils/tools.py:247-260). */
+int pinb200_set_option(const char* name, int64_t value);
+/* Diagnostics.  "ws_profile": after pinb200_set_option("ws_profile", 1), every wsq_decode_kernel launch records per-warp
+   cycle counters; this copies them to `host_out` as uint64 [148 CTAs][20 warps][8 phases] (count = elements). */
+int pinb200_debug_read(const char* what, void* host_out, int64_t count);
 
 /* Outputs of the fused query; any pointer may be NULL to skip that output. */
 typedef struct pinb200_query_out {

@@ -76,6 +76,8 @@ SIGNATURES = {
     "pinb200_query_sdf": (C.c_int, [C.POINTER(MapView), C.POINTER(DecoderView), C.POINTER(DecoderView), c_f32p,
                                     c_i32p, C.c_int64, C.POINTER(QueryOpts), C.POINTER(QueryOut), C.c_void_p]),
     "pinb200_query_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "pinb200_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "pinb200_debug_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64]),
     "pinb200_knn_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, C.c_int32, c_i32p, c_i32p, c_f32p, c_f32p,
                                      c_i32p, C.c_void_p]),
     "pinb200_radius_search": (C.c_int, [C.POINTER(MapView), c_f32p, C.c_int64, c_f32p, c_i32p, C.c_void_p]),

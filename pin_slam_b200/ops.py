@@ -8,7 +8,15 @@ import torch
 from . import _lib
 from ._lib import DecoderView, GnOpts, MapTrainOpts, MapView, QueryOpts, QueryOut
 
-SPLIT_MIN_QUERIES = 32768  # == PINB200_SPLIT_MIN_QUERIES
+SPLIT_MIN_QUERIES = 32768  # == PINB200_SPLIT_MIN_QUERIES (default; see set_option)
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide tunables of the query path (pinb200_set_option): "split_min_queries", "decode_variant"."""
+    global SPLIT_MIN_QUERIES
+    _lib.check(_lib.load().pinb200_set_option(name.encode(), int(value)), "pinb200_set_option")
+    if name == "split_min_queries":
+        SPLIT_MIN_QUERIES = int(value) if int(value) > 0 else 32768
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
 

@@ -227,6 +227,55 @@ def test_fused_query_vs_oracle_synthetic(F, K, L, wf, pgo, C):
     assert torch.equal(out2["sdf"], out["sdf"])
 
 
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("F,K,L,pgo,color,leaky", [(32, 8, 2, False, False, False), (8, 6, 1, False, True, False),
+                                                   (16, 4, 2, True, False, False), (32, 8, 1, True, True, True),
+                                                   (8, 3, 2, False, False, True)])
+def test_split_pipeline_decoders_vs_oracle(F, K, L, pgo, color, leaky, variant):
+    """The two-launch pipeline (search_kernel -> tcgen05 decode) forced onto oracle-sized batches: the
+    warp-specialised forward-mode decode (variant 1, default) and the phase-synchronous decode with backward MMAs
+    (variant 0) against the oracle -- value, d/dq, colour head + its Jacobian, ragged last tile, queries without
+    neighbours, and the value-only launch (128-query tiles)."""
+    m = synthetic_map(n_surface=60000, seed=F + K, resolution=0.4, buffer_size=200003, feature_dim=F, color=color,
+                      after_pgo=pgo, local_radius=14.0, diff_td=3.0)
+    dec = po.make_decoder(F + 3, 64, L, 1, 0.044, seed=3)
+    cdec = po.make_decoder(F + 3, 64, L, 3, 1.0, seed=4) if color else None
+    if leaky:
+        dec.leaky = True
+        if cdec is not None:
+            cdec.leaky = True
+    q = queries_near(m, 20011, seed=5)
+    q[:16] = torch.tensor([300.0, -200.0, 50.0])  # no neighbours at all
+    kw = dict(color_dec=cdec, color_grad=True) if color else {}
+    ref = po.query_sdf(m, dec, q, K, True, **kw)
+    r64 = oracle64(m, dec, q, K, True, ref, **kw)
+    mh = map_handle_from_oracle(m, True)
+    dh = decoder_handle_from_oracle(dec)
+    ch = decoder_handle_from_oracle(cdec, sigmoid_out=True) if color else None
+    o = ops()
+    o.set_option("split_min_queries", 1)
+    o.set_option("decode_variant", variant)
+    try:
+        out = o.query_sdf(mh, dh, q.cuda(), nn_k=K, weighted_first=True, need_grad=True, color_dec=ch, color_grad=color)
+        out2 = o.query_sdf(mh, dh, q.cuda(), nn_k=K, weighted_first=True, need_grad=False, color_dec=ch)
+        torch.cuda.synchronize()
+    finally:
+        o.set_option("split_min_queries", 0)
+        o.set_option("decode_variant", 1)
+    assert np.array_equal(out["nn_count"].cpu().numpy(), ref["nn_count"].numpy())
+    assert_sdf_close(out["sdf"].cpu(), ref["sdf"], dec.sdf_scale)
+    assert_sdf_close(out2["sdf"].cpu(), ref["sdf"], dec.sdf_scale)
+    gscale = float(ref["grad"].abs().mean()) + 1e-12
+    assert_rel_close(out["grad"].cpu(), ref["grad"], 1e-4, gscale, r64["grad"], kink_rows=6)
+    assert float(out["sdf_std"].abs().max()) == 0.0
+    if color:
+        assert_sdf_close(out["color"].cpu(), ref["color"], 1.0)
+        assert_sdf_close(out2["color"].cpu(), ref["color"], 1.0)
+        cscale = float(ref["color_grad"].abs().mean()) + 1e-12
+        assert_rel_close(out["color_grad"].cpu(), ref["color_grad"], 1e-4, cscale, r64["color_grad"], kink_rows=8)
+
+
+
 def test_fused_transform_matches_pretransformed():
     m = synthetic_map(n_surface=30000, seed=1, buffer_size=100003, feature_dim=8)
     dec = po.make_decoder(11, 64, 1, 1, 0.044, seed=1)
