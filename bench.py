@@ -306,8 +306,8 @@ def replica_benchmark(dev, n_frames=8, n_track_iter=10, n_map_iter=20):
     ach = bq * n / (t * 1e-3) / 1e9
     out["dense_query"] = {"pixels": n, "ms": t, "bytes_per_query": round(bq, 1), "occupied_probes_mean": round(n_occ, 2),
                           "valid_knn_mean": round(k_v, 2),
-                          "kernels": "pinb::search_kernel + pinb::decode_umma_kernel<8> (SDF) + pinb::decode_umma_kernel<8> "
-                                     "(colour, 3 backward passes)",
+                          "kernels": "pinb::search_kernel + pinb::wsq_decode_kernel<8,true,false> (SDF + d/dq) + "
+                                     "pinb::wsq_decode_kernel<8,true,false> (colour head + its Jacobian, all 3 channels in one pass)",
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
     return out
 
@@ -514,7 +514,7 @@ def main():
     kernel_ms = sorted(step_ms)[len(step_ms) // 2]
     achieved = bq * N_QUERY / (ms_per_step * 1e-3) / 1e9
     split = N_QUERY >= ops.SPLIT_MIN_QUERIES
-    k1_kernels = ("pinb::search_kernel + pinb::decode_umma_kernel<%d>" % cfg.feature_dim) if split else \
+    k1_kernels = ("pinb::search_kernel + pinb::wsq_decode_kernel<%d,true,false>" % cfg.feature_dim) if split else \
         "pinb::query_kernel<%d,%s,false>" % (cfg.feature_dim, "true" if cfg.weighted_first else "false")
 
     line = None
@@ -533,8 +533,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": k1_kernels,
                          "kernel_ms_median": kernel_ms,
-                         "note": "K1 = the two launches of the query pipeline (neighbour search, then gather + tcgen05 "
-                                 "decoder); achieved = algorithmic bytes/query x queries / mean CUDA-event time of the "
+                         "note": "K1 = the two launches of the query pipeline (neighbour search, then the warp-specialised "
+                                 "gather + tcgen05 decoder with forward-mode d/dq); achieved = algorithmic bytes/query x "
+                                 "queries / mean CUDA-event time of the "
                                  "pipeline; traffic = dram bytes of both launches (ncu, profiles/k1_traffic.json)"},
             "clocks": clocks,
         }

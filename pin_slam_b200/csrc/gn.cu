@@ -2,8 +2,10 @@
 //   pass 1 (gn_accumulate_kernel): per source point validity mask, Geman-McClure
 //          robust weights and the 6x6 normal equations J^T W J / -J^T W r, reduced
 //          warp -> block -> fp64 atomics (27 unique scalars + 4 counters);
-//   pass 2 (gn_solve_kernel, one warp): weight normalisation w /= 2 mean(w),
-//          LM damping, fp64 6x6 solve, expmap, T <- dT @ T.
+//   pass 2 (gn_solve): weight normalisation w /= 2 mean(w), LM damping, fp64 6x6 solve,
+//          expmap, T <- dT @ T -- run by the LAST block of pass 1 to finish (threadfence +
+//          ticket counter), so a registration step is one launch; gn_solve_kernel remains
+//          for the empty-input case.
 // Replaces utils/tracker.py:409-524 (registration_step) and :652-679 (implicit_reg)
 // without any host synchronisation.
 #include <algorithm>
@@ -13,14 +15,18 @@
 
 namespace pinb {
 
-constexpr int GN_NSUM = 46;  // 36 N + 6 g + sum_w + sum|r| + count + sum w r^2
+constexpr int GN_NSUM = 46;    // 36 N + 6 g + sum_w + sum|r| + count + sum w r^2
+constexpr int GN_TICKET = 63;  // sums[63] (zeroed with the sums): finished-block counter of the fused solve
+__device__ void gn_solve(const double* sums, float lm_lambda, double* __restrict__ result, double* __restrict__ t_inout);
+__device__ __forceinline__ void gn_finish(double* sums, float lm_lambda, double* result, double* t_inout);
 
 __global__ void __launch_bounds__(256) gn_accumulate_kernel(
     const float* __restrict__ xyz, const float* __restrict__ sdf, const float* __restrict__ grad,
     const float* __restrict__ sdf_std, const int32_t* __restrict__ nn_count, const float* __restrict__ sdf_label,
     const float* __restrict__ normals, long long n, int min_nn, float min_gn, float max_gn, float max_std,
     float gm_dist, float gm_grad, const float* __restrict__ c_obs, const float* __restrict__ c_pred,
-    const float* __restrict__ c_grad, int cc, int color_mode, float w_photo, double* __restrict__ sums) {
+    const float* __restrict__ c_grad, int cc, int color_mode, float w_photo, double* __restrict__ sums, float lm_lambda,
+    double* __restrict__ result, double* __restrict__ t_inout) {
   // 21 upper-triangular entries of N, 6 of g, 5 scalars
   constexpr int NA = 32;
   float acc[NA];
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(256) gn_accumulate_kernel(
       atomicAdd(sums + 36 + (i - 21), t);
     }
   }
+  gn_finish(sums, lm_lambda, result, t_inout);
 }
 
 __device__ void expmap_d(const double* w, double* R) {  // tracker.py:784-795
@@ -191,9 +198,7 @@ __device__ void sym3_eig(const double* A, double* ev) {
   ev[1] = 3.0 * q - ev[0] - ev[2];
 }
 
-__global__ void gn_solve_kernel(const double* __restrict__ sums, float lm_lambda, double* __restrict__ result,
-                                double* __restrict__ t_inout) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void gn_solve(const double* sums, float lm_lambda, double* __restrict__ result, double* __restrict__ t_inout) {
   const double cnt = sums[44];
   double dT[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   for (int i = 0; i < 32; ++i) result[i] = 0.0;
@@ -271,6 +276,31 @@ __global__ void gn_solve_kernel(const double* __restrict__ sums, float lm_lambda
   }
 }
 
+__global__ void gn_solve_kernel(const double* __restrict__ sums, float lm_lambda, double* __restrict__ result,
+                                double* __restrict__ t_inout) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gn_solve(sums, lm_lambda, result, t_inout);
+}
+
+// the block that finishes last solves the normal equations (all other blocks' fp64 atomics are visible: every block
+// fences before it takes its ticket)
+__device__ __forceinline__ void gn_finish(double* sums, float lm_lambda, double* result, double* t_inout) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + GN_TICKET);
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double loc[GN_NSUM + 2];
+    for (int i = 0; i < GN_NSUM + 2; ++i) loc[i] = __ldcg(sums + i);  // written by L2 atomics: bypass L1
+    gn_solve(loc, lm_lambda, result, t_inout);
+  }
+}
+
 }  // namespace pinb
 
 using namespace pinb;
@@ -302,9 +332,9 @@ extern "C" int pinb200_gn_step(const float* xyz, const float* sdf, const float* 
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 2);
     gn_accumulate_kernel<<<grid, 256, 0, st>>>(xyz, sdf, grad, sdf_std, nn_count, sdf_label, normals, n, min_nn,
                                                min_grad_norm, max_grad_norm, max_sdf_std, gm_dist, gm_grad, color_obs, color_pred,
-                                               color_grad, color_channels, color_mode, w_photo, sums);
-    int rc = check_launch("gn_accumulate_kernel");
-    if (rc) return rc;
+                                               color_grad, color_channels, color_mode, w_photo, sums, lm_lambda, result,
+                                               t_inout);
+    return check_launch("gn_accumulate_kernel");
   }
   gn_solve_kernel<<<1, 32, 0, st>>>(sums, lm_lambda, result, t_inout);
   return check_launch("gn_solve_kernel");

@@ -32,10 +32,13 @@ constexpr int WS_GT = 2;       // gather teams of 4 warps: team t fills the A ti
 constexpr int WS_GW = 4;       // warps per gather team
 constexpr int WS_LW = 4;       // loader warps
 constexpr int WS_THREADS = (4 * WS_EG + WS_GT * WS_GW + WS_LW) * 32;
-// register budget per thread (setmaxnreg, one value per 4-warp group; 8*32*88 + 8*32*128 + 4*32*80 = 65536)
-constexpr int WS_REG_E = 88, WS_REG_G = 128, WS_REG_L = 80;
-constexpr int WS_A0 = 3;       // A-tile ring slots
-constexpr int WS_TCOLS = 192;  // TMEM columns per epilogue group: [0,64) D, [64,128) A1 hi, [128,192) A1 lo
+// register budget per thread (setmaxnreg, one value per 4-warp group).  The pool is what the CTA was launched with
+// (640 threads x 96 registers): 8*32*80 + 8*32*120 + 4*32*80 = 61440
+constexpr int WS_REG_E = 80, WS_REG_G = 120, WS_REG_L = 80;
+static_assert((4 * WS_EG * WS_REG_E + WS_GT * WS_GW * WS_REG_G + WS_LW * WS_REG_L) * 32 <= WS_THREADS * 96, "setmaxnreg pool");
+constexpr int WS_A0 = 2;       // A-tile ring slots, one per gather team / epilogue group pair: layer 0 of a tile is issued early,
+                               // so its slot is free again while the rest of the chain runs (3 slots measured the same)
+constexpr int WS_TCOLS = 256;  // TMEM columns per epilogue group: [0,64) D0, [64,128) A1 hi, [128,192) A1 lo, [192,256) D1
 
 struct WsMeta {  // float offsets inside a meta block of 32 queries, [field][k][lane]
   static constexpr int li = 0;                   // [8][32] neighbour id | REMAP, -1 invalid
@@ -54,8 +57,10 @@ struct WsLayout {  // byte offsets from the dynamic shared memory base
   int bars, tmem, total;
 };
 // mbarrier indices
+constexpr int WS_MB_MAX = 16;
 constexpr int WSB_A0_FULL = 0, WSB_A0_EMPTY = WSB_A0_FULL + WS_A0, WSB_META_FULL = WSB_A0_EMPTY + WS_A0,
-              WSB_META_EMPTY = WSB_META_FULL + 8, WSB_MMA = WSB_META_EMPTY + 8, WSB_COUNT = WSB_MMA + WS_EG;
+              WSB_META_EMPTY = WSB_META_FULL + WS_MB_MAX, WSB_MMA0 = WSB_META_EMPTY + WS_MB_MAX, WSB_MMA1 = WSB_MMA0 + WS_EG,
+              WSB_COUNT = WSB_MMA1 + WS_EG;
 
 // Optional cycle accounting (pinb200_set_option("ws_profile", 1)): per warp, clock64 deltas of up to 8 phases,
 // summed over the tiles of the launch; read back with pinb200_debug_read("ws_profile", ...).
@@ -63,27 +68,30 @@ constexpr int WS_PROF_SLOTS = 8;
 __device__ unsigned long long g_ws_prof[148 * (WS_THREADS / 32) * WS_PROF_SLOTS];
 static int g_ws_profile = 0;
 
-struct WsClock {
-  unsigned long long acc[WS_PROF_SLOTS];
-  long long last;
-  bool on;
-  __device__ __forceinline__ void start(bool enable) {
-    on = enable;
+template <bool PROF>
+struct WsClock {  // PROF = false: no code at all (64-bit counters in the production kernel spilled to local memory)
+  unsigned int acc[WS_PROF_SLOTS];
+  unsigned int last;
+  __device__ __forceinline__ void start() {
+    if (PROF) {
 #pragma unroll
-    for (int i = 0; i < WS_PROF_SLOTS; ++i) acc[i] = 0ull;
-    last = on ? clock64() : 0;
+      for (int i = 0; i < WS_PROF_SLOTS; ++i) acc[i] = 0u;
+      last = (unsigned int)clock();
+    }
   }
   __device__ __forceinline__ void lap(int slot) {
-    if (on) {
-      const long long now = clock64();
-      acc[slot] += (unsigned long long)(now - last);
+    if (PROF) {
+      const unsigned int now = (unsigned int)clock();
+      acc[slot] += now - last;
       last = now;
     }
   }
   __device__ __forceinline__ void flush(int warp) {
-    if (on && (threadIdx.x & 31) == 0 && blockIdx.x < 148) {
+    if (PROF) {
+      if ((threadIdx.x & 31) == 0 && blockIdx.x < 148) {
 #pragma unroll
-      for (int i = 0; i < WS_PROF_SLOTS; ++i) g_ws_prof[(blockIdx.x * (WS_THREADS / 32) + warp) * WS_PROF_SLOTS + i] = acc[i];
+        for (int i = 0; i < WS_PROF_SLOTS; ++i) g_ws_prof[(blockIdx.x * (WS_THREADS / 32) + warp) * WS_PROF_SLOTS + i] = acc[i];
+      }
     }
   }
 };
@@ -104,6 +112,22 @@ __device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity), "r"(1000000)  // <= 1 ms per attempt
         : "memory");
+  }
+  if (!done) __trap();
+}
+// ring waits of the producer roles (not latency critical): back off between attempts instead of re-polling
+__device__ __forceinline__ void ws_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (int it = 0; it < (1 << 22) && !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(1000000)
+        : "memory");
+    if (!done) __nanosleep(128);
   }
   if (!done) __trap();
 }
@@ -134,6 +158,32 @@ __device__ __forceinline__ void ws_tmem_st16(uint32_t taddr, const uint32_t (&v)
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+
+// TMEM load split into issue and wait, so that shared-memory loads can be put under its latency; the wait takes the
+// destination registers as in/out operands to keep their consumers behind it
+__device__ __forceinline__ void ws_tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void ws_tmem_ld_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])::"memory");
+}
+__device__ __forceinline__ void ws_lds16(const float* src, float (&b)[16]) {
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + 4 * e4);
+    b[4 * e4] = t.x;
+    b[4 * e4 + 1] = t.y;
+    b[4 * e4 + 2] = t.z;
+    b[4 * e4 + 3] = t.w;
+  }
 }
 
 // Meta block column of one query, from the search results (registers).  GRAD adds the forward-mode seeds:
@@ -225,19 +275,17 @@ __device__ __forceinline__ void ws_write_meta(const pinb200_map_view& m, int K, 
   }
 }
 
-template <int FT, bool GRAD>
-__global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_constant__ QueryParams p, const WsLayout lay,
-                                                                   const int profile) {
+template <int FT, bool GRAD, bool PROF>
+__global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_constant__ QueryParams p, const WsLayout lay) {
   constexpr int H = 64;
   using DM = UmmaDims<FT>;
   constexpr int K0 = DM::K0, F = FT, D = FT + 3;
   using M = RowMap<FT>;
   constexpr int QT = GRAD ? 32 : 128;   // queries per tile
   constexpr int BPT = QT / WT;          // meta blocks per tile
-  constexpr int MB = GRAD ? 4 : 8;      // meta ring slots
+  constexpr int MB = GRAD ? 8 : 16;     // meta ring slots (blocks of 32 queries; a value-only tile has 4)
   constexpr int MSTRIDE = GRAD ? WsMeta::floats_g : WsMeta::floats_ng;
   constexpr int NPASS = WT / M::RPP;    // gather passes per meta block (F = 32: 8 passes of 4 queries)
-  constexpr int GU = NPASS / WS_GW >= 2 ? 2 : 1;  // passes in flight per gather warp
   extern __shared__ __align__(1024) unsigned char ws_smem[];
   unsigned char* sm = ws_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -247,7 +295,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + lay.tmem);
   float* meta = reinterpret_cast<float*>(sm + lay.meta);
-  WsClock clk;
+  WsClock<PROF> clk;
 
   // ---- prologue (the only block-wide barrier): TMEM, mbarriers, decoder weights
   if (warp == 0) {
@@ -262,11 +310,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
       init(WSB_A0_FULL + s, WS_GW);
       init(WSB_A0_EMPTY + s, 1);
     }
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < WS_MB_MAX; ++s) {
       init(WSB_META_FULL + s, 1);
       init(WSB_META_EMPTY + s, WS_GW);
     }
-    for (int g = 0; g < WS_EG; ++g) init(WSB_MMA + g, 1);
+    for (int g = 0; g < WS_EG; ++g) {
+      init(WSB_MMA0 + g, 1);
+      init(WSB_MMA1 + g, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   um_stage_weight(p.dec.w[0], D, H, D, H, K0, false, sm + lay.w0_hi, sm + lay.w0_lo);
@@ -279,7 +330,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
   if (tid < 4) reinterpret_cast<float*>(sm + lay.bout)[tid] = (p.dec.b_out && tid < OC) ? __ldg(p.dec.b_out + tid) : 0.f;
   um_publish_and_sync();
   const uint32_t tmem_base = *s_tmem;
-  clk.start(profile != 0);
+  clk.start();
 
   const long long n_tiles = (p.n + QT - 1) / QT;
   const int n_blocks = p.n_tiles;  // 32-query stash blocks
@@ -287,16 +338,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
   if (warp < 4 * WS_EG) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_E));
     // =====================================================================================================
-    // E: epilogue group g owns the tiles i = g, g + 2, ... of this CTA
-    // profile slots: 0 group barrier, 1 wait A tile (issuing thread) + layer-0 MMAs, 2 layer-0 epilogue,
-    //                3 layer-1 MMAs, 4 last-layer epilogue + outputs
+    // E: epilogue group g owns the tiles i = g, g + 2, ... of this CTA.  Software pipeline over its tiles: layer 0
+    // of tile t+1 is issued right behind layer 1 of tile t (its own accumulator columns), so it runs under the
+    // last-layer epilogue of tile t.
+    // profile slots: 0 wait layer-0 MMAs, 1 layer-0 epilogue + group barrier, 2 MMA issue (+ wait for the next A tile),
+    //                3 wait layer-1 MMAs, 4 last-layer epilogue + outputs
     // =====================================================================================================
     const int g = warp >> 2, qd = warp & 3;
     const int r = qd * WT + lane;  // tile row == TMEM lane
     const uint32_t tb = tmem_base + g * WS_TCOLS;
     const uint32_t tl = tb + ((uint32_t)(qd * 32) << 16);
-    const uint32_t mma_bar = um_smem_u32(bars + WSB_MMA + g);
-    uint32_t mph = 0;
+    const uint32_t bar0 = um_smem_u32(bars + WSB_MMA0 + g), bar1 = um_smem_u32(bars + WSB_MMA1 + g);
+    uint32_t ph0 = 0, ph1 = 0;
     const int t = GRAD ? (lane & 3) : 0;  // row type: 0 value, 1..3 tangent d/dq_{t-1}
     const float bsel = t == 0 ? 1.f : 0.f;
     const int src = lane & ~3;  // the value row of this row's query
@@ -304,110 +357,139 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     const float* s_b1 = reinterpret_cast<const float*>(sm + lay.b1);
     const float* s_wout = reinterpret_cast<const float*>(sm + lay.wout);
     const float* s_bout = reinterpret_cast<const float*>(sm + lay.bout);
-    const uint32_t w0_hi = um_smem_u32(sm + lay.w0_hi), w0_lo = um_smem_u32(sm + lay.w0_lo);
-    const uint32_t w1_hi = um_smem_u32(sm + lay.w1_hi), w1_lo = um_smem_u32(sm + lay.w1_lo);
     constexpr uint32_t A_SBO0 = (K0 / 4) * UM_A_LBO, W_SBO0 = (K0 / 4) * UM_W_LBO, W_SBO1 = (H / 4) * UM_W_LBO;
+    // a k-step (8 columns = two 16-byte chunks) advances the start-address field of a descriptor by 2 * LBO / 16
+    constexpr uint64_t A_STEP = (2 * UM_A_LBO) >> 4, W_STEP = (2 * UM_W_LBO) >> 4;
+    const uint64_t w0h_d = um_desc(um_smem_u32(sm + lay.w0_hi), UM_W_LBO, W_SBO0), w0l_d = um_desc(um_smem_u32(sm + lay.w0_lo), UM_W_LBO, W_SBO0);
+    const uint64_t w1h_d = um_desc(um_smem_u32(sm + lay.w1_hi), UM_W_LBO, W_SBO1), w1l_d = um_desc(um_smem_u32(sm + lay.w1_lo), UM_W_LBO, W_SBO1);
     const uint32_t idesc = um_idesc(H);
-    int i = g;
-    for (long long T = blockIdx.x + (long long)g * gridDim.x; T < n_tiles; T += (long long)WS_EG * gridDim.x, i += WS_EG) {
-      const int slot = i % WS_A0;
-      // every row of the group has read the previous tile's accumulator before the next MMA overwrites it
-      ws_fence_before();
-      ws_group_bar(1 + g);
-      clk.lap(0);
-      if (qd == 0) ws_wait(um_smem_u32(bars + WSB_A0_FULL + slot), (uint32_t)(i / WS_A0) & 1u);
-      if (r == 0) {
+    const uint32_t td1 = L > 1 ? tb + 192 : tb;  // accumulator of the last hidden layer
+    const uint32_t tl1 = L > 1 ? tl + 192 : tl;
+
+    // layer 0 of the CTA's i-th tile (called by the group's first warp; lane 0 issues)
+    auto issue_l0 = [&](int ii) {
+      const int slot = ii % WS_A0;
+      ws_wait(um_smem_u32(bars + WSB_A0_FULL + slot), (uint32_t)(ii / WS_A0) & 1u);
+      if (lane == 0) {
         ws_fence_after();
-        const uint32_t a_hi = um_smem_u32(sm + lay.a0 + slot * lay.a0_stride), a_lo = a_hi + lay.a0_half;
-#pragma unroll 1
+        const uint32_t a_hi = um_smem_u32(sm + lay.a0 + slot * lay.a0_stride);
+        const uint64_t ah = um_desc(a_hi, UM_A_LBO, A_SBO0), al = um_desc(a_hi + lay.a0_half, UM_A_LBO, A_SBO0);
+#pragma unroll
         for (int s = 0; s < K0 / 8; ++s) {
-          const uint64_t ah = um_desc(a_hi + s * 2 * UM_A_LBO, UM_A_LBO, A_SBO0);
-          const uint64_t al = um_desc(a_lo + s * 2 * UM_A_LBO, UM_A_LBO, A_SBO0);
-          const uint64_t bh = um_desc(w0_hi + s * 2 * UM_W_LBO, UM_W_LBO, W_SBO0);
-          const uint64_t bl = um_desc(w0_lo + s * 2 * UM_W_LBO, UM_W_LBO, W_SBO0);
-          um_mma(tb, al, bh, idesc, s > 0);  // small terms first
-          um_mma(tb, ah, bl, idesc, 1);
-          um_mma(tb, ah, bh, idesc, 1);
+          um_mma(tb, al + s * A_STEP, w0h_d + s * W_STEP, idesc, s > 0);  // small terms first
+          um_mma(tb, ah + s * A_STEP, w0l_d + s * W_STEP, idesc, 1);
+          um_mma(tb, ah + s * A_STEP, w0h_d + s * W_STEP, idesc, 1);
         }
-        ws_commit(mma_bar);
+        ws_commit(bar0);
         ws_commit(um_smem_u32(bars + WSB_A0_EMPTY + slot));  // the A tile may be refilled once these MMAs have read it
       }
-      ws_wait(mma_bar, mph);
-      mph ^= 1u;
+      __syncwarp();
+    };
+    // bias (value rows) + ReLU gate of 16 accumulator columns.  The gate of a tangent row is the sign pattern of its
+    // query's value row: the 16 sign bits travel in ONE quad-leader shuffle per chunk.
+    auto gated16 = [&](const uint32_t (&v)[16], const float (&bb)[16], float (&z)[16]) {
+      uint32_t mk = 0u;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        z[e] = fmaf(bsel, bb[e], __uint_as_float(v[e]));
+        mk |= z[e] > 0.f ? (1u << e) : 0u;
+      }
+      if (GRAD) mk = __shfl_sync(FULL, mk, src);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) z[e] = ((mk >> e) & 1u) ? z[e] : slope * z[e];
+    };
+
+    int i = g;
+    long long T = blockIdx.x + (long long)g * gridDim.x;
+    if (T < n_tiles && qd == 0) issue_l0(i);
+    for (; T < n_tiles; T += (long long)WS_EG * gridDim.x, i += WS_EG) {
+      const bool has_next = T + (long long)WS_EG * gridDim.x < n_tiles;
+      ws_wait(bar0, ph0);
+      ph0 ^= 1u;
       ws_fence_after();
-      clk.lap(1);
+      clk.lap(0);
       if (L > 1) {
-        // ---- layer-0 epilogue: bias (value rows), ReLU gate of the query's value row, hi / lo split -> A1 in TMEM
+        // ---- layer-0 epilogue: gated activations, hi / lo split -> A1 in TMEM
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[16], hi[16], lo[16];
-          um_tmem_ld16(tl + 16 * c, v);
+          uint32_t v[16];
+          float z[16], bb[16];
+          ws_tmem_ld16_issue(tl + 16 * c, v);
+          ws_lds16(s_b0 + 16 * c, bb);  // under the TMEM load
+          ws_tmem_ld_wait(v);
+          gated16(v, bb, z);
+          uint32_t lo[16];
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 b = *reinterpret_cast<const float4*>(s_b0 + 16 * c + 4 * e4);
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float z = fmaf(bsel, bb[e], __uint_as_float(v[4 * e4 + e]));
-              const float zv = GRAD ? __shfl_sync(FULL, z, src) : z;
-              const float o = zv > 0.f ? z : slope * z;
-              const uint32_t h = __float_as_uint(o) & TF32_MASK;
-              hi[4 * e4 + e] = h;
-              lo[4 * e4 + e] = __float_as_uint(o - __uint_as_float(h));
-            }
+          for (int e = 0; e < 16; ++e) {
+            v[e] = __float_as_uint(z[e]) & TF32_MASK;
+            lo[e] = __float_as_uint(z[e] - __uint_as_float(v[e]));
           }
-          ws_tmem_st16(tl + 64 + 16 * c, hi);
+          ws_tmem_st16(tl + 64 + 16 * c, v);
           ws_tmem_st16(tl + 128 + 16 * c, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // every row has written its A1 columns and has read its D0 columns
         ws_fence_before();
         ws_group_bar(1 + g);
-        clk.lap(2);
-        if (r == 0) {
-          ws_fence_after();
-#pragma unroll 1
-          for (int s = 0; s < H / 8; ++s) {
-            const uint64_t bh = um_desc(w1_hi + s * 2 * UM_W_LBO, UM_W_LBO, W_SBO1);
-            const uint64_t bl = um_desc(w1_lo + s * 2 * UM_W_LBO, UM_W_LBO, W_SBO1);
-            ws_mma_ts(tb, tb + 128 + 8 * s, bh, idesc, s > 0);
-            ws_mma_ts(tb, tb + 64 + 8 * s, bl, idesc, 1);
-            ws_mma_ts(tb, tb + 64 + 8 * s, bh, idesc, 1);
+        clk.lap(1);
+        if (qd == 0) {
+          if (lane == 0) {
+            ws_fence_after();
+#pragma unroll
+            for (int s = 0; s < H / 8; ++s) {
+              ws_mma_ts(td1, tb + 128 + 8 * s, w1h_d + s * W_STEP, idesc, s > 0);
+              ws_mma_ts(td1, tb + 64 + 8 * s, w1l_d + s * W_STEP, idesc, 1);
+              ws_mma_ts(td1, tb + 64 + 8 * s, w1h_d + s * W_STEP, idesc, 1);
+            }
+            ws_commit(bar1);
           }
-          ws_commit(mma_bar);
+          __syncwarp();
+          if (has_next) issue_l0(i + WS_EG);  // runs behind layer 1 on the tensor pipe, under this tile's last epilogue
         }
-        ws_wait(mma_bar, mph);
-        mph ^= 1u;
+        clk.lap(2);
+        ws_wait(bar1, ph1);
+        ph1 ^= 1u;
         ws_fence_after();
         clk.lap(3);
       }
-      // ---- last hidden layer: bias, gate, output head(s) in registers
+      // ---- last hidden layer: gated activations, output head(s) in registers
       float o[4] = {0.f, 0.f, 0.f, 0.f};
       {
         const float* bl = L > 1 ? s_b1 : s_b0;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[16];
-          um_tmem_ld16(tl + 16 * c, v);
+        for (int c = 0; c < 2; ++c) {  // 32 columns per step: two TMEM loads and their bias rows in flight together
+          uint32_t va[16], vb[16];
+          float za[16], zb[16];
+          ws_tmem_ld16_issue(tl1 + 32 * c, va);
+          ws_tmem_ld16_issue(tl1 + 32 * c + 16, vb);
+          ws_lds16(bl + 32 * c, za);
+          ws_lds16(bl + 32 * c + 16, zb);
+          ws_tmem_ld_wait(va);
+          ws_tmem_ld_wait(vb);
+          gated16(va, za, za);
+          gated16(vb, zb, zb);
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 b = *reinterpret_cast<const float4*>(bl + 16 * c + 4 * e4);
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-            float hh[4];
+          for (int ch = 0; ch < 4; ++ch)
+            if (ch < OC) {
+              float wa[16], wb[16];
+              ws_lds16(s_wout + ch * H + 32 * c, wa);
+              ws_lds16(s_wout + ch * H + 32 * c + 16, wb);
+              float oa = 0.f, ob = 0.f;  // two independent chains
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float z = fmaf(bsel, bb[e], __uint_as_float(v[4 * e4 + e]));
-              const float zv = GRAD ? __shfl_sync(FULL, z, src) : z;
-              hh[e] = zv > 0.f ? z : slope * z;
-            }
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              if (ch < OC) {
-                const float4 wo = *reinterpret_cast<const float4*>(s_wout + ch * H + 16 * c + 4 * e4);
-                o[ch] = fmaf(hh[3], wo.w, fmaf(hh[2], wo.z, fmaf(hh[1], wo.y, fmaf(hh[0], wo.x, o[ch]))));
+              for (int e = 0; e < 16; ++e) {
+                oa = fmaf(za[e], wa[e], oa);
+                ob = fmaf(zb[e], wb[e], ob);
               }
-          }
+              o[ch] += oa + ob;
+            }
         }
       }
+      if (L == 1) {  // single hidden layer: the next tile's layer 0 overwrites the accumulator every row just read
+        ws_fence_before();
+        ws_group_bar(1 + g);
+        if (qd == 0 && has_next) issue_l0(i + WS_EG);
+      }
+      clk.lap(4);
       // ---- outputs: value rows write the prediction, tangent rows one component of its gradient
       const int ql = GRAD ? (r >> 2) : r;
       const long long qi = T * QT + ql;
@@ -444,29 +526,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
             }
           }
         }
-      clk.lap(4);
+      clk.lap(5);
     }
   } else if (warp < 4 * WS_EG + WS_GT * WS_GW) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_G));
     // =====================================================================================================
-    // G: gather teams -- the 4 warps of a team work on the same tile, each on its share of the queries
+    // G: gather teams -- the 4 warps of a team work on the same tile, each on its share of the queries: per round a
+    // lane has GU passes x K feature-row loads (16 x LDG.128 for F = 32) in flight; the two teams (and the ring of A
+    // tiles) overlap one team's load latency with the other team's reduction.  (A register double buffer over the
+    // passes of ONE warp was tried: it spills inside the loop at 120 registers and lost 5 %.)
     // profile slots: 0 wait free A tile, 1 wait meta block, 2 feature-row loads issued, 3 reduce + A-tile stores,
     //                4 position rows + fence + arrive
     // =====================================================================================================
     const int team = (warp - 4 * WS_EG) / WS_GW, gw = (warp - 4 * WS_EG) % WS_GW;
     const int sub = lane / M::LPR, c4 = lane % M::LPR;
     const float4* __restrict__ f4 = reinterpret_cast<const float4*>(p.feat) + c4;
+    constexpr int GU = NPASS / WS_GW >= 2 ? 2 : 1;  // passes in flight per gather warp
     int i = team;
     for (long long T = blockIdx.x + (long long)team * gridDim.x; T < n_tiles; T += (long long)WS_GT * gridDim.x, i += WS_GT) {
       const int slot = i % WS_A0;
-      ws_wait(um_smem_u32(bars + WSB_A0_EMPTY + slot), ((uint32_t)(i / WS_A0) & 1u) ^ 1u);
-      clk.lap(0);
       unsigned char* a_hi = sm + lay.a0 + slot * lay.a0_stride;
       unsigned char* a_lo = a_hi + lay.a0_half;
+      bool slot_free = false;
 #pragma unroll 1
       for (int b = 0; b < BPT; ++b) {
         const int blk = i * BPT + b, ms = blk % MB;
-        ws_wait(um_smem_u32(bars + WSB_META_FULL + ms), (uint32_t)(blk / MB) & 1u);
+        ws_wait_relaxed(um_smem_u32(bars + WSB_META_FULL + ms), (uint32_t)(blk / MB) & 1u);
         clk.lap(1);
         const float* mt = meta + ms * MSTRIDE;
         const int* m_li = reinterpret_cast<const int*>(mt + WsMeta::li);
@@ -487,6 +572,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
             }
           }
           clk.lap(2);
+          if (!slot_free) {  // the loads are in flight while the previous tile in this slot is consumed by layer 0
+            ws_wait_relaxed(um_smem_u32(bars + WSB_A0_EMPTY + slot), ((uint32_t)(i / WS_A0) & 1u) ^ 1u);
+            slot_free = true;
+            clk.lap(0);
+          }
 #pragma unroll
           for (int u = 0; u < GU; ++u) {
             const int ql = (p0 + u) * M::RPP + sub;
@@ -533,6 +623,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
           }
           clk.lap(3);
         }
+        if (!slot_free) {  // warps without a pass in this block (F = 8) still write position rows
+          ws_wait_relaxed(um_smem_u32(bars + WSB_A0_EMPTY + slot), ((uint32_t)(i / WS_A0) & 1u) ^ 1u);
+          slot_free = true;
+        }
         // position part (columns F .. F+2) and zero padding of the rows: thread per row
         if (GRAD || (b % WS_GW) == gw) {
           const int row = GRAD ? gw * WT + lane : b * WT + lane;
@@ -571,7 +665,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
         const int blk = i * BPT + b;
         if (blk % WS_LW != lw) continue;
         const int ms = blk % MB;
-        ws_wait(um_smem_u32(bars + WSB_META_EMPTY + ms), ((uint32_t)(blk / MB) & 1u) ^ 1u);
+        ws_wait_relaxed(um_smem_u32(bars + WSB_META_EMPTY + ms), ((uint32_t)(blk / MB) & 1u) ^ 1u);
         clk.lap(0);
         float* mt = meta + ms * MSTRIDE;
         const long long st = T * BPT + b;  // stash block
@@ -650,7 +744,7 @@ static WsLayout plan_ws_layout(const pinb200_decoder_view& d, bool grad) {
   l.a0_stride = 2 * l.a0_half;
   l.a0 = take(WS_A0 * l.a0_stride);
   l.meta_stride = (grad ? WsMeta::floats_g : WsMeta::floats_ng) * 4;
-  l.n_meta = grad ? 4 : 8;
+  l.n_meta = grad ? 8 : 16;
   l.meta = take(l.n_meta * l.meta_stride);
   l.bars = take(WSB_COUNT * 8);
   l.tmem = take(4);
@@ -658,7 +752,7 @@ static WsLayout plan_ws_layout(const pinb200_decoder_view& d, bool grad) {
   return l;
 }
 
-template <int FT, bool GRAD>
+template <int FT, bool GRAD, bool PROF>
 static int launch_wsq(QueryParams& p, cudaStream_t stream) {
   const WsLayout lay = plan_ws_layout<FT>(p.dec, GRAD);
   const size_t smem_bytes = (size_t)lay.total;
@@ -666,7 +760,7 @@ static int launch_wsq(QueryParams& p, cudaStream_t stream) {
     set_error("wsq_decode kernel needs %zu B shared memory (> 227 KB)", smem_bytes);
     return PINB200_ERR_UNSUPPORTED;
   }
-  auto kern = wsq_decode_kernel<FT, GRAD>;
+  auto kern = wsq_decode_kernel<FT, GRAD, PROF>;
   static std::mutex mu;
   static std::vector<int> done;
   int dev = 0;
@@ -687,16 +781,18 @@ static int launch_wsq(QueryParams& p, cudaStream_t stream) {
   constexpr int QT = GRAD ? 32 : 128;
   const long long n_tiles = (p.n + QT - 1) / QT;
   const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count());
-  kern<<<grid, WS_THREADS, smem_bytes, stream>>>(p, lay, g_ws_profile);
+  kern<<<grid, WS_THREADS, smem_bytes, stream>>>(p, lay);
   return check_launch("wsq_decode_kernel");
 }
 
 int dispatch_wsq(QueryParams& p, cudaStream_t stream) {
   const bool grad = p.opts.need_grad != 0;
   switch (p.dec.in_dim - 3) {
-    case 8: return grad ? launch_wsq<8, true>(p, stream) : launch_wsq<8, false>(p, stream);
-    case 16: return grad ? launch_wsq<16, true>(p, stream) : launch_wsq<16, false>(p, stream);
-    case 32: return grad ? launch_wsq<32, true>(p, stream) : launch_wsq<32, false>(p, stream);
+    case 8: return grad ? launch_wsq<8, true, false>(p, stream) : launch_wsq<8, false, false>(p, stream);
+    case 16: return grad ? launch_wsq<16, true, false>(p, stream) : launch_wsq<16, false, false>(p, stream);
+    case 32:
+      if (g_ws_profile) return grad ? launch_wsq<32, true, true>(p, stream) : launch_wsq<32, false, true>(p, stream);
+      return grad ? launch_wsq<32, true, false>(p, stream) : launch_wsq<32, false, false>(p, stream);
     default: break;
   }
   set_error("wsq_decode: feature_dim %d unsupported", p.dec.in_dim - 3);

@@ -18,6 +18,22 @@ torch.manual_seed(42)
 dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
 q = surface_queries(npm, 200000, seed=1, sigma=0.1)
 ref = None
+
+
+def timed(fn, n=10):
+    ts = []
+    for it in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts = sorted(ts[3:])
+    return ts[len(ts) // 2], ts[0]
+
+
 for variant in [int(a) for a in sys.argv[1:]] or [0, 1]:
     ops.set_option("decode_variant", variant)
     out = {}
@@ -39,6 +55,9 @@ for variant in [int(a) for a in sys.argv[1:]] or [0, 1]:
         dg = (out["grad"] - ref["grad"]).abs().max().item()
         line += f"; vs first variant: max |d sdf| {ds:.3e}, max |d grad| {dg:.3e} (|grad| mean {ref['grad'].abs().mean().item():.3e})"
     print(line, flush=True)
+    o2 = {}
+    med, mn = timed(lambda: npm.query_sdf(q, dec, need_grad=False, out=o2))
+    print(f"variant {variant}: value-only (need_grad=False) cold-L2 median {med:.4f} ms, min {mn:.4f} ms", flush=True)
 
 # per-warp phase cycle counters of the warp-specialised decode (one profiled launch)
 import numpy as np
@@ -51,7 +70,7 @@ ops.set_option("ws_profile", 0)
 buf = np.zeros(148 * 20 * 8, dtype=np.uint64)
 _lib.check(_lib.load().pinb200_debug_read(b"ws_profile", buf.ctypes.data, buf.size), "debug_read")
 prof = buf.reshape(148, 20, 8).astype(np.float64)
-names = {"E": ["group_bar", "waitA+mma0", "epi0", "mma1", "epi1+out"], "G": ["wait_A_free", "wait_meta", "issue_loads", "reduce+store", "pos+fence"],
+names = {"E": ["wait_mma0", "epi0+bar", "issue(+waitA)", "wait_mma1", "epi1", "outputs"], "G": ["wait_A_free", "wait_meta", "issue_loads", "reduce+store", "pos+fence"],
          "L": ["wait_meta_free", "stash_loads", "seeds+store"]}
 for role, ws in (("E", range(0, 8)), ("G", range(8, 16)), ("L", range(16, 20))):
     med = np.median(prof[:, list(ws), :], axis=0)  # [warps, slots] median over CTAs
