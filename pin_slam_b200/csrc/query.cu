@@ -27,6 +27,7 @@ namespace pinb {
 // K1a of the split pipeline: phase A1 alone, at high occupancy (no decoder weights in shared memory, <= 128
 // registers): the probe rounds of ~16 resident warps per SM keep the load/store unit busy, which the fused kernel's
 // 12 warps (most of them in compute phases at any time) cannot.  One warp = one 32-query tile.
+template <bool SEEDS>
 __global__ void __launch_bounds__(128, 4) search_kernel(const __grid_constant__ QueryParams p) {
   extern __shared__ __align__(16) float smem[];
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem);
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(128, 4) search_kernel(const __grid_constant__ 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int st = blockIdx.x * nwarp + warp; st < p.n_tiles; st += gridDim.x * nwarp)
-    a1_tile(p, s_delta, (long long)st * WT, WT, lane, p.stash + (size_t)st * Stash::floats);
+    a1_tile<SEEDS>(p, s_delta, (long long)st * WT, WT, lane, p.stash + (size_t)st * Stash::floats);
 }
 
 // ---------------------------------------------------------------------------
@@ -629,7 +630,10 @@ static int launch_search(QueryParams& p, cudaStream_t stream) {
   p.n_tiles = (int)((p.n + WT - 1) / WT);
   const long long ctas = (p.n_tiles + 3) / 4;
   const int grid = (int)std::min<long long>(ctas, (long long)sm_count() * 4);
-  search_kernel<<<grid, 128, align4(p.map.n_probe) * sizeof(float), stream>>>(p);
+  if (p.seeds)
+    search_kernel<true><<<grid, 128, align4(p.map.n_probe) * sizeof(float), stream>>>(p);
+  else
+    search_kernel<false><<<grid, 128, align4(p.map.n_probe) * sizeof(float), stream>>>(p);
   return check_launch("search_kernel");
 }
 
@@ -705,6 +709,10 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   const bool split = opts->workspace && opts->workspace_bytes >= need && n >= g_split_min_queries;
   if (split) {
     p.stash = reinterpret_cast<float*>(opts->workspace);
+    // the warp-specialised decode takes the forward-mode seeds of d/dq from the search launch (second workspace region)
+    const bool want_seeds = g_decode_variant == 1 && umma_decode_supported(p) &&
+                            (opts->need_grad || (color_dec && opts->need_grad && out->color_grad));
+    p.seeds = want_seeds ? p.stash + (size_t)p.n_tiles * Stash::floats : nullptr;
     rc = launch_search(p, (cudaStream_t)stream);
     if (rc) return rc;
   }
@@ -759,7 +767,7 @@ extern "C" int pinb200_set_option(const char* name, int64_t value) {
 }
 
 extern "C" int64_t pinb200_query_workspace_bytes(int64_t n) {
-  return n <= 0 ? 0 : ((n + WT - 1) / WT) * (int64_t)Stash::floats * (int64_t)sizeof(float);
+  return n <= 0 ? 0 : ((n + WT - 1) / WT) * (int64_t)(Stash::floats + Seeds::floats) * (int64_t)sizeof(float);
 }
 
 extern "C" int pinb200_knn_search(const pinb200_map_view* map, const float* query_xyz, int64_t n, int32_t nn_k,

@@ -48,6 +48,7 @@ struct QueryParams {
   int n_tiles;
   int qpt;  // queries per warp tile
   float* stash;  // split pipeline: [n_tiles][Stash::floats] workspace written by search_kernel, read by the decode launch
+  float* seeds;  // split pipeline with d/dq on the warp-specialised decode: [n_tiles][Seeds::floats] forward-mode seeds
   QueryLayout lay;
 };
 
@@ -345,6 +346,90 @@ struct Stash {
 };
 static_assert(Stash::floats % 4 == 0, "stash block is copied with 16-byte accesses");
 
+// Forward-mode seeds of d sdf / d q for one query (wsq.cu pushes them through the decoder as tangent rows):
+//   w_k = u_k / sum u,  u_k = 1 / (d_k^2 + eps)  =>  omega_kj = d w_k / d q_j = w_k (c_k d_kj - sum_m w_m c_m d_mj),
+//   c_k = -2 u_k,  d_k = q - p_k (the point the distance was measured to);   x_n = sum_k w_k n_k  =>
+//   P_ji = d (x_n)_i / d q_j = sum_k omega_kj (n_k - n_0)_i + sum_k w_k (R_k e_j)_i
+// (sum_k omega_kj = 0: the shift by the nearest neighbour keeps the sums cancellation-free when neighbours coincide;
+// R_k = I before loop closure).  Block layout [field][k][lane]: omega [3 j][8 k][32], P [3 j][3 i][32].
+struct Seeds {
+  static constexpr int om = 0;
+  static constexpr int P = om + WT * 24;
+  static constexpr int floats = P + WT * 9;
+};
+__device__ __forceinline__ void tangent_seeds(const pinb200_map_view& m, int K, const int (&lif)[KREG], const float (&w)[KREG],
+                                              const float (&px)[KREG], const float (&py)[KREG], const float (&pz)[KREG], float qx,
+                                              float qy, float qz, float usum, int nn, float* sd, int lane) {
+  float c[KREG], S0 = 0.f, S1 = 0.f, S2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) {
+    const bool v = k < K && lif[k] >= 0;
+    c[k] = (v && nn > 0) ? -2.f * (w[k] * usum) : 0.f;
+    const float wc = v ? w[k] * c[k] : 0.f;
+    S0 = fmaf(wc, __fsub_rn(qx, px[k]), S0);
+    S1 = fmaf(wc, __fsub_rn(qy, py[k]), S1);
+    S2 = fmaf(wc, __fsub_rn(qz, pz[k]), S2);
+  }
+  float P[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float n0x = 0.f, n0y = 0.f, n0z = 0.f;
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) {
+    const bool v = k < K && lif[k] >= 0;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    if (v) {
+      const float dx = __fsub_rn(qx, px[k]), dy = __fsub_rn(qy, py[k]), dz = __fsub_rn(qz, pz[k]);
+      o0 = w[k] * (c[k] * dx - S0);
+      o1 = w[k] * (c[k] * dy - S1);
+      o2 = w[k] * (c[k] * dz - S2);
+      float nx, ny, nz;
+      float4 quat;
+      neighbour_vec(m, lif[k], dx, dy, dz, qx, qy, qz, nx, ny, nz, quat);
+      if (k == 0) {
+        n0x = nx;
+        n0y = ny;
+        n0z = nz;
+      }
+      const float ex = nx - n0x, ey = ny - n0y, ez = nz - n0z;
+      P[0][0] = fmaf(o0, ex, P[0][0]);
+      P[0][1] = fmaf(o0, ey, P[0][1]);
+      P[0][2] = fmaf(o0, ez, P[0][2]);
+      P[1][0] = fmaf(o1, ex, P[1][0]);
+      P[1][1] = fmaf(o1, ey, P[1][1]);
+      P[1][2] = fmaf(o1, ez, P[1][2]);
+      P[2][0] = fmaf(o2, ex, P[2][0]);
+      P[2][1] = fmaf(o2, ey, P[2][1]);
+      P[2][2] = fmaf(o2, ez, P[2][2]);
+      if (m.after_pgo) {  // column j of the point's (passive) rotation
+        float r0, r1, r2;
+        quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, 1.f, 0.f, 0.f, r0, r1, r2);
+        P[0][0] = fmaf(w[k], r0, P[0][0]);
+        P[0][1] = fmaf(w[k], r1, P[0][1]);
+        P[0][2] = fmaf(w[k], r2, P[0][2]);
+        quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, 0.f, 1.f, 0.f, r0, r1, r2);
+        P[1][0] = fmaf(w[k], r0, P[1][0]);
+        P[1][1] = fmaf(w[k], r1, P[1][1]);
+        P[1][2] = fmaf(w[k], r2, P[1][2]);
+        quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, 0.f, 0.f, 1.f, r0, r1, r2);
+        P[2][0] = fmaf(w[k], r0, P[2][0]);
+        P[2][1] = fmaf(w[k], r1, P[2][1]);
+        P[2][2] = fmaf(w[k], r2, P[2][2]);
+      } else {
+        P[0][0] += w[k];
+        P[1][1] += w[k];
+        P[2][2] += w[k];
+      }
+    }
+    sd[Seeds::om + (0 * KREG + k) * WT + lane] = o0;
+    sd[Seeds::om + (1 * KREG + k) * WT + lane] = o1;
+    sd[Seeds::om + (2 * KREG + k) * WT + lane] = o2;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sd[Seeds::P + (j * 3 + i) * WT + lane] = P[j][i];
+}
+
+template <bool SEEDS = false>
 __device__ __forceinline__ void a1_tile(const QueryParams& p, const uint32_t* s_delta, long long q0s, int WQ, int lane,
                                         float* stash) {
   const pinb200_map_view& m = p.map;
@@ -476,6 +561,7 @@ __device__ __forceinline__ void a1_tile(const QueryParams& p, const uint32_t* s_
   s_pos[0 * WT + lane] = sx;  // position part of the IDW-averaged decoder input (weighted_first)
   s_pos[1 * WT + lane] = sy;
   s_pos[2 * WT + lane] = sz;
+  if (SEEDS) tangent_seeds(m, K, lif, w, px, py, pz, qx, qy, qz, usum, cnt, p.seeds + (size_t)(q0s / WT) * Seeds::floats, lane);
   if (live && !p.is_color) {
     if (p.opts.training_mode && (p.opts.training_rows <= 0 || qi < p.opts.training_rows)) {
       // certainty scatter_add / ts amax (:685-710); invalid entries add 0 / max with 0 in the reference

@@ -30,12 +30,13 @@ namespace pinb {
 constexpr int WS_EG = 2;       // epilogue groups of 4 warps
 constexpr int WS_GT = 2;       // gather teams of 4 warps: team t fills the A tiles of the CTA's tiles i = t (mod WS_GT)
 constexpr int WS_GW = 4;       // warps per gather team
-constexpr int WS_LW = 4;       // loader warps
-constexpr int WS_THREADS = (4 * WS_EG + WS_GT * WS_GW + WS_LW) * 32;
+constexpr int WS_LW = 2;       // loader warps; the other two warps of their 4-warp group issue the MMAs (one per epilogue group)
+constexpr int WS_THREADS = (4 * WS_EG + WS_GT * WS_GW + WS_LW + WS_EG) * 32;
+static_assert((WS_LW + WS_EG) % 4 == 0, "setmaxnreg works on groups of 4 warps");
 // register budget per thread (setmaxnreg, one value per 4-warp group).  The pool is what the CTA was launched with
 // (640 threads x 96 registers): 8*32*80 + 8*32*120 + 4*32*80 = 61440
 constexpr int WS_REG_E = 80, WS_REG_G = 120, WS_REG_L = 80;
-static_assert((4 * WS_EG * WS_REG_E + WS_GT * WS_GW * WS_REG_G + WS_LW * WS_REG_L) * 32 <= WS_THREADS * 96, "setmaxnreg pool");
+static_assert((4 * WS_EG * WS_REG_E + WS_GT * WS_GW * WS_REG_G + (WS_LW + WS_EG) * WS_REG_L) * 32 <= WS_THREADS * 96, "setmaxnreg pool");
 constexpr int WS_A0 = 2;       // A-tile ring slots, one per gather team / epilogue group pair: layer 0 of a tile is issued early,
                                // so its slot is free again while the rest of the chain runs (3 slots measured the same)
 constexpr int WS_TCOLS = 256;  // TMEM columns per epilogue group: [0,64) D0, [64,128) A1 hi, [128,192) A1 lo, [192,256) D1
@@ -60,7 +61,7 @@ struct WsLayout {  // byte offsets from the dynamic shared memory base
 constexpr int WS_MB_MAX = 16;
 constexpr int WSB_A0_FULL = 0, WSB_A0_EMPTY = WSB_A0_FULL + WS_A0, WSB_META_FULL = WSB_A0_EMPTY + WS_A0,
               WSB_META_EMPTY = WSB_META_FULL + WS_MB_MAX, WSB_MMA0 = WSB_META_EMPTY + WS_MB_MAX, WSB_MMA1 = WSB_MMA0 + WS_EG,
-              WSB_COUNT = WSB_MMA1 + WS_EG;
+              WSB_A1_READY = WSB_MMA1 + WS_EG, WSB_D1_FREE = WSB_A1_READY + WS_EG, WSB_COUNT = WSB_D1_FREE + WS_EG;
 
 // Optional cycle accounting (pinb200_set_option("ws_profile", 1)): per warp, clock64 deltas of up to 8 phases,
 // summed over the tiles of the launch; read back with pinb200_debug_read("ws_profile", ...).
@@ -186,93 +187,26 @@ __device__ __forceinline__ void ws_lds16(const float* src, float (&b)[16]) {
   }
 }
 
-// Meta block column of one query, from the search results (registers).  GRAD adds the forward-mode seeds:
-//   w_k = u_k / sum u,  u_k = 1 / (d_k^2 + eps)  =>  d w_k / d q = w_k (c_k d_k - sum_m w_m c_m d_m),  c_k = -2 u_k,
-//   d_k = q - p_k (the point the distance was measured to);  x_n = sum_k w_k n_k  =>
-//   d x_n / d q_j = sum_k omega_kj (n_k - n_0) + sum_k w_k R_k e_j   (sum_k omega_kj = 0: the shift by the nearest
-//   neighbour keeps the sum cancellation-free when neighbours coincide; R_k = I before loop closure)
-template <bool GRAD>
-__device__ __forceinline__ void ws_write_meta(const pinb200_map_view& m, int K, const int (&lif)[KREG], const float (&w)[KREG],
-                                              const float (&dx)[KREG], const float (&dy)[KREG], const float (&dz)[KREG], float qx,
-                                              float qy, float qz, float usum, int nn, float px, float py, float pz, float* mt,
-                                              int lane) {
-  int* m_li = reinterpret_cast<int*>(mt + WsMeta::li);
-#pragma unroll
-  for (int k = 0; k < KREG; ++k) {
-    m_li[k * WT + lane] = k < K ? lif[k] : -1;
-    mt[WsMeta::w + k * WT + lane] = k < K ? w[k] : 0.f;
-  }
-  mt[WsMeta::xn + 0 * WT + lane] = px;
-  mt[WsMeta::xn + 1 * WT + lane] = py;
-  mt[WsMeta::xn + 2 * WT + lane] = pz;
-  if (GRAD) {
-    float c[KREG], S0 = 0.f, S1 = 0.f, S2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < KREG; ++k) {
-      const bool v = k < K && lif[k] >= 0;
-      c[k] = (v && nn > 0) ? -2.f * (w[k] * usum) : 0.f;
-      const float wc = v ? w[k] * c[k] : 0.f;
-      S0 = fmaf(wc, dx[k], S0);
-      S1 = fmaf(wc, dy[k], S1);
-      S2 = fmaf(wc, dz[k], S2);
-    }
-    float P[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-    float n0x = 0.f, n0y = 0.f, n0z = 0.f;
-#pragma unroll
-    for (int k = 0; k < KREG; ++k) {
-      const bool v = k < K && lif[k] >= 0;
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-      if (v) {
-        o0 = w[k] * (c[k] * dx[k] - S0);
-        o1 = w[k] * (c[k] * dy[k] - S1);
-        o2 = w[k] * (c[k] * dz[k] - S2);
-        float nx, ny, nz;
-        float4 quat;
-        neighbour_vec(m, lif[k], dx[k], dy[k], dz[k], qx, qy, qz, nx, ny, nz, quat);
-        if (k == 0) {
-          n0x = nx;
-          n0y = ny;
-          n0z = nz;
-        }
-        const float ex = nx - n0x, ey = ny - n0y, ez = nz - n0z;
-        P[0][0] = fmaf(o0, ex, P[0][0]);
-        P[0][1] = fmaf(o0, ey, P[0][1]);
-        P[0][2] = fmaf(o0, ez, P[0][2]);
-        P[1][0] = fmaf(o1, ex, P[1][0]);
-        P[1][1] = fmaf(o1, ey, P[1][1]);
-        P[1][2] = fmaf(o1, ez, P[1][2]);
-        P[2][0] = fmaf(o2, ex, P[2][0]);
-        P[2][1] = fmaf(o2, ey, P[2][1]);
-        P[2][2] = fmaf(o2, ez, P[2][2]);
-        if (m.after_pgo) {  // column j of the point's (passive) rotation
-          float r0, r1, r2;
-          quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, 1.f, 0.f, 0.f, r0, r1, r2);
-          P[0][0] = fmaf(w[k], r0, P[0][0]);
-          P[0][1] = fmaf(w[k], r1, P[0][1]);
-          P[0][2] = fmaf(w[k], r2, P[0][2]);
-          quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, 0.f, 1.f, 0.f, r0, r1, r2);
-          P[1][0] = fmaf(w[k], r0, P[1][0]);
-          P[1][1] = fmaf(w[k], r1, P[1][1]);
-          P[1][2] = fmaf(w[k], r2, P[1][2]);
-          quat_rotate_passive(quat.x, quat.y, quat.z, quat.w, 0.f, 0.f, 1.f, r0, r1, r2);
-          P[2][0] = fmaf(w[k], r0, P[2][0]);
-          P[2][1] = fmaf(w[k], r1, P[2][1]);
-          P[2][2] = fmaf(w[k], r2, P[2][2]);
-        } else {
-          P[0][0] += w[k];
-          P[1][1] += w[k];
-          P[2][2] += w[k];
-        }
-      }
-      mt[WsMeta::om + (0 * KREG + k) * WT + lane] = o0;
-      mt[WsMeta::om + (1 * KREG + k) * WT + lane] = o1;
-      mt[WsMeta::om + (2 * KREG + k) * WT + lane] = o2;
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) mt[WsMeta::P + (j * 3 + i) * WT + lane] = P[j][i];
-  }
+static_assert(WsMeta::P - WsMeta::om == Seeds::P - Seeds::om && WsMeta::floats_g - WsMeta::om == Seeds::floats,
+              "the seed block of the search launch is copied verbatim into the meta block");
+
+__device__ __forceinline__ bool ws_elect() {  // one lane of the (converged) warp; keeps the code warp-uniform for the compiler
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void ws_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(um_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void ws_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
 template <int FT, bool GRAD, bool PROF>
@@ -317,6 +251,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     for (int g = 0; g < WS_EG; ++g) {
       init(WSB_MMA0 + g, 1);
       init(WSB_MMA1 + g, 1);
+      init(WSB_A1_READY + g, 128);
+      init(WSB_D1_FREE + g, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -338,11 +274,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
   if (warp < 4 * WS_EG) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_E));
     // =====================================================================================================
-    // E: epilogue group g owns the tiles i = g, g + 2, ... of this CTA.  Software pipeline over its tiles: layer 0
-    // of tile t+1 is issued right behind layer 1 of tile t (its own accumulator columns), so it runs under the
-    // last-layer epilogue of tile t.
-    // profile slots: 0 wait layer-0 MMAs, 1 layer-0 epilogue + group barrier, 2 MMA issue (+ wait for the next A tile),
-    //                3 wait layer-1 MMAs, 4 last-layer epilogue + outputs
+    // E: epilogue group g owns the tiles i = g, g + 2, ... of this CTA.  Its threads never issue an MMA and never
+    // meet at a barrier: they wait for the group's MMA warp through mbarriers (bar0 / bar1: layer 0 / 1 complete)
+    // and tell it through two more (a1_ready: A1 written + D0 read, d1_free: last accumulator read).
+    // profile slots: 0 wait layer-0 MMAs, 1 layer-0 epilogue, 3 wait layer-1 MMAs, 4 last-layer epilogue, 5 outputs
     // =====================================================================================================
     const int g = warp >> 2, qd = warp & 3;
     const int r = qd * WT + lane;  // tile row == TMEM lane
@@ -357,34 +292,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     const float* s_b1 = reinterpret_cast<const float*>(sm + lay.b1);
     const float* s_wout = reinterpret_cast<const float*>(sm + lay.wout);
     const float* s_bout = reinterpret_cast<const float*>(sm + lay.bout);
-    constexpr uint32_t A_SBO0 = (K0 / 4) * UM_A_LBO, W_SBO0 = (K0 / 4) * UM_W_LBO, W_SBO1 = (H / 4) * UM_W_LBO;
-    // a k-step (8 columns = two 16-byte chunks) advances the start-address field of a descriptor by 2 * LBO / 16
-    constexpr uint64_t A_STEP = (2 * UM_A_LBO) >> 4, W_STEP = (2 * UM_W_LBO) >> 4;
-    const uint64_t w0h_d = um_desc(um_smem_u32(sm + lay.w0_hi), UM_W_LBO, W_SBO0), w0l_d = um_desc(um_smem_u32(sm + lay.w0_lo), UM_W_LBO, W_SBO0);
-    const uint64_t w1h_d = um_desc(um_smem_u32(sm + lay.w1_hi), UM_W_LBO, W_SBO1), w1l_d = um_desc(um_smem_u32(sm + lay.w1_lo), UM_W_LBO, W_SBO1);
-    const uint32_t idesc = um_idesc(H);
-    const uint32_t td1 = L > 1 ? tb + 192 : tb;  // accumulator of the last hidden layer
-    const uint32_t tl1 = L > 1 ? tl + 192 : tl;
+    const uint32_t tl1 = L > 1 ? tl + 192 : tl;  // accumulator of the last hidden layer
+    const uint32_t a1_ready = um_smem_u32(bars + WSB_A1_READY + g), d1_free = um_smem_u32(bars + WSB_D1_FREE + g);
 
-    // layer 0 of the CTA's i-th tile (called by the group's first warp; lane 0 issues)
-    auto issue_l0 = [&](int ii) {
-      const int slot = ii % WS_A0;
-      ws_wait(um_smem_u32(bars + WSB_A0_FULL + slot), (uint32_t)(ii / WS_A0) & 1u);
-      if (lane == 0) {
-        ws_fence_after();
-        const uint32_t a_hi = um_smem_u32(sm + lay.a0 + slot * lay.a0_stride);
-        const uint64_t ah = um_desc(a_hi, UM_A_LBO, A_SBO0), al = um_desc(a_hi + lay.a0_half, UM_A_LBO, A_SBO0);
-#pragma unroll
-        for (int s = 0; s < K0 / 8; ++s) {
-          um_mma(tb, al + s * A_STEP, w0h_d + s * W_STEP, idesc, s > 0);  // small terms first
-          um_mma(tb, ah + s * A_STEP, w0l_d + s * W_STEP, idesc, 1);
-          um_mma(tb, ah + s * A_STEP, w0h_d + s * W_STEP, idesc, 1);
-        }
-        ws_commit(bar0);
-        ws_commit(um_smem_u32(bars + WSB_A0_EMPTY + slot));  // the A tile may be refilled once these MMAs have read it
-      }
-      __syncwarp();
-    };
     // bias (value rows) + ReLU gate of 16 accumulator columns.  The gate of a tangent row is the sign pattern of its
     // query's value row: the 16 sign bits travel in ONE quad-leader shuffle per chunk.
     auto gated16 = [&](const uint32_t (&v)[16], const float (&bb)[16], float (&z)[16]) {
@@ -399,11 +309,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
       for (int e = 0; e < 16; ++e) z[e] = ((mk >> e) & 1u) ? z[e] : slope * z[e];
     };
 
-    int i = g;
-    long long T = blockIdx.x + (long long)g * gridDim.x;
-    if (T < n_tiles && qd == 0) issue_l0(i);
-    for (; T < n_tiles; T += (long long)WS_EG * gridDim.x, i += WS_EG) {
-      const bool has_next = T + (long long)WS_EG * gridDim.x < n_tiles;
+    for (long long T = blockIdx.x + (long long)g * gridDim.x; T < n_tiles; T += (long long)WS_EG * gridDim.x) {
       ws_wait(bar0, ph0);
       ph0 ^= 1u;
       ws_fence_after();
@@ -428,25 +334,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
           ws_tmem_st16(tl + 128 + 16 * c, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        // every row has written its A1 columns and has read its D0 columns
+        // this row has written its A1 columns and has read its D0 columns: tell the group's MMA warp
         ws_fence_before();
-        ws_group_bar(1 + g);
+        ws_arrive(a1_ready);
         clk.lap(1);
-        if (qd == 0) {
-          if (lane == 0) {
-            ws_fence_after();
-#pragma unroll
-            for (int s = 0; s < H / 8; ++s) {
-              ws_mma_ts(td1, tb + 128 + 8 * s, w1h_d + s * W_STEP, idesc, s > 0);
-              ws_mma_ts(td1, tb + 64 + 8 * s, w1l_d + s * W_STEP, idesc, 1);
-              ws_mma_ts(td1, tb + 64 + 8 * s, w1h_d + s * W_STEP, idesc, 1);
-            }
-            ws_commit(bar1);
-          }
-          __syncwarp();
-          if (has_next) issue_l0(i + WS_EG);  // runs behind layer 1 on the tensor pipe, under this tile's last epilogue
-        }
-        clk.lap(2);
         ws_wait(bar1, ph1);
         ph1 ^= 1u;
         ws_fence_after();
@@ -484,11 +375,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
             }
         }
       }
-      if (L == 1) {  // single hidden layer: the next tile's layer 0 overwrites the accumulator every row just read
-        ws_fence_before();
-        ws_group_bar(1 + g);
-        if (qd == 0 && has_next) issue_l0(i + WS_EG);
-      }
+      // this row has read its accumulator columns of the last layer
+      ws_fence_before();
+      ws_arrive(d1_free);
       clk.lap(4);
       // ---- outputs: value rows write the prediction, tangent rows one component of its gradient
       const int ql = GRAD ? (r >> 2) : r;
@@ -652,10 +541,81 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
       if (lane == 0) ws_arrive(um_smem_u32(bars + WSB_A0_FULL + slot));
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_L));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_L));  // one call site for the whole 4-warp group
+    if (warp >= 4 * WS_EG + WS_GT * WS_GW + WS_LW) {
     // =====================================================================================================
-    // L: loader warps -- stash block of 32 queries -> meta block (thread per query)
-    // profile slots: 0 wait free meta block, 1 stash loads, 2 seeds + meta stores
+    // M: one MMA warp per epilogue group (lane 0 issues).  Software pipeline over the group's tiles: layer 0 of tile
+    // t+1 goes right behind layer 1 of tile t (separate accumulator columns), so it runs under the last-layer
+    // epilogue of tile t.  With the issue loop on its own warp the epilogue warps are never blocked by a full
+    // tensor-pipe queue (the group's first warp was: 3.8k of 11.5k cycles per tile, profiles/r02_k1_wsq_*).
+    // profile slots: 0 wait A1 / D0, 1 wait D1 free, 2 layer-1 issue, 3 wait A tile, 4 layer-0 issue
+    // =====================================================================================================
+    const int g = warp - (4 * WS_EG + WS_GT * WS_GW + WS_LW);
+    const uint32_t tb = tmem_base + g * WS_TCOLS;
+    const uint32_t bar0 = um_smem_u32(bars + WSB_MMA0 + g), bar1 = um_smem_u32(bars + WSB_MMA1 + g);
+    const uint32_t a1_ready = um_smem_u32(bars + WSB_A1_READY + g), d1_free = um_smem_u32(bars + WSB_D1_FREE + g);
+    constexpr uint32_t A_SBO0 = (K0 / 4) * UM_A_LBO, W_SBO0 = (K0 / 4) * UM_W_LBO, W_SBO1 = (H / 4) * UM_W_LBO;
+    // a k-step (8 columns = two 16-byte chunks) advances the start-address field of a descriptor by 2 * LBO / 16
+    constexpr uint64_t A_STEP = (2 * UM_A_LBO) >> 4, W_STEP = (2 * UM_W_LBO) >> 4;
+    const uint64_t w0h_d = um_desc(um_smem_u32(sm + lay.w0_hi), UM_W_LBO, W_SBO0), w0l_d = um_desc(um_smem_u32(sm + lay.w0_lo), UM_W_LBO, W_SBO0);
+    const uint64_t w1h_d = um_desc(um_smem_u32(sm + lay.w1_hi), UM_W_LBO, W_SBO1), w1l_d = um_desc(um_smem_u32(sm + lay.w1_lo), UM_W_LBO, W_SBO1);
+    const uint32_t idesc = um_idesc(H);
+    const uint32_t td1 = L > 1 ? tb + 192 : tb;  // accumulator of the last hidden layer
+    auto issue_l0 = [&](int ii) {  // layer 0 of the CTA's ii-th tile
+      const int slot = ii % WS_A0;
+      ws_wait(um_smem_u32(bars + WSB_A0_FULL + slot), (uint32_t)(ii / WS_A0) & 1u);
+      clk.lap(3);
+      if (ws_elect()) {
+        ws_fence_after();
+        const uint32_t a_hi = um_smem_u32(sm + lay.a0 + slot * lay.a0_stride);
+        const uint64_t ah = um_desc(a_hi, UM_A_LBO, A_SBO0), al = um_desc(a_hi + lay.a0_half, UM_A_LBO, A_SBO0);
+#pragma unroll
+        for (int s = 0; s < K0 / 8; ++s) {
+          um_mma(tb, al + s * A_STEP, w0h_d + s * W_STEP, idesc, s > 0);  // small terms first
+          um_mma(tb, ah + s * A_STEP, w0l_d + s * W_STEP, idesc, 1);
+          um_mma(tb, ah + s * A_STEP, w0h_d + s * W_STEP, idesc, 1);
+        }
+        ws_commit(bar0);
+        ws_commit(um_smem_u32(bars + WSB_A0_EMPTY + slot));  // the A tile may be refilled once these MMAs have read it
+      }
+      __syncwarp();
+      clk.lap(4);
+    };
+    int i = g;
+    uint32_t n = 0;  // tiles of this group so far
+    long long T = blockIdx.x + (long long)g * gridDim.x;
+    if (T < n_tiles) issue_l0(i);
+    for (; T < n_tiles; T += (long long)WS_EG * gridDim.x, i += WS_EG, ++n) {
+      const bool has_next = T + (long long)WS_EG * gridDim.x < n_tiles;
+      if (L > 1) {
+        ws_wait(a1_ready, n & 1u);  // every row: A1 written, D0 read
+        clk.lap(0);
+        if (n > 0) ws_wait(d1_free, (n - 1u) & 1u);  // every row has read the previous tile's last accumulator
+        clk.lap(1);
+        if (ws_elect()) {
+          ws_fence_after();
+#pragma unroll
+          for (int s = 0; s < H / 8; ++s) {
+            ws_mma_ts(td1, tb + 128 + 8 * s, w1h_d + s * W_STEP, idesc, s > 0);
+            ws_mma_ts(td1, tb + 64 + 8 * s, w1l_d + s * W_STEP, idesc, 1);
+            ws_mma_ts(td1, tb + 64 + 8 * s, w1h_d + s * W_STEP, idesc, 1);
+          }
+          ws_commit(bar1);
+        }
+        __syncwarp();
+        clk.lap(2);
+      } else {
+        ws_wait(d1_free, n & 1u);  // single hidden layer: the epilogue reads the layer-0 accumulator itself
+        clk.lap(1);
+      }
+      if (has_next) issue_l0(i + WS_EG);
+    }
+    } else {
+    // =====================================================================================================
+    // L: loader warps -- TMA bulk copies of the search launch's results into the meta ring: neighbour ids + IDW weights
+    // (2 KB), position part (384 B) and, with d/dq, the forward-mode seeds (4.1 KB) of a 32-query block, all counted in
+    // bytes on the block's "full" mbarrier.  No thread touches the data.
+    // profile slots: 0 wait free meta block, 1 copies issued
     // =====================================================================================================
     const int lw = warp - 4 * WS_EG - WS_GT * WS_GW;
     int i = 0;
@@ -668,45 +628,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
         ws_wait_relaxed(um_smem_u32(bars + WSB_META_EMPTY + ms), ((uint32_t)(blk / MB) & 1u) ^ 1u);
         clk.lap(0);
         float* mt = meta + ms * MSTRIDE;
+        const uint32_t full = um_smem_u32(bars + WSB_META_FULL + ms);
         const long long st = T * BPT + b;  // stash block
-        int lif[KREG], nn = 0;
-        float w[KREG], dx[KREG], dy[KREG], dz[KREG], qx = 0.f, qy = 0.f, qz = 0.f, usum = 0.f, px = 0.f, py = 0.f, pz = 0.f;
-#pragma unroll
-        for (int k = 0; k < KREG; ++k) {
-          lif[k] = -1;
-          w[k] = dx[k] = dy[k] = dz[k] = 0.f;
-        }
         if (st < n_blocks) {
-          const float* __restrict__ sb = p.stash + (size_t)st * Stash::floats + lane;
-#pragma unroll
-          for (int k = 0; k < KREG; ++k)
-            if (k < K) {
-              lif[k] = __float_as_int(__ldg(sb + Stash::li + k * WT));
-              w[k] = __ldg(sb + Stash::w + k * WT);
-              if (GRAD) {
-                dx[k] = __ldg(sb + Stash::dx + k * WT);
-                dy[k] = __ldg(sb + Stash::dy + k * WT);
-                dz[k] = __ldg(sb + Stash::dz + k * WT);
-              }
-            }
-          px = __ldg(sb + Stash::pos);
-          py = __ldg(sb + Stash::pos + WT);
-          pz = __ldg(sb + Stash::pos + 2 * WT);
-          if (GRAD) {
-            qx = __ldg(sb + Stash::q);
-            qy = __ldg(sb + Stash::q + WT);
-            qz = __ldg(sb + Stash::q + 2 * WT);
-            usum = __ldg(sb + Stash::usum);
-            nn = __float_as_int(__ldg(sb + Stash::nn));
+          if (ws_elect()) {
+            const float* sb = p.stash + (size_t)st * Stash::floats;
+            constexpr uint32_t B_LW = 2 * WT * 8 * 4, B_XN = 3 * WT * 4, B_SD = Seeds::floats * 4;
+            ws_arrive_expect_tx(full, B_LW + B_XN + (GRAD ? B_SD : 0u));
+            ws_bulk_g2s(mt + WsMeta::li, sb + Stash::li, B_LW, full);  // li | w are adjacent in both layouts
+            ws_bulk_g2s(mt + WsMeta::xn, sb + Stash::pos, B_XN, full);
+            if (GRAD) ws_bulk_g2s(mt + WsMeta::om, p.seeds + (size_t)st * Seeds::floats, B_SD, full);
           }
+        } else {  // tail of the last value-only tile: a block without neighbours
+          for (int e = lane; e < MSTRIDE; e += 32) mt[e] = e < WsMeta::w ? __int_as_float(-1) : 0.f;
+          __syncwarp();
+          if (lane == 0) ws_arrive(full);
         }
-        clk.lap(1);
-        ws_write_meta<GRAD>(m, K, lif, w, dx, dy, dz, qx, qy, qz, usum, nn, px, py, pz, mt, lane);
         __syncwarp();
-        if (lane == 0) ws_arrive(um_smem_u32(bars + WSB_META_FULL + ms));
-        clk.lap(2);
+        clk.lap(1);
       }
     }
+  }
   }
   clk.flush(warp);
 

@@ -70,9 +70,9 @@ ops.set_option("ws_profile", 0)
 buf = np.zeros(148 * 20 * 8, dtype=np.uint64)
 _lib.check(_lib.load().pinb200_debug_read(b"ws_profile", buf.ctypes.data, buf.size), "debug_read")
 prof = buf.reshape(148, 20, 8).astype(np.float64)
-names = {"E": ["wait_mma0", "epi0+bar", "issue(+waitA)", "wait_mma1", "epi1", "outputs"], "G": ["wait_A_free", "wait_meta", "issue_loads", "reduce+store", "pos+fence"],
+names = {"E": ["wait_mma0", "epi0", "-", "wait_mma1", "epi1", "outputs"], "M": ["wait_A1", "wait_D1free", "issue_L1", "wait_Atile", "issue_L0"], "G": ["wait_A_free", "wait_meta", "issue_loads", "reduce+store", "pos+fence"],
          "L": ["wait_meta_free", "stash_loads", "seeds+store"]}
-for role, ws in (("E", range(0, 8)), ("G", range(8, 16)), ("L", range(16, 20))):
+for role, ws in (("E", range(0, 8)), ("G", range(8, 16)), ("L", range(16, 18)), ("M", range(18, 20))):
     med = np.median(prof[:, list(ws), :], axis=0)  # [warps, slots] median over CTAs
     print(role, "median cycles per warp over the launch (", ", ".join(names[role]), "):")
     for w, row in zip(ws, med):
