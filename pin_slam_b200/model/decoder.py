@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from .fused_features import FusedFeatures
 
 
 class Decoder(nn.Module):
@@ -35,6 +36,8 @@ class Decoder(nn.Module):
 
     # ---- torch path for materialised features (API compatibility) ----
     def mlp(self, features):
+        if isinstance(features, FusedFeatures):
+            features = features.materialize()
         act = F.leaky_relu if self.use_leaky_relu else F.relu
         h = features
         for layer in self.layers:
@@ -42,6 +45,10 @@ class Decoder(nn.Module):
         return self.lout(h)
 
     def sdf(self, features):
+        if isinstance(features, FusedFeatures):  # lazy handle of a weighted_first query: one fused K1 launch
+            fused = features.decode(self, color=False)
+            if fused is not None:
+                return fused
         return self.mlp(features).squeeze(1) * self.sdf_scale
 
     def time_conditionded_sdf(self, features, ts):
@@ -58,6 +65,10 @@ class Decoder(nn.Module):
         return torch.argmax(self.sem_label_prob(features), dim=1)
 
     def regress_color(self, features):
+        if isinstance(features, FusedFeatures):
+            fused = features.decode(self, color=True)
+            if fused is not None:
+                return fused
         return torch.sigmoid(self.mlp(features))
 
     # ---- kernel view ----

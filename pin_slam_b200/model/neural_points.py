@@ -426,13 +426,40 @@ class NeuralPoints(nn.Module):
     def query_certainty(self, query_points: torch.Tensor):
         return ops.query_certainty(self.map_handle(False), query_points.detach().contiguous())
 
+    FUSED_QUERY_FEATURE = True  # inference-mode weighted_first queries return lazy handles (model/fused_features.py)
+
     def query_feature(self, query_points: torch.Tensor, query_ts: torch.Tensor = None, training_mode: bool = True,
                       query_locally: bool = True, query_geo_feature: bool = True, query_color_feature: bool = False):
-        """Reference-compatible query: the kNN search (the reference's "slow part") runs in the CUDA
-        kernel; the returned feature vectors are assembled from the neighbour ids with differentiable
-        torch ops, so callers may keep using autograd (first and second order) exactly as before."""
+        """Reference-compatible query (model/neural_points.py:530-746).  Inference-mode `weighted_first` queries on
+        the GPU return `FusedFeatures` handles in place of the feature tensors: `Decoder.sdf` /
+        `Decoder.regress_color` then run the fused K1 kernel and `torch.autograd.grad` receives the kernel's
+        analytic gradient, so the reference's unchanged tracker / mesher code gets one fused launch per decoder.
+        Everything else takes the eager path below."""
         if not query_geo_feature and not query_color_feature:
             sys.exit("you need to at least query one kind of feature")
+        if (self.FUSED_QUERY_FEATURE and self.config.weighted_first and not training_mode and query_points.is_cuda
+                and query_geo_feature):
+            from .fused_features import FusedFeatures, _Group
+
+            k = self.config.query_nn_k
+            idx32, _, w, cnt, _ = ops.knn_search(self.map_handle(query_locally), query_points.detach().contiguous(), k,
+                                                 want_gidx=True)
+            cert_tab = self.local_point_certainties if query_locally else self.point_certainties
+            valid = idx32 >= 0
+            certainty = (cert_tab[idx32.long().clamp(min=0)] * valid * w).sum(dim=1)
+            grp = _Group(self, query_points, query_locally)
+            geo = FusedFeatures(grp, "geo")
+            col = FusedFeatures(grp, "color") if (query_color_feature and self.color_features is not None) else None
+            return geo, col, w.unsqueeze(-1), cnt.long(), certainty
+        return self._query_feature_eager(query_points, query_ts, training_mode, query_locally, query_geo_feature,
+                                         query_color_feature)
+
+    def _query_feature_eager(self, query_points: torch.Tensor, query_ts: torch.Tensor = None, training_mode: bool = True,
+                             query_locally: bool = True, query_geo_feature: bool = True,
+                             query_color_feature: bool = False):
+        """The kNN search (the reference's "slow part") runs in the CUDA kernel; the returned feature vectors are
+        assembled from the neighbour ids with differentiable torch ops, so callers may keep using autograd (first
+        and second order) exactly as before."""
         k = self.config.query_nn_k
         h = self.map_handle(query_locally)
         idx32, _, _, cnt, gidx32 = ops.knn_search(h, query_points.detach().contiguous(), k, want_gidx=True)

@@ -325,3 +325,29 @@ def test_cuda_voxel_downsample_equals_reference_formulation(n, voxel):
     got_b = ops.voxel_downsample(pts.to(DEV), voxel, val.to(DEV))
     assert torch.equal(got_a.cpu(), cpu_a)
     assert torch.equal(got_b.cpu(), cpu_b)
+
+
+def test_unchanged_reference_tracker_runs_fused():
+    """The reference's unmodified utils/tracker.py (oracle/_ref) over the install()ed drop-ins: its
+    query_feature -> Decoder.sdf -> get_gradient sequence is served by the fused K1 kernel (lazy feature handles,
+    pin_slam_b200/model/fused_features.py) and returns the fused path's values; the eager path stays available."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isfile(os.path.join(root, "oracle", "_ref", "utils", "tracker.py")):
+        pytest.skip("oracle/_ref not vendored (built by __graft_entry__.build() where /root/reference exists)")
+    pr = subprocess.run([sys.executable, os.path.join(root, "tests", "unchanged_caller_check.py")], capture_output=True,
+                        text=True, timeout=600)
+    assert pr.returncode == 0, pr.stdout[-2000:] + pr.stderr[-4000:]
+    res = json.loads([l for l in pr.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    for name, r in res.items():
+        # one kNN launch for the weights / counts / certainty + one fused launch per decoder call
+        assert r["launches"] <= 12, (name, r)  # incl. the one-off probe-index build of a fresh map handle
+        assert r["sdf_err"] == 0.0 and r["grad_err"] == 0.0 and r["mask_equal"], (name, r)
+        assert r["cert_err"] <= 1e-5, (name, r)
+        if "color_err" in r:
+            assert r["color_err"] == 0.0 and r["cgrad_err"] == 0.0, (name, r)
+        assert r["eager_vs_fused_sdf"] <= 2e-6 and r["eager_vs_fused_grad"] <= 2e-4 * max(r["grad_scale"], 1e-3) * 50, (name, r)
