@@ -61,7 +61,7 @@ struct WsLayout {  // byte offsets from the dynamic shared memory base
 constexpr int WS_MB_MAX = 16;
 constexpr int WSB_A0_FULL = 0, WSB_A0_EMPTY = WSB_A0_FULL + WS_A0, WSB_META_FULL = WSB_A0_EMPTY + WS_A0,
               WSB_META_EMPTY = WSB_META_FULL + WS_MB_MAX, WSB_MMA0 = WSB_META_EMPTY + WS_MB_MAX, WSB_MMA1 = WSB_MMA0 + WS_EG,
-              WSB_A1_READY = WSB_MMA1 + WS_EG, WSB_D1_FREE = WSB_A1_READY + WS_EG, WSB_COUNT = WSB_D1_FREE + WS_EG;
+              WSB_A1_READY = WSB_MMA1 + WS_EG, WSB_D1_FREE = WSB_A1_READY + 4 * WS_EG, WSB_COUNT = WSB_D1_FREE + WS_EG;
 
 // Optional cycle accounting (pinb200_set_option("ws_profile", 1)): per warp, clock64 deltas of up to 8 phases,
 // summed over the tiles of the launch; read back with pinb200_debug_read("ws_profile", ...).
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     for (int g = 0; g < WS_EG; ++g) {
       init(WSB_MMA0 + g, 1);
       init(WSB_MMA1 + g, 1);
-      init(WSB_A1_READY + g, 128);
+      for (int c = 0; c < 4; ++c) init(WSB_A1_READY + 4 * g + c, 128);
       init(WSB_D1_FREE + g, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     const float* s_wout = reinterpret_cast<const float*>(sm + lay.wout);
     const float* s_bout = reinterpret_cast<const float*>(sm + lay.bout);
     const uint32_t tl1 = L > 1 ? tl + 192 : tl;  // accumulator of the last hidden layer
-    const uint32_t a1_ready = um_smem_u32(bars + WSB_A1_READY + g), d1_free = um_smem_u32(bars + WSB_D1_FREE + g);
+    const uint32_t a1_ready = um_smem_u32(bars + WSB_A1_READY + 4 * g), d1_free = um_smem_u32(bars + WSB_D1_FREE + g);
 
     // bias (value rows) + ReLU gate of 16 accumulator columns.  The gate of a tangent row is the sign pattern of its
     // query's value row: the 16 sign bits travel in ONE quad-leader shuffle per chunk.
@@ -332,11 +332,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
           }
           ws_tmem_st16(tl + 64 + 16 * c, v);
           ws_tmem_st16(tl + 128 + 16 * c, lo);
+          // this row's 16 A1 columns are written (and its D0 columns read): the group's MMA warp starts the two
+          // k-steps of layer 1 that need them while the later chunks are still in the epilogue
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          ws_fence_before();
+          ws_arrive(a1_ready + 8 * c);
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        // this row has written its A1 columns and has read its D0 columns: tell the group's MMA warp
-        ws_fence_before();
-        ws_arrive(a1_ready);
         clk.lap(1);
         ws_wait(bar1, ph1);
         ph1 ^= 1u;
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     const int g = warp - (4 * WS_EG + WS_GT * WS_GW + WS_LW);
     const uint32_t tb = tmem_base + g * WS_TCOLS;
     const uint32_t bar0 = um_smem_u32(bars + WSB_MMA0 + g), bar1 = um_smem_u32(bars + WSB_MMA1 + g);
-    const uint32_t a1_ready = um_smem_u32(bars + WSB_A1_READY + g), d1_free = um_smem_u32(bars + WSB_D1_FREE + g);
+    const uint32_t a1_ready = um_smem_u32(bars + WSB_A1_READY + 4 * g), d1_free = um_smem_u32(bars + WSB_D1_FREE + g);
     constexpr uint32_t A_SBO0 = (K0 / 4) * UM_A_LBO, W_SBO0 = (K0 / 4) * UM_W_LBO, W_SBO1 = (H / 4) * UM_W_LBO;
     // a k-step (8 columns = two 16-byte chunks) advances the start-address field of a descriptor by 2 * LBO / 16
     constexpr uint64_t A_STEP = (2 * UM_A_LBO) >> 4, W_STEP = (2 * UM_W_LBO) >> 4;
@@ -588,22 +589,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     for (; T < n_tiles; T += (long long)WS_EG * gridDim.x, i += WS_EG, ++n) {
       const bool has_next = T + (long long)WS_EG * gridDim.x < n_tiles;
       if (L > 1) {
-        ws_wait(a1_ready, n & 1u);  // every row: A1 written, D0 read
-        clk.lap(0);
         if (n > 0) ws_wait(d1_free, (n - 1u) & 1u);  // every row has read the previous tile's last accumulator
         clk.lap(1);
-        if (ws_elect()) {
-          ws_fence_after();
 #pragma unroll
-          for (int s = 0; s < H / 8; ++s) {
-            ws_mma_ts(td1, tb + 128 + 8 * s, w1h_d + s * W_STEP, idesc, s > 0);
-            ws_mma_ts(td1, tb + 64 + 8 * s, w1l_d + s * W_STEP, idesc, 1);
-            ws_mma_ts(td1, tb + 64 + 8 * s, w1h_d + s * W_STEP, idesc, 1);
+        for (int c = 0; c < 4; ++c) {  // layer 1 follows the layer-0 epilogue chunk by chunk (16 A1 columns = 2 k-steps)
+          ws_wait(a1_ready + 8 * c, n & 1u);
+          clk.lap(0);
+          if (ws_elect()) {
+            ws_fence_after();
+#pragma unroll
+            for (int s = 2 * c; s < 2 * c + 2; ++s) {
+              ws_mma_ts(td1, tb + 128 + 8 * s, w1h_d + s * W_STEP, idesc, s > 0);
+              ws_mma_ts(td1, tb + 64 + 8 * s, w1l_d + s * W_STEP, idesc, 1);
+              ws_mma_ts(td1, tb + 64 + 8 * s, w1h_d + s * W_STEP, idesc, 1);
+            }
+            if (c == 3) ws_commit(bar1);
           }
-          ws_commit(bar1);
+          __syncwarp();
+          clk.lap(2);
         }
-        __syncwarp();
-        clk.lap(2);
       } else {
         ws_wait(d1_free, n & 1u);  // single hidden layer: the epilogue reads the layer-0 accumulator itself
         clk.lap(1);
