@@ -513,7 +513,7 @@ def main():
     peak, peak_src = hbm_peak()
     kernel_ms = sorted(step_ms)[len(step_ms) // 2]
     achieved = bq * N_QUERY / (ms_per_step * 1e-3) / 1e9
-    split = N_QUERY >= ops.SPLIT_MIN_QUERIES
+    split = ops.uses_split(N_QUERY, cfg.weighted_first)
     k1_kernels = ("pinb::search_kernel + pinb::wsq_decode_kernel<%d,true,false>" % cfg.feature_dim) if split else \
         "pinb::query_kernel<%d,%s,false>" % (cfg.feature_dim, "true" if cfg.weighted_first else "false")
 

@@ -117,18 +117,21 @@ typedef struct pinb200_query_opts {
                                (mapper.py:941) */
   const double* transform;  /* optional device ptr, 4x4 row-major fp64: q = T*p evaluated in fp32 (tools.py:534-553) */
   void* workspace;          /* optional device scratch of >= pinb200_query_workspace_bytes(N) bytes.  With it, batches
-                               of >= PINB200_SPLIT_MIN_QUERIES queries run as two launches (neighbour search at high
+                               of >= PINB200_SPLIT_MIN_QUERIES (weighted_first: _WF) queries run as two launches (neighbour search at high
                                occupancy, then gather + decoder on tcgen05 tiles); without it, or for small batches,
                                one fused launch.  The neighbour search is bit-identical either way; the decoder
                                outputs agree within the 3xTF32 bound (different accumulation order). */
   int64_t workspace_bytes;
 } pinb200_query_opts;
 
-#define PINB200_SPLIT_MIN_QUERIES 32768
+#define PINB200_SPLIT_MIN_QUERIES 32768   /* decode-every-neighbour maps */
+#define PINB200_SPLIT_MIN_QUERIES_WF 1024 /* weighted_first maps whose decoder runs on the tcgen05 kernels (hidden 64, 1-2 layers,
+                                             F in {8,16,32}): the two-launch pipeline is faster from ~1 k queries on */
 int64_t pinb200_query_workspace_bytes(int64_t n_queries);
 /* Run-time tunables of the query path (process-wide; for tests and A/B measurements):
-     "split_min_queries"  batch size from which the two-launch pipeline is used (default PINB200_SPLIT_MIN_QUERIES;
-                          <= 0 restores the default)
+     "split_min_queries"  batch size from which the two-launch pipeline is used, both kinds of map (<= 0 restores the
+                          defaults PINB200_SPLIT_MIN_QUERIES / PINB200_SPLIT_MIN_QUERIES_WF)
+     "split_min_queries_wf"  the same for weighted_first maps only
      "decode_variant"     0: phase-synchronous tcgen05 decode with backward MMAs (decode_umma_kernel)
                           1: warp-specialised forward-mode decode (wsq_decode_kernel; default)
      "ws_profile"         1: wsq_decode_kernel records per-warp phase cycle counters (pinb200_debug_read)

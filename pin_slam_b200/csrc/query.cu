@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ pin
 namespace pinb {
 
 // run-time tunables (pinb200_set_option)
-static long long g_split_min_queries = PINB200_SPLIT_MIN_QUERIES;
+static long long g_split_min_queries = PINB200_SPLIT_MIN_QUERIES;        // decode-every-neighbour maps (mma.sync decode)
+static long long g_split_min_queries_wf = PINB200_SPLIT_MIN_QUERIES_WF;  // weighted_first maps (tensor-core decode)
 static int g_decode_variant = 1;  // 0: decode_umma_kernel (phase-synchronous, backward MMAs), 1: wsq_decode_kernel
 
 // ---------------------------------------------------------------------------
@@ -706,7 +707,13 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   // Large batches run as two launches (search at high occupancy, then decode) through the caller's workspace; small
   // ones (tracker / mapper sized, latency-bound) stay fused in one launch.
   const int64_t need = pinb200_query_workspace_bytes(n);
-  const bool split = opts->workspace && opts->workspace_bytes >= need && n >= g_split_min_queries;
+  // weighted_first maps with a tcgen05-decodable configuration: the two-launch pipeline wins from ~1 k queries on
+  // (8 k queries, F = 32: 48 us vs 72 us for the fused launch; scripts/exp_small_n.py)
+  QueryParams probe{};
+  probe.dec = *sdf_dec;
+  probe.opts = *opts;
+  const long long split_min = umma_decode_supported(probe) ? g_split_min_queries_wf : g_split_min_queries;
+  const bool split = opts->workspace && opts->workspace_bytes >= need && n >= split_min;
   if (split) {
     p.stash = reinterpret_cast<float*>(opts->workspace);
     // the warp-specialised decode takes the forward-mode seeds of d/dq from the search launch (second workspace region)
@@ -749,8 +756,11 @@ extern "C" int pinb200_set_option(const char* name, int64_t value) {
     return PINB200_ERR_BAD_ARG;
   }
   const std::string key(name);
-  if (key == "split_min_queries") {
+  if (key == "split_min_queries") {  // both thresholds; <= 0 restores the defaults
     g_split_min_queries = value > 0 ? value : PINB200_SPLIT_MIN_QUERIES;
+    g_split_min_queries_wf = value > 0 ? value : PINB200_SPLIT_MIN_QUERIES_WF;
+  } else if (key == "split_min_queries_wf") {
+    g_split_min_queries_wf = value > 0 ? value : PINB200_SPLIT_MIN_QUERIES_WF;
   } else if (key == "decode_variant") {
     if (value < 0 || value > 1) {
       set_error("set_option: decode_variant %lld (0: phase-synchronous tcgen05 decode, 1: warp-specialised)", (long long)value);

@@ -258,8 +258,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
   }
   um_stage_weight(p.dec.w[0], D, H, D, H, K0, false, sm + lay.w0_hi, sm + lay.w0_lo);
   if (L > 1) um_stage_weight(p.dec.w[1], H, H, H, H, H, false, sm + lay.w1_hi, sm + lay.w1_lo);
+  __syncthreads();
+  // the layer-0 bias rides on the MMA: input column D is 1 for value rows (0 for tangent rows), weight column D = b0
+  static_assert(D < K0, "a spare (padding) input column carries the bias");
+  if (tid < H) {
+    const float bv = p.dec.b[0] ? __ldg(p.dec.b[0] + tid) : 0.f;
+    const float bh = __uint_as_float(__float_as_uint(bv) & TF32_MASK);
+    const int off = (tid >> 3) * ((K0 >> 2) * UM_W_LBO) + (D >> 2) * UM_W_LBO + (tid & 7) * 16 + (D & 3) * 4;
+    *reinterpret_cast<float*>(sm + lay.w0_hi + off) = bh;
+    *reinterpret_cast<float*>(sm + lay.w0_lo + off) = bv - bh;
+  }
   for (int e = tid; e < H; e += WS_THREADS) {
-    reinterpret_cast<float*>(sm + lay.b0)[e] = p.dec.b[0] ? __ldg(p.dec.b[0] + e) : 0.f;
+    reinterpret_cast<float*>(sm + lay.b0)[e] = 0.f;  // layer-0 bias: see the weight staging above
     reinterpret_cast<float*>(sm + lay.b1)[e] = (L > 1 && p.dec.b[1]) ? __ldg(p.dec.b[1] + e) : 0.f;
   }
   for (int e = tid; e < 4 * H; e += WS_THREADS) reinterpret_cast<float*>(sm + lay.wout)[e] = e < OC * H ? __ldg(p.dec.w_out + e) : 0.f;
@@ -309,6 +319,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
       for (int e = 0; e < 16; ++e) z[e] = ((mk >> e) & 1u) ? z[e] : slope * z[e];
     };
 
+    auto gate16 = [&](const uint32_t (&v)[16], float (&z)[16]) {  // gated16 without a bias
+      uint32_t mk = 0u;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        z[e] = __uint_as_float(v[e]);
+        mk |= z[e] > 0.f ? (1u << e) : 0u;
+      }
+      if (GRAD) mk = __shfl_sync(FULL, mk, src);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) z[e] = ((mk >> e) & 1u) ? z[e] : slope * z[e];
+    };
+    // where this row's results go: element (query qi, channel ch) at out_base[qi * out_qstride + ch * out_chstride]
+    float* out_base;
+    float* out_std = nullptr;
+    int out_qstride, out_chstride, out_nch = p.is_color ? OC : 1;
+    if (t == 0) {
+      out_base = p.is_color ? p.out.color : p.out.sdf;
+      out_qstride = p.is_color ? OC : 1;
+      out_chstride = 1;
+      if (!p.is_color) out_std = p.out.sdf_std;
+    } else {
+      out_base = p.is_color ? p.out.color_grad : p.out.grad;
+      if (out_base) out_base += t - 1;
+      out_qstride = p.is_color ? 3 * OC : 3;
+      out_chstride = 3;
+    }
     for (long long T = blockIdx.x + (long long)g * gridDim.x; T < n_tiles; T += (long long)WS_EG * gridDim.x) {
       ws_wait(bar0, ph0);
       ph0 ^= 1u;
@@ -319,11 +355,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t v[16];
-          float z[16], bb[16];
-          ws_tmem_ld16_issue(tl + 16 * c, v);
-          ws_lds16(s_b0 + 16 * c, bb);  // under the TMEM load
-          ws_tmem_ld_wait(v);
-          gated16(v, bb, z);
+          float z[16];
+          um_tmem_ld16(tl + 16 * c, v);
+          gate16(v, z);  // the bias came through the MMA
           uint32_t lo[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -380,42 +414,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
       ws_fence_before();
       ws_arrive(d1_free);
       clk.lap(4);
-      // ---- outputs: value rows write the prediction, tangent rows one component of its gradient
-      const int ql = GRAD ? (r >> 2) : r;
-      const long long qi = T * QT + ql;
-      const bool live = qi < p.n;
+      // ---- outputs: value rows write the prediction, tangent rows one component of its gradient (destinations
+      // resolved once per thread, see out_base)
+      const long long qi = T * QT + (GRAD ? (r >> 2) : r);
+      if (p.dec.sigmoid_out) {
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        if (ch < OC) {
-          const float oo = fmaf(bsel, s_bout[ch], o[ch]);
-          float res;
-          if (p.dec.sigmoid_out) {
+        for (int ch = 0; ch < 4; ++ch)
+          if (ch < OC) {
+            const float oo = fmaf(bsel, s_bout[ch], o[ch]);
             const float val = 1.f / (1.f + expf(-oo));
             const float dv = val * (1.f - val);
             const float dvq = GRAD ? __shfl_sync(FULL, dv, src) : dv;
-            res = t == 0 ? val : dvq * oo;
-          } else {
-            res = oo * p.dec.out_scale;
+            o[ch] = t == 0 ? val : dvq * oo;
           }
-          if (live) {
-            if (t == 0) {
-              if (!p.is_color) {
-                if (ch == 0) {
-                  if (p.out.sdf) p.out.sdf[qi] = res;
-                  if (p.out.sdf_std) p.out.sdf_std[qi] = 0.f;
-                }
-              } else if (p.out.color) {
-                p.out.color[qi * OC + ch] = res;
-              }
-            } else {
-              if (!p.is_color) {
-                if (ch == 0 && p.out.grad) p.out.grad[3 * qi + (t - 1)] = res;
-              } else if (p.out.color_grad) {
-                p.out.color_grad[(qi * OC + ch) * 3 + (t - 1)] = res;
-              }
-            }
-          }
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) o[ch] = fmaf(bsel, s_bout[ch], o[ch]) * p.dec.out_scale;
+      }
+      if (qi < p.n) {
+        if (out_base) {
+          float* dst = out_base + qi * out_qstride;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            if (ch < out_nch) dst[ch * out_chstride] = o[ch];
         }
+        if (out_std) out_std[qi] = 0.f;
+      }
       clk.lap(5);
     }
   } else if (warp < 4 * WS_EG + WS_GT * WS_GW) {
@@ -523,7 +547,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
           const int ql = GRAD ? row >> 2 : lane, tt = GRAD ? row & 3 : 0;
           const float* src3 = tt == 0 ? mt + WsMeta::xn : mt + WsMeta::P + (tt - 1) * 3 * WT;
           float4 hi, lo;
-          um_split4(make_float4(src3[ql], src3[WT + ql], src3[2 * WT + ql], 0.f), hi, lo);
+          um_split4(make_float4(src3[ql], src3[WT + ql], src3[2 * WT + ql], tt == 0 ? 1.f : 0.f), hi, lo);  // column D: bias input
           int off = um_a_off(row, F / 4, K0);
           *reinterpret_cast<float4*>(a_hi + off) = hi;
           *reinterpret_cast<float4*>(a_lo + off) = lo;

@@ -9,14 +9,27 @@ from . import _lib
 from ._lib import DecoderView, GnOpts, MapTrainOpts, MapView, QueryOpts, QueryOut
 
 SPLIT_MIN_QUERIES = 32768  # == PINB200_SPLIT_MIN_QUERIES (default; see set_option)
+SPLIT_MIN_QUERIES_WF = 1024  # == PINB200_SPLIT_MIN_QUERIES_WF: weighted_first maps on the tensor-core decode
+
+
+def uses_split(n: int, weighted_first: bool, dec=None) -> bool:
+    """Whether a batch of n queries runs as two launches (search, then decode) -- mirrors pinb200_query_sdf."""
+    wf = bool(weighted_first)
+    if wf and dec is not None:
+        v = dec.view
+        wf = v.hidden_dim == 64 and 1 <= v.n_hidden <= 2 and (v.in_dim - 3) in (8, 16, 32)
+    return n >= (SPLIT_MIN_QUERIES_WF if wf else SPLIT_MIN_QUERIES)
 
 
 def set_option(name: str, value: int) -> None:
     """Process-wide tunables of the query path (pinb200_set_option): "split_min_queries", "decode_variant"."""
-    global SPLIT_MIN_QUERIES
+    global SPLIT_MIN_QUERIES, SPLIT_MIN_QUERIES_WF
     _lib.check(_lib.load().pinb200_set_option(name.encode(), int(value)), "pinb200_set_option")
     if name == "split_min_queries":
         SPLIT_MIN_QUERIES = int(value) if int(value) > 0 else 32768
+        SPLIT_MIN_QUERIES_WF = int(value) if int(value) > 0 else 1024
+    elif name == "split_min_queries_wf":
+        SPLIT_MIN_QUERIES_WF = int(value) if int(value) > 0 else 1024
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -189,7 +202,7 @@ def _query_args(xyz, nn_k, weighted_first, training_mode, need_grad, color_dec, 
         if color_grad:
             qo.color_grad = _ptr(buf("color_grad", (n, cc, 3)))
     ws_ptr, ws_bytes = None, 0
-    if n >= SPLIT_MIN_QUERIES:  # large batch: scratch for the two-launch (search, then decode) pipeline
+    if n >= (SPLIT_MIN_QUERIES_WF if weighted_first else SPLIT_MIN_QUERIES):  # scratch for the two-launch pipeline
         need = int(_lib.load().pinb200_query_workspace_bytes(n))
         ws = o.get("_workspace")
         if ws is None or ws.numel() < need or ws.device != dev:
@@ -215,7 +228,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
                                _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), xyz.shape[0], C.byref(opts),
                                C.byref(qo), _stream())
     _lib.check(rc, "pinb200_query_sdf")
-    _count((2 if color_dec is not None else 1) + (1 if xyz.shape[0] >= SPLIT_MIN_QUERIES else 0))
+    _count((2 if color_dec is not None else 1) + (1 if uses_split(xyz.shape[0], weighted_first, dec) else 0))
     return o
 
 

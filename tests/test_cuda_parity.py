@@ -743,7 +743,7 @@ def test_host_facing_pipelined_query_equals_device_query():
             npm.query_sdf_host(q_host, dec, host, chunks=chunks)
             torch.cuda.current_stream().synchronize()
             piece = -(-n // chunks)
-            same_kernels = (n >= ops.SPLIT_MIN_QUERIES) == (piece >= ops.SPLIT_MIN_QUERIES)
+            same_kernels = ops.uses_split(n, cfg.weighted_first) == ops.uses_split(piece, cfg.weighted_first)
             for k, h in host.items():
                 r = ref[k].cpu()
                 if same_kernels or k in ("nn_count", "certainty", "sdf_std"):
