@@ -712,7 +712,8 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   QueryParams probe{};
   probe.dec = *sdf_dec;
   probe.opts = *opts;
-  const long long split_min = umma_decode_supported(probe) ? g_split_min_queries_wf : g_split_min_queries;
+  // (training-mode batches of the mapper are value-only and tile poorly at 16-26 k rows: they keep the general threshold)
+  const long long split_min = (umma_decode_supported(probe) && !opts->training_mode) ? g_split_min_queries_wf : g_split_min_queries;
   const bool split = opts->workspace && opts->workspace_bytes >= need && n >= split_min;
   if (split) {
     p.stash = reinterpret_cast<float*>(opts->workspace);

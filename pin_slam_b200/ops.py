@@ -12,9 +12,9 @@ SPLIT_MIN_QUERIES = 32768  # == PINB200_SPLIT_MIN_QUERIES (default; see set_opti
 SPLIT_MIN_QUERIES_WF = 1024  # == PINB200_SPLIT_MIN_QUERIES_WF: weighted_first maps on the tensor-core decode
 
 
-def uses_split(n: int, weighted_first: bool, dec=None) -> bool:
+def uses_split(n: int, weighted_first: bool, dec=None, training_mode: bool = False) -> bool:
     """Whether a batch of n queries runs as two launches (search, then decode) -- mirrors pinb200_query_sdf."""
-    wf = bool(weighted_first)
+    wf = bool(weighted_first) and not training_mode
     if wf and dec is not None:
         v = dec.view
         wf = v.hidden_dim == 64 and 1 <= v.n_hidden <= 2 and (v.in_dim - 3) in (8, 16, 32)
@@ -202,7 +202,7 @@ def _query_args(xyz, nn_k, weighted_first, training_mode, need_grad, color_dec, 
         if color_grad:
             qo.color_grad = _ptr(buf("color_grad", (n, cc, 3)))
     ws_ptr, ws_bytes = None, 0
-    if n >= (SPLIT_MIN_QUERIES_WF if weighted_first else SPLIT_MIN_QUERIES):  # scratch for the two-launch pipeline
+    if n >= (SPLIT_MIN_QUERIES_WF if (weighted_first and not training_mode) else SPLIT_MIN_QUERIES):  # scratch for the two-launch pipeline
         need = int(_lib.load().pinb200_query_workspace_bytes(n))
         ws = o.get("_workspace")
         if ws is None or ws.numel() < need or ws.device != dev:
@@ -228,7 +228,7 @@ def query_sdf(mh: MapHandle, dec: DecoderHandle, xyz: torch.Tensor, *, nn_k: int
                                _ptr(xyz, torch.float32), _ptr(query_ts, torch.int32), xyz.shape[0], C.byref(opts),
                                C.byref(qo), _stream())
     _lib.check(rc, "pinb200_query_sdf")
-    _count((2 if color_dec is not None else 1) + (1 if uses_split(xyz.shape[0], weighted_first, dec) else 0))
+    _count((2 if color_dec is not None else 1) + (1 if uses_split(xyz.shape[0], weighted_first, dec, training_mode) else 0))
     return o
 
 
