@@ -387,6 +387,13 @@ int pinb200_voxel_downsample(const float* points, int64_t n, float voxel_size, c
  * them, ORDER PRESERVED, to the o_* arrays (a second arena: the call does not work in place).  counts (device, 2 x i64):
  * [0] samples kept, [1] samples kept among the last n_tail (the current frame's).  scratch: pinb200_pool_filter_scratch(n)
  * i32.  Replaces six boolean-mask indexings (six reallocations of multi-million-row tensors per frame). */
+/* Loop-closure map surgery: row i of xyz [N,3] (and of quat [N,4] wxyz, may be NULL) is moved by the correction of
+   its frame t_i = ts_a[i] (or trunc((ts_a[i] + ts_b[i]) / 2) when ts_b is given: config.use_mid_ts):
+     xyz_i <- R_t xyz_i + t_t,   quat_i <- dquat_t (x) quat_i,      tf3x4 [n_ts,12] = rows of [R | t], dquat [n_ts,4].
+   Replaces model/neural_points.py:791-822 (adjust_map) and utils/mapper.py:527-531 (transform_data_pool). */
+int pinb200_frame_transform(float* xyz, float* quat, const int32_t* ts_a, const int32_t* ts_b, const float* tf3x4,
+                            const float* dquat, int64_t n, int32_t n_ts, void* stream);
+
 int64_t pinb200_pool_filter_scratch(int64_t n);
 int pinb200_pool_filter(const float* coord, const float* gcoord, const float* label, const float* weight,
                         const int32_t* ts, const float* color, int32_t color_channels, int64_t n, int64_t n_tail,

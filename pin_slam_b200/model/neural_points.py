@@ -538,10 +538,18 @@ class NeuralPoints(nn.Module):
             ts = ((self.point_ts_create + self.point_ts_update) / 2).int().long()
         else:
             ts = self.point_ts_create.long()
-        tf = pose_diff_torch[ts].to(self.neural_points)
-        self.neural_points = (tf[:, :3, :3] @ self.neural_points.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
-        dq = _rotmat_to_quat(pose_diff_torch[:, :3, :3])[ts].to(self.point_orientations)
-        self.point_orientations = _quat_multiply(dq, self.point_orientations)
+        if self.neural_points.is_cuda and self.neural_points.dtype == torch.float32:
+            # one streaming kernel over the points (pinb200_frame_transform); the per-frame quaternions are tiny
+            pts, ori = self.neural_points.clone(), self.point_orientations.contiguous().clone()
+            ops.frame_transform(pts, self.point_ts_create.contiguous(), pose_diff_torch, quat=ori,
+                                dquat=_rotmat_to_quat(pose_diff_torch[:, :3, :3]),
+                                ts_b=self.point_ts_update.contiguous() if self.config.use_mid_ts else None)
+            self.neural_points, self.point_orientations = pts, ori
+        else:
+            tf = pose_diff_torch[ts].to(self.neural_points)
+            self.neural_points = (tf[:, :3, :3] @ self.neural_points.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+            dq = _rotmat_to_quat(pose_diff_torch[:, :3, :3])[ts].to(self.point_orientations)
+            self.point_orientations = _quat_multiply(dq, self.point_orientations)
         self._invalidate()
 
     def recreate_hash(self, sensor_position: torch.Tensor, sensor_orientation: torch.Tensor, kept_points: bool = True,

@@ -501,3 +501,16 @@ class NcclComm:
         if cls._instance is None or cls._instance.device != torch.device(device):
             cls._instance = cls(device)
         return cls._instance
+
+
+def frame_transform(xyz: torch.Tensor, ts_a: torch.Tensor, pose_diff: torch.Tensor, quat: Optional[torch.Tensor] = None,
+                    dquat: Optional[torch.Tensor] = None, ts_b: Optional[torch.Tensor] = None) -> None:
+    """In place: xyz_i <- R_t xyz_i + t_t (and quat_i <- dquat_t (x) quat_i) with t = the frame of row i
+    (pinb200_frame_transform; adjust_map / transform_data_pool of the reference)."""
+    tf = pose_diff[:, :3, :].to(torch.float32).contiguous()
+    rc = _lib.load().pinb200_frame_transform(_ptr(xyz, torch.float32), _ptr(quat, torch.float32), _ptr(ts_a, torch.int32),
+                                             _ptr(ts_b, torch.int32), _ptr(tf, torch.float32),
+                                             _ptr(None if dquat is None else dquat.to(torch.float32).contiguous(), torch.float32),
+                                             xyz.shape[0], tf.shape[0], _stream())
+    _lib.check(rc, "pinb200_frame_transform")
+    _count()

@@ -242,8 +242,12 @@ class Mapper:
             self.used_poses = torch.as_tensor(src[: cur + 1], device=self.device, dtype=torch.float64)
 
     def transform_data_pool(self, pose_diff_torch):
-        tf = pose_diff_torch[self.time_pool.long()].to(self.global_coord_pool)
-        self.global_coord_pool = (tf[:, :3, :3] @ self.global_coord_pool.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+        g = self.global_coord_pool
+        if g.is_cuda and g.dtype == torch.float32 and g.is_contiguous():
+            ops.frame_transform(g, self.time_pool.contiguous(), pose_diff_torch)  # in place, one streaming kernel
+            return
+        tf = pose_diff_torch[self.time_pool.long()].to(g)
+        self.global_coord_pool = (tf[:, :3, :3] @ g.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
 
     # ------------------------------------------------------------------ per-frame preparation
     def dynamic_filter(self, points_torch, type_2_on: bool = True):

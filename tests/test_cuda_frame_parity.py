@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import pin_oracle as po
 from tests.helpers import load_npz, t
 
 pytestmark = pytest.mark.gpu
@@ -351,3 +352,58 @@ def test_unchanged_reference_tracker_runs_fused():
         if "color_err" in r:
             assert r["color_err"] == 0.0 and r["cgrad_err"] == 0.0, (name, r)
         assert r["eager_vs_fused_sdf"] <= 2e-6 and r["eager_vs_fused_grad"] <= 2e-4 * max(r["grad_scale"], 1e-3) * 50, (name, r)
+
+
+def test_cuda_loop_closure_transform_matches_reference():
+    """Row f4 on the device: pinb200_frame_transform (adjust_map / transform_data_pool of the reference,
+    model/neural_points.py:791-822, utils/mapper.py:527-531) against the reference's loop-closure fixture and, for
+    both time-stamp modes, against the torch formulation on random data."""
+    from pin_slam_b200 import ops
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import NeuralPoints
+    from pin_slam_b200.model.neural_points import _quat_multiply, _rotmat_to_quat
+
+    fx = load_npz("loop_kitti")
+    g = lambda k: fx["map." + k]  # noqa: E731
+    cfg = HotPathConfig.kitti(device=DEV, feature_dim=int(g("geo_features").shape[1]), buffer_size=int(g("buffer_size")),
+                              voxel_size_m=float(g("resolution")), local_map_radius=float(fx["cfg.local_map_radius"]))
+    npm = NeuralPoints(cfg)
+    npm.config.use_mid_ts = bool(fx["cfg.use_mid_ts"])
+    npm.neural_points = t(g("neural_points")).to(DEV)
+    npm.point_orientations = t(g("point_orientations")).to(DEV)
+    npm.point_ts_create = t(g("point_ts_create")).to(DEV)
+    npm.point_ts_update = t(g("point_ts_update")).to(DEV)
+    npm.adjust_map(t(fx["pose_diff"]).to(DEV))
+    assert npm.after_pgo
+    np.testing.assert_allclose(npm.neural_points.cpu().numpy(), fx["adjusted.neural_points"], rtol=1e-6, atol=2e-6)
+    q, qr = npm.point_orientations.cpu().numpy(), fx["adjusted.point_orientations"]
+    sign = np.sign((q * qr).sum(1, keepdims=True))  # q and -q are the same rotation
+    np.testing.assert_allclose(q * sign, qr, rtol=1e-5, atol=1e-6)
+
+    gen = torch.Generator().manual_seed(0)
+    n, nts = 200003, 37
+    xyz = torch.randn(n, 3, generator=gen) * 30
+    quat = torch.randn(n, 4, generator=gen)
+    quat = quat / quat.norm(dim=1, keepdim=True)
+    ts_a = torch.randint(0, nts, (n,), generator=gen).int()
+    ts_b = torch.randint(0, nts, (n,), generator=gen).int()
+    pose = torch.eye(4, dtype=torch.float64).repeat(nts, 1, 1)
+    for i in range(nts):
+        pose[i, :3, :3] = po.expmap(0.05 * torch.randn(3, generator=gen, dtype=torch.float64))
+        pose[i, :3, 3] = torch.randn(3, generator=gen, dtype=torch.float64)
+    dq_frames = _rotmat_to_quat(pose[:, :3, :3])
+    for mid in (False, True):
+        ts = ((ts_a + ts_b) / 2).int().long() if mid else ts_a.long()
+        tf = pose[ts].float()
+        ref_xyz = (tf[:, :3, :3] @ xyz.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]
+        ref_q = _quat_multiply(dq_frames[ts].float(), quat)
+        x, qd = xyz.to(DEV).clone(), quat.to(DEV).clone()
+        ops.frame_transform(x, ts_a.to(DEV), pose.to(DEV), quat=qd, dquat=dq_frames.to(DEV), ts_b=ts_b.to(DEV) if mid else None)
+        np.testing.assert_allclose(x.cpu().numpy(), ref_xyz.numpy(), rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(qd.cpu().numpy(), ref_q.numpy(), rtol=1e-6, atol=1e-6)
+    # pool form: no orientations
+    x = xyz.to(DEV).clone()
+    ops.frame_transform(x, ts_a.to(DEV), pose.to(DEV))
+    tf = pose[ts_a.long()].float()
+    np.testing.assert_allclose(x.cpu().numpy(), ((tf[:, :3, :3] @ xyz.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]).numpy(),
+                               rtol=1e-6, atol=1e-5)
