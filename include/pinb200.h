@@ -387,6 +387,20 @@ int pinb200_voxel_downsample(const float* points, int64_t n, float voxel_size, c
  * them, ORDER PRESERVED, to the o_* arrays (a second arena: the call does not work in place).  counts (device, 2 x i64):
  * [0] samples kept, [1] samples kept among the last n_tail (the current frame's).  scratch: pinb200_pool_filter_scratch(n)
  * i32.  Replaces six boolean-mask indexings (six reallocations of multi-million-row tensors per frame). */
+/* Map growth (model/neural_points.py:311-392 NeuralPoints.update): tests the n voxel-down-sampled candidates [n,3]
+   against the hash table (empty slot | owner farther than sqrt(3) voxels | owner not refreshed within `diff_travel` of
+   travel distance when temporal_on; grow_all: every candidate, the first / reboot frame) and appends the passing ones, in
+   candidate order, to the caller's arenas behind row n_points: points [cap,3], orient [cap,4] (identity), ts_create /
+   ts_update [cap] (cur_ts), certainty [cap] (0).  The table is updated with the reference's sequential semantics (the
+   last candidate of a slot decides its owner).  n_new (device int64) receives the number of appended points;
+   scratch: pinb200_map_grow_scratch(n) int32 elements.  The feature rows are initialised by the caller (torch RNG
+   stream of the reference). */
+int64_t pinb200_map_grow_scratch(int64_t n);
+int pinb200_map_grow(const float* cand, int64_t n, int32_t* table, int64_t buffer_size, float resolution, float* points,
+                     float* orient, int32_t* ts_create, int32_t* ts_update, float* certainty, int64_t n_points,
+                     int64_t capacity, const float* travel_dist, int32_t cur_ts, int32_t grow_all, int32_t temporal_on,
+                     float diff_travel, float far2 /* 3 * resolution^2 */, int32_t* scratch, int64_t* n_new, void* stream);
+
 /* Loop-closure map surgery: row i of xyz [N,3] (and of quat [N,4] wxyz, may be NULL) is moved by the correction of
    its frame t_i = ts_a[i] (or trunc((ts_a[i] + ts_b[i]) / 2) when ts_b is given: config.use_mid_ts):
      xyz_i <- R_t xyz_i + t_t,   quat_i <- dquat_t (x) quat_i,      tf3x4 [n_ts,12] = rows of [R | t], dquat [n_ts,4].

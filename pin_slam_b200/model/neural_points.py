@@ -84,6 +84,55 @@ def voxel_down_sample_min_value(points: torch.Tensor, voxel_size: float, value: 
     return best % n
 
 
+class _MapArena:
+    """Fixed-capacity storage behind the global map tensors.  The reference grows seven
+    tensors with torch.cat every frame; here `NeuralPoints.neural_points`, `.point_orientations`, `.point_ts_create`,
+    `.point_ts_update`, `.point_certainties`, `.geo_features` (+ pad row) and `.color_features` are views `[:count]` of
+    these buffers and pinb200_map_grow appends in place.  Tensors assigned from outside (pruning, rehash, loop
+    closure, checkpoints, tests) are adopted on the next update."""
+
+    NAMES = ("neural_points", "point_orientations", "point_ts_create", "point_ts_update", "point_certainties")
+
+    def __init__(self):
+        self.buf, self.cap = None, 0
+
+    def owns(self, npm):
+        if self.buf is None:
+            return False
+        for name in self.NAMES + ("geo_features",):
+            if getattr(npm, name).data_ptr() != self.buf[name].data_ptr():
+                return False
+        return npm.color_features is None or npm.color_features.data_ptr() == self.buf["color_features"].data_ptr()
+
+    def reserve(self, npm, rows):
+        if self.owns(npm) and rows <= self.cap:
+            return
+        n, dev = npm.count(), npm.neural_points.device
+        cap = max(int(rows * 1.5) + 4096, 1 << 16)
+        new = {"neural_points": torch.empty((cap, 3), dtype=torch.float32, device=dev),
+               "point_orientations": torch.empty((cap, 4), dtype=torch.float32, device=dev),
+               "point_ts_create": torch.empty((cap,), dtype=torch.int32, device=dev),
+               "point_ts_update": torch.empty((cap,), dtype=torch.int32, device=dev),
+               "point_certainties": torch.empty((cap,), dtype=torch.float32, device=dev),
+               "geo_features": torch.empty((cap + 1, npm.geo_features.shape[1]), dtype=torch.float32, device=dev),
+               "color_features": None if npm.color_features is None else
+               torch.empty((cap + 1, npm.color_features.shape[1]), dtype=torch.float32, device=dev)}
+        for name in self.NAMES:
+            new[name][:n].copy_(getattr(npm, name))
+        new["geo_features"][: n + 1].copy_(npm.geo_features)
+        if npm.color_features is not None:
+            new["color_features"][: n + 1].copy_(npm.color_features)
+        self.buf, self.cap = new, cap
+        self.bind(npm, n)
+
+    def bind(self, npm, n):
+        for name in self.NAMES:
+            setattr(npm, name, self.buf[name][:n])
+        npm.geo_features = self.buf["geo_features"][: n + 1]
+        if self.buf["color_features"] is not None:
+            npm.color_features = self.buf["color_features"][: n + 1]
+
+
 class NeuralPoints(nn.Module):
     STRICT_REFERENCE_G2L = True  # reproduce the reference's global2local fill value (see reset_local_map)
 
@@ -230,6 +279,8 @@ class NeuralPoints(nn.Module):
         res = self.resolution
         pick = voxel_down_sample(points, res)
         cand = points[pick]
+        if cand.is_cuda and cand.dtype == torch.float32 and self.neural_points.dtype == torch.float32:
+            return self._update_device(cand.contiguous(), sensor_position, sensor_orientation, cur_ts)
         slot = self._slots(cand)
         owner = self.buffer_pt_index[slot].long()
         if (not self.is_empty()) and (cur_ts != self.reboot_ts):
@@ -264,6 +315,39 @@ class NeuralPoints(nn.Module):
             (self.point_certainties, torch.zeros(n_new, device=self.device, dtype=self.dtype)), 0)
         self.reset_local_map(sensor_position, sensor_orientation, cur_ts, reboot_map=True)
         return ratio
+
+    def _update_device(self, cand, sensor_position, sensor_orientation, cur_ts):
+        """update() on the device: pinb200_map_grow appends into the arenas and rewrites the hash table (4 launches
+        instead of ~40 torch ops and seven torch.cat reallocations); ONE host sync remains -- the number of new points,
+        which sizes the reference's randn draw for the new feature rows (the RNG stream must advance exactly as in
+        model/neural_points.py:395-411, also at feature_std 0)."""
+        arena = self.__dict__.get("_arena")
+        if arena is None:
+            arena = self.__dict__["_arena"] = _MapArena()
+        n0, nc = self.count(), cand.shape[0]
+        arena.reserve(self, n0 + nc)
+        sc = self.__dict__.get("_grow_scratch")
+        need = 3 * nc + (nc + 255) // 256 + 8
+        if sc is None or sc[0].numel() < need or sc[0].device != cand.device:
+            sc = self.__dict__["_grow_scratch"] = (torch.empty(int(need * 1.5), dtype=torch.int32, device=cand.device),
+                                                   torch.zeros(1, dtype=torch.int64, device=cand.device))
+        grow_all = self.is_empty() or cur_ts == self.reboot_ts
+        b = arena.buf
+        ops.map_grow(cand, self.buffer_pt_index, self.resolution, b["neural_points"], b["point_orientations"],
+                     b["point_ts_create"], b["point_ts_update"], b["point_certainties"], n0,
+                     None if grow_all else self.travel_dist, cur_ts, grow_all, self.temporal_local_map_on,
+                     self.diff_travel_dist_local, sc[0], sc[1])
+        n_new = int(sc[1].item())
+        # one extra (padding) row; the randn draw is kept even at std 0 so the RNG stream matches the reference
+        init = self.geo_feature_std * torch.randn(n_new + 1, self.geo_feature_dim, device=self.device, dtype=self.dtype)
+        b["geo_features"][n0: n0 + n_new + 1].copy_(init)
+        if self.color_features is not None:
+            init = self.color_feature_std * torch.randn(n_new + 1, self.color_feature_dim, device=self.device,
+                                                        dtype=self.dtype)
+            b["color_features"][n0: n0 + n_new + 1].copy_(init)
+        arena.bind(self, n0 + n_new)
+        self.reset_local_map(sensor_position, sensor_orientation, cur_ts, reboot_map=True)
+        return n_new / nc
 
     def reset_local_map(self, sensor_position: torch.Tensor, sensor_orientation: torch.Tensor, cur_ts: int,
                         use_travel_dist: bool = True, diff_ts_local: int = 50, reboot_map: bool = False):
@@ -633,6 +717,11 @@ class NeuralPoints(nn.Module):
         state["_handles"] = {}  # raw device pointers never travel
         state["_rec_tables"] = {}  # derived data (800 MB per index space at the default buffer_size)
         state.pop("_host_pipe", None)  # CUDA streams / staging buffers of query_sdf_host
+        state.pop("_arena", None)
+        state.pop("_grow_scratch", None)
+        for k, v in list(state.items()):  # views of the growth arenas: pickle the rows, not the capacity
+            if torch.is_tensor(v) and v.untyped_storage().nbytes() > 2 * v.numel() * v.element_size() + 4096:
+                state[k] = v.clone()
         return state
 
 

@@ -514,3 +514,23 @@ def frame_transform(xyz: torch.Tensor, ts_a: torch.Tensor, pose_diff: torch.Tens
                                              xyz.shape[0], tf.shape[0], _stream())
     _lib.check(rc, "pinb200_frame_transform")
     _count()
+
+
+def map_grow(cand: torch.Tensor, table: torch.Tensor, resolution: float, points, orient, ts_create, ts_update, certainty,
+             n_points: int, travel_dist, cur_ts: int, grow_all: bool, temporal_on: bool, diff_travel: float, scratch,
+             n_new: torch.Tensor) -> None:
+    """pinb200_map_grow: append the candidates that pass the reference's growth test to the arenas (rows n_points..),
+    update the hash table; `n_new` (device int64[1]) receives the count."""
+    lib = _lib.load()
+    n = cand.shape[0]
+    need = int(lib.pinb200_map_grow_scratch(n))
+    if scratch.numel() < need:
+        raise RuntimeError("map_grow: scratch too small")
+    rc = lib.pinb200_map_grow(_ptr(cand, torch.float32), n, _ptr(table, torch.int32), table.shape[0], float(resolution),
+                              _ptr(points, torch.float32), _ptr(orient, torch.float32), _ptr(ts_create, torch.int32),
+                              _ptr(ts_update, torch.int32), _ptr(certainty, torch.float32), int(n_points), points.shape[0],
+                              _ptr(travel_dist, torch.float32), int(cur_ts), int(bool(grow_all)), int(bool(temporal_on)),
+                              float(diff_travel), float(3 * resolution**2), _ptr(scratch, torch.int32), n_new.data_ptr(),
+                              _stream())
+    _lib.check(rc, "pinb200_map_grow")
+    _count(4)
