@@ -15,10 +15,11 @@ Differences in storage (values identical to the reference):
   * there is no CPU path: the map lives on a CUDA device and every query runs a
     kernel from libpinb200.so (a missing library raises, nothing falls back).
 
-Map maintenance (update / reset_local_map / prune / rehash) is host-orchestrated
-PyTorch in this round (SURVEY.md section 8 f1 marks it "next"); it consumes the
-RNG stream exactly like the reference (randn for the new feature rows even when
-feature_std == 0).
+Map maintenance: voxel down-sampling, map growth (`update`, into fixed-capacity
+arenas) and the loop-closure point transform run as kernels (SURVEY.md section 8
+f1 / f4); reset_local_map / prune / rehash are host-orchestrated PyTorch.  The RNG
+stream is consumed exactly like the reference (randn for the new feature rows even
+when feature_std == 0).
 """
 import sys
 
