@@ -97,3 +97,33 @@ def test_install_registers_reference_module_names():
     out = subprocess.check_output([sys.executable, "-c", code]).decode().split()
     assert out == ["pin_slam_b200.model.neural_points", "pin_slam_b200.model.decoder", "pin_slam_b200.utils.tracker",
                    "pin_slam_b200.utils.mapper"]
+
+
+def test_run_time_options_and_split_rule():
+    """pinb200_set_option / ops.uses_split (no GPU needed: host-side state only): known options are accepted and
+    mirrored in ops, unknown ones and out-of-range values fail loudly, workspace sizes cover stash + seeds."""
+    from pin_slam_b200 import _lib, ops
+
+    lib = _lib.load()
+    assert ops.uses_split(2048, True) and not ops.uses_split(512, True)
+    assert not ops.uses_split(20000, False) and ops.uses_split(40000, False)
+    assert not ops.uses_split(20000, True, training_mode=True)  # mapper batches keep the general threshold
+    ops.set_option("split_min_queries", 64)
+    try:
+        assert ops.uses_split(64, True) and ops.uses_split(64, False)
+    finally:
+        ops.set_option("split_min_queries", 0)
+    assert ops.SPLIT_MIN_QUERIES == 32768 and ops.SPLIT_MIN_QUERIES_WF == 1024
+    ops.set_option("split_min_queries_wf", 4096)
+    assert not ops.uses_split(2048, True)
+    ops.set_option("split_min_queries_wf", 0)
+    for variant in (0, 1):
+        ops.set_option("decode_variant", variant)
+    with pytest.raises(RuntimeError):
+        ops.set_option("decode_variant", 7)
+    with pytest.raises(RuntimeError):
+        ops.set_option("no_such_option", 1)
+    # 32 queries per tile: stash (1536 floats) + forward-mode seeds (1056 floats)
+    assert lib.pinb200_query_workspace_bytes(1) == (1536 + 1056) * 4
+    assert lib.pinb200_query_workspace_bytes(33) == 2 * (1536 + 1056) * 4
+    assert lib.pinb200_map_grow_scratch(1000) >= 3 * 1000 + 4
