@@ -387,6 +387,18 @@ int pinb200_voxel_downsample(const float* points, int64_t n, float voxel_size, c
  * them, ORDER PRESERVED, to the o_* arrays (a second arena: the call does not work in place).  counts (device, 2 x i64):
  * [0] samples kept, [1] samples kept among the last n_tail (the current frame's).  scratch: pinb200_pool_filter_scratch(n)
  * i32.  Replaces six boolean-mask indexings (six reallocations of multi-million-row tensors per frame). */
+/* Per-ray training samples (utils/data_sampler.py:18-260 DataSampler.sample), ray-major output of
+   total = 1 + n_surface + n_front + n_behind samples per point: the end point, Gaussian samples around it
+   (z_surf [n_surface*n] standard-normal draws, element j*n + i belongs to point i), uniform samples in front
+   (u_front [n_front*n]) and behind (u_behind [n_behind*n]); label = signed distance along the ray, weight with the
+   reference's distance / drop-off terms and a negative sign for free-space samples; colours copied for the surface
+   samples, 0 for free space.  The random draws are the caller's (torch generator of the reference). */
+int pinb200_ray_samples(const float* points, const float* colors, int32_t color_channels, int64_t n, const float* z_surf,
+                        const float* u_front, const float* u_behind, int32_t n_surface, int32_t n_front, int32_t n_behind,
+                        float sigma, float free_begin_ratio, float free_end_dist, float max_range, int32_t dist_weight_on,
+                        float dist_weight_scale, int32_t behind_dropoff_on, float* coord, float* label, float* weight,
+                        float* color, void* stream);
+
 /* Map growth (model/neural_points.py:311-392 NeuralPoints.update): tests the n voxel-down-sampled candidates [n,3]
    against the hash table (empty slot | owner farther than sqrt(3) voxels | owner not refreshed within `diff_travel` of
    travel distance when temporal_on; grow_all: every candidate, the first / reboot frame) and appends the passing ones, in

@@ -534,3 +534,23 @@ def map_grow(cand: torch.Tensor, table: torch.Tensor, resolution: float, points,
                               _stream())
     _lib.check(rc, "pinb200_map_grow")
     _count(4)
+
+
+def ray_samples(points, colors, z_surf, u_front, u_behind, ns, nf, nb, sigma, begin_ratio, end_dist, max_range,
+                dist_weight_on, dist_weight_scale, behind_dropoff_on):
+    """pinb200_ray_samples: (coord [n*total,3], label, weight, color or None) in ray-major order."""
+    n, dev = points.shape[0], points.device
+    total = 1 + ns + nf + nb
+    coord = torch.empty((n * total, 3), dtype=torch.float32, device=dev)
+    label = torch.empty((n * total,), dtype=torch.float32, device=dev)
+    weight = torch.empty((n * total,), dtype=torch.float32, device=dev)
+    color = None if colors is None else torch.empty((n * total, colors.shape[1]), dtype=torch.float32, device=dev)
+    rc = _lib.load().pinb200_ray_samples(_ptr(points, torch.float32), _ptr(colors, torch.float32),
+                                         0 if colors is None else colors.shape[1], n, _ptr(z_surf, torch.float32),
+                                         _ptr(u_front, torch.float32), _ptr(u_behind, torch.float32), int(ns), int(nf), int(nb),
+                                         float(sigma), float(begin_ratio), float(end_dist), float(max_range),
+                                         int(bool(dist_weight_on)), float(dist_weight_scale), int(bool(behind_dropoff_on)),
+                                         _ptr(coord), _ptr(label), _ptr(weight), _ptr(color), _stream())
+    _lib.check(rc, "pinb200_ray_samples")
+    _count()
+    return coord, label, weight, color

@@ -29,6 +29,8 @@ class DataSampler:
     `surface_sample_n` Gaussian samples around it, `free_front_n` uniform samples in front and
     `free_behind_n` behind; label = signed distance along the ray (positive in front)."""
 
+    FUSED = True  # CUDA inputs: the arithmetic runs in pinb200_ray_samples (the RNG draws stay torch calls)
+
     def __init__(self, config):
         self.config = config
         self.dev = config.device
@@ -40,6 +42,16 @@ class DataSampler:
         ns, nf, nb = c.surface_sample_n, c.free_front_n, c.free_behind_n
         total = 1 + ns + nf + nb
         sigma = c.surface_sample_range_m
+        if self.FUSED and points.is_cuda and points.dtype == torch.float32 and normals is None and n > 0:
+            # the reference's RNG draws (same generator, order and sizes), everything else in one kernel
+            z_surf = torch.randn(n * ns, 1, device=dev)
+            u_front = torch.rand(n * nf, 1, device=dev)
+            u_behind = torch.rand(n * nb, 1, device=dev)
+            coord, label, weight, color_label = ops.ray_samples(
+                points.contiguous(), None if colors is None else colors.contiguous(), z_surf, u_front, u_behind, ns, nf, nb,
+                sigma, c.free_sample_begin_ratio, c.free_sample_end_dist_m, c.max_range, c.dist_weight_on,
+                c.dist_weight_scale, c.behind_dropoff_on)
+            return coord, label, None, None, color_label, weight
         dist = torch.linalg.norm(points, dim=1, keepdim=True)  # [n,1]
         # same RNG draws, in the same order, as the reference sampler
         disp_surf = torch.randn(n * ns, 1, device=dev) * sigma

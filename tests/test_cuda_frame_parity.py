@@ -407,3 +407,45 @@ def test_cuda_loop_closure_transform_matches_reference():
     tf = pose[ts_a.long()].float()
     np.testing.assert_allclose(x.cpu().numpy(), ((tf[:, :3, :3] @ xyz.unsqueeze(-1)).squeeze(-1) + tf[:, :3, 3]).numpy(),
                                rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["kitti", "replica"])
+def test_cuda_ray_sampler_kernel_equals_torch_formulation(kind):
+    """Row f2: pinb200_ray_samples against the torch port of utils/data_sampler.py:18-260 (which the CPU tests pin to
+    the reference's fixtures) on the same RNG draws: coordinates, labels, weights, colours, ray-major order."""
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.utils.mapper import DataSampler
+
+    cfg = HotPathConfig.kitti(device=DEV) if kind == "kitti" else HotPathConfig.replica(device=DEV)
+    g = torch.Generator().manual_seed(5)
+    n = 7013
+    pts = (torch.randn(n, 3, generator=g) * (20.0 if kind == "kitti" else 2.0)).to(DEV)
+    col = torch.rand(n, 3, generator=g).to(DEV) if kind == "replica" else None
+    smp = DataSampler(cfg)
+    out = {}
+    for fused in (True, False):
+        DataSampler.FUSED = fused
+        try:
+            torch.manual_seed(11)
+            out[fused] = smp.sample(pts, None, None, col)
+        finally:
+            DataSampler.FUSED = True
+    a, b = out[True], out[False]
+    for x, y, tol in ((a[0], b[0], 2e-6), (a[1], b[1], 2e-6), (a[5], b[5], 2e-6)):
+        np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=tol, atol=tol * 10)
+    assert (a[4] is None) == (b[4] is None)
+    if a[4] is not None:
+        assert torch.equal(a[4], b[4])
+    assert torch.equal(torch.sign(a[5]), torch.sign(b[5]))
+    # both paths leave the generator in the same state
+    torch.manual_seed(11)
+    smp.sample(pts, None, None, col)
+    r1 = torch.rand(4, device=DEV)
+    DataSampler.FUSED = False
+    try:
+        torch.manual_seed(11)
+        smp.sample(pts, None, None, col)
+        r2 = torch.rand(4, device=DEV)
+    finally:
+        DataSampler.FUSED = True
+    assert torch.equal(r1, r2)
