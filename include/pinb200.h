@@ -387,6 +387,27 @@ int pinb200_voxel_downsample(const float* points, int64_t n, float voxel_size, c
  * them, ORDER PRESERVED, to the o_* arrays (a second arena: the call does not work in place).  counts (device, 2 x i64):
  * [0] samples kept, [1] samples kept among the last n_tail (the current frame's).  scratch: pinb200_pool_filter_scratch(n)
  * i32.  Replaces six boolean-mask indexings (six reallocations of multi-million-row tensors per frame). */
+/* Local-map reset (model/neural_points.py:424-513 NeuralPoints.reset_local_map), split around the one host sync (the
+   local point count shapes the local tensors).
+   _select: keep_i = recent_i & near_i -> local_mask [n+1] (last entry 1: the padding row), counts = {recent points,
+            local points} (device int64[2]); recent = travel-distance window (use_travel_dist) or time-stamp window around
+            ts_create (or the truncated mean with ts_update: use_mid_ts), optionally only ts >= reboot_ts, everything if
+            fewer than 100 are recent or temporal_on = 0; near = |p_i - sensor|^2 < radius2, evaluated in float64 when the
+            sensor position is float64 (torch type promotion).  scratch: pinb200_local_map_scratch(n) int32.
+   _gather: idx_pad [n_local+1] int64 (ascending global ids, then n), global2local [n+1] (local id | miss_value outside
+            the local map | -1 for the padding entry), and the gathered positions / orientations / certainties /
+            update stamps. */
+int64_t pinb200_local_map_scratch(int64_t n);
+int pinb200_local_map_select(const float* points, const int32_t* ts_create, const int32_t* ts_update, const float* travel_dist,
+                             int64_t n, int32_t cur_ts, int32_t temporal_on, int32_t use_mid_ts, int32_t use_travel_dist,
+                             int32_t diff_ts_local, int32_t reboot_map, int32_t reboot_ts, float diff_travel,
+                             const void* sensor_pos, int32_t sensor_is_f64, double radius2, uint8_t* local_mask,
+                             int32_t* scratch, int64_t* counts, void* stream);
+int pinb200_local_map_gather(const float* points, const float* orient, const float* certainty, const int32_t* ts_update,
+                             const uint8_t* local_mask, const int32_t* scratch, int64_t n, int64_t n_local, int32_t miss_value,
+                             int64_t* idx_pad, int32_t* global2local, float* l_points, float* l_orient, float* l_certainty,
+                             int32_t* l_ts_update, void* stream);
+
 /* Per-ray training samples (utils/data_sampler.py:18-260 DataSampler.sample), ray-major output of
    total = 1 + n_surface + n_front + n_behind samples per point: the end point, Gaussian samples around it
    (z_surf [n_surface*n] standard-normal draws, element j*n + i belongs to point i), uniform samples in front

@@ -100,6 +100,12 @@ SIGNATURES = {
     "pinb200_voxel_table_size": (C.c_int64, [C.c_int64]),
     "pinb200_voxel_downsample": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_f32p, C.c_void_p, C.c_void_p, C.c_int64,
                                            c_i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pinb200_local_map_scratch": (C.c_int64, [C.c_int64]),
+    "pinb200_local_map_select": (C.c_int, [c_f32p, c_i32p, c_i32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32,
+                                           C.c_double, C.c_void_p, c_i32p, C.c_void_p, C.c_void_p]),
+    "pinb200_local_map_gather": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i32p, C.c_void_p, c_i32p, C.c_int64, C.c_int64,
+                                           C.c_int32, C.c_void_p, c_i32p, c_f32p, c_f32p, c_f32p, c_i32p, C.c_void_p]),
     "pinb200_ray_samples": (C.c_int, [c_f32p, c_f32p, C.c_int32, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_int32,
                                       c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),

@@ -16,8 +16,8 @@ Differences in storage (values identical to the reference):
     kernel from libpinb200.so (a missing library raises, nothing falls back).
 
 Map maintenance: voxel down-sampling, map growth (`update`, into fixed-capacity
-arenas) and the loop-closure point transform run as kernels (SURVEY.md section 8
-f1 / f4); reset_local_map / prune / rehash are host-orchestrated PyTorch.  The RNG
+arenas), the local-map reset and the loop-closure point transform run as kernels
+(SURVEY.md section 8 f1 / f4); prune / rehash are host-orchestrated PyTorch.  The RNG
 stream is consumed exactly like the reference (randn for the new feature rows even
 when feature_std == 0).
 """
@@ -355,6 +355,10 @@ class NeuralPoints(nn.Module):
         self.cur_ts = cur_ts
         self.max_ts = max(self.max_ts, cur_ts)
         n = self.count()
+        if (self.neural_points.is_cuda and self.neural_points.dtype == torch.float32 and torch.is_tensor(sensor_position)
+                and sensor_position.is_cuda and sensor_position.dtype in (torch.float32, torch.float64)):
+            return self._reset_local_map_device(sensor_position, sensor_orientation, cur_ts, use_travel_dist,
+                                                diff_ts_local, reboot_map)
         if self.temporal_local_map_on:
             if self.config.use_mid_ts:
                 ts_used = ((self.point_ts_create + self.point_ts_update) / 2).int()
@@ -390,6 +394,45 @@ class NeuralPoints(nn.Module):
         g2l = torch.full((n + 1,), miss, dtype=torch.int32, device=self.device)
         g2l[idx] = torch.arange(n_local, dtype=torch.int32, device=self.device)
         g2l[-1] = -1
+        self.global2local = g2l
+        self.local_geo_features = nn.Parameter(self.geo_features.index_select(0, idx_pad))
+        if self.color_features is not None:
+            self.local_color_features = nn.Parameter(self.color_features.index_select(0, idx_pad))
+        self.local_orientation = sensor_orientation
+        self._invalidate()
+
+    def _reset_local_map_device(self, sensor_position, sensor_orientation, cur_ts, use_travel_dist, diff_ts_local,
+                                reboot_map):
+        """reset_local_map on the device: keep flags + scan (pinb200_local_map_select), ONE host sync for the local point
+        count, then index list / global2local / gathers in one launch (pinb200_local_map_gather)."""
+        n, dev = self.count(), self.neural_points.device
+        sc = self.__dict__.get("_local_scratch")
+        need = (n + 1 + 255) // 256 + 1
+        if sc is None or sc[0].numel() < need or sc[0].device != dev:
+            sc = self.__dict__["_local_scratch"] = (torch.empty(int(need * 1.5) + 64, dtype=torch.int32, device=dev),
+                                                    torch.zeros(2, dtype=torch.int64, device=dev))
+        mask = torch.empty(n + 1, dtype=torch.bool, device=dev)
+        pts, ori = self.neural_points.contiguous(), self.point_orientations.contiguous()
+        cert, tsu = self.point_certainties.contiguous(), self.point_ts_update.contiguous()
+        temporal = self.temporal_local_map_on
+        ops.local_map_select(pts, self.point_ts_create.contiguous() if temporal else None,
+                             tsu if (temporal and self.config.use_mid_ts) else None,
+                             self.travel_dist if (temporal and use_travel_dist) else None, cur_ts, temporal,
+                             self.config.use_mid_ts, use_travel_dist, diff_ts_local, reboot_map, self.reboot_ts,
+                             self.diff_travel_dist_local, sensor_position, self.local_map_radius**2, mask, sc[0], sc[1])
+        n_local = int(sc[1][1].item())
+        idx_pad = torch.empty(n_local + 1, dtype=torch.int64, device=dev)
+        g2l = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        self.local_neural_points = torch.empty((n_local, 3), dtype=torch.float32, device=dev)
+        self.local_point_orientations = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
+        self.local_point_certainties = torch.empty((n_local,), dtype=torch.float32, device=dev)
+        self.local_point_ts_update = torch.empty((n_local,), dtype=torch.int32, device=dev)
+        # reference quirk Q1 (model/neural_points.py:498): points outside the local map translate to local id 1
+        miss = 1 if (self.STRICT_REFERENCE_G2L and n_local + 1 > 2) else -1
+        ops.local_map_gather(pts, ori, cert, tsu, mask, sc[0], n_local, miss, idx_pad, g2l, self.local_neural_points,
+                             self.local_point_orientations, self.local_point_certainties, self.local_point_ts_update)
+        self.local_mask = mask
+        self._local_idx = idx_pad
         self.global2local = g2l
         self.local_geo_features = nn.Parameter(self.geo_features.index_select(0, idx_pad))
         if self.color_features is not None:
@@ -720,6 +763,7 @@ class NeuralPoints(nn.Module):
         state.pop("_host_pipe", None)  # CUDA streams / staging buffers of query_sdf_host
         state.pop("_arena", None)
         state.pop("_grow_scratch", None)
+        state.pop("_local_scratch", None)
         for k, v in list(state.items()):  # views of the growth arenas: pickle the rows, not the capacity
             if torch.is_tensor(v) and v.untyped_storage().nbytes() > 2 * v.numel() * v.element_size() + 4096:
                 state[k] = v.clone()

@@ -554,3 +554,29 @@ def ray_samples(points, colors, z_surf, u_front, u_behind, ns, nf, nb, sigma, be
     _lib.check(rc, "pinb200_ray_samples")
     _count()
     return coord, label, weight, color
+
+
+def local_map_select(points, ts_create, ts_update, travel_dist, cur_ts, temporal_on, use_mid_ts, use_travel_dist,
+                     diff_ts_local, reboot_map, reboot_ts, diff_travel, sensor_pos, radius2, local_mask, scratch, counts):
+    """pinb200_local_map_select: keep flags -> local_mask [n+1] (bool), counts = {recent, n_local} (device int64[2])."""
+    if sensor_pos.dtype not in (torch.float32, torch.float64) or not sensor_pos.is_cuda:
+        raise RuntimeError("local_map_select: sensor position must be a float32 / float64 CUDA tensor")
+    rc = _lib.load().pinb200_local_map_select(
+        _ptr(points, torch.float32), _ptr(ts_create, torch.int32), _ptr(ts_update, torch.int32),
+        _ptr(travel_dist, torch.float32), points.shape[0], int(cur_ts), int(bool(temporal_on)), int(bool(use_mid_ts)),
+        int(bool(use_travel_dist)), int(diff_ts_local), int(bool(reboot_map)), int(reboot_ts), float(diff_travel),
+        sensor_pos.contiguous().data_ptr(), int(sensor_pos.dtype == torch.float64), float(radius2), local_mask.data_ptr(),
+        _ptr(scratch, torch.int32), counts.data_ptr(), _stream())
+    _lib.check(rc, "pinb200_local_map_select")
+    _count(3)
+
+
+def local_map_gather(points, orient, certainty, ts_update, local_mask, scratch, n_local, miss, idx_pad, g2l, l_points,
+                     l_orient, l_cert, l_ts):
+    rc = _lib.load().pinb200_local_map_gather(
+        _ptr(points, torch.float32), _ptr(orient, torch.float32), _ptr(certainty, torch.float32),
+        _ptr(ts_update, torch.int32), local_mask.data_ptr(), _ptr(scratch, torch.int32), points.shape[0], int(n_local),
+        int(miss), idx_pad.data_ptr(), _ptr(g2l, torch.int32), _ptr(l_points, torch.float32), _ptr(l_orient, torch.float32),
+        _ptr(l_cert, torch.float32), _ptr(l_ts, torch.int32), _stream())
+    _lib.check(rc, "pinb200_local_map_gather")
+    _count()
