@@ -31,6 +31,9 @@ template <bool SEEDS>
 __global__ void __launch_bounds__(128, 4) search_kernel(const __grid_constant__ QueryParams p) {
   extern __shared__ __align__(16) float smem[];
   uint32_t* s_delta = reinterpret_cast<uint32_t*>(smem);
+  // programmatic dependent launch: the decode launch may start its prologue (TMEM, mbarriers, weight staging) on the
+  // SMs this grid's tail frees; it waits (griddepcontrol.wait) before it reads anything written here
+  asm volatile("griddepcontrol.launch_dependents;");
   fill_probe_deltas(p.map, s_delta);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -725,6 +728,7 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
     if (rc) return rc;
   }
   // decode: tcgen05 tiles of 128 queries where the configuration allows it, else the warp-level mma.sync kernel
+  p.pdl = split ? 1 : 0;  // only the launch that directly follows the search launch
   auto decode = [&](QueryParams& qp) {
     if (split && umma_decode_supported(qp))
       return g_decode_variant == 1 ? dispatch_wsq(qp, (cudaStream_t)stream) : dispatch_decode_umma(qp, (cudaStream_t)stream);
@@ -734,6 +738,7 @@ extern "C" int pinb200_query_sdf(const pinb200_map_view* map, const pinb200_deco
   if (rc) return rc;
   if (color_dec) {  // second launch: decode the colour features with the kNN the first launch saved
     QueryParams c = p;
+    c.pdl = 0;
     c.dec = *color_dec;
     c.feat = map->color_feat;
     c.use_saved_knn = split ? 0 : 1;  // the split pipeline re-uses the stash instead

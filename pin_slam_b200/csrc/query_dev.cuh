@@ -49,6 +49,7 @@ struct QueryParams {
   int qpt;  // queries per warp tile
   float* stash;  // split pipeline: [n_tiles][Stash::floats] workspace written by search_kernel, read by the decode launch
   float* seeds;  // split pipeline with d/dq on the warp-specialised decode: [n_tiles][Seeds::floats] forward-mode seeds
+  int pdl;       // host only: this decode launch directly follows its search launch (programmatic dependent launch)
   QueryLayout lay;
 };
 

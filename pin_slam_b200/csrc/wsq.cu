@@ -646,6 +646,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) wsq_decode_kernel(const __grid_
     // profile slots: 0 wait free meta block, 1 copies issued
     // =====================================================================================================
     const int lw = warp - 4 * WS_EG - WS_GT * WS_GW;
+    // the only role that reads what the search launch wrote: with programmatic dependent launch this grid may have
+    // started before that one finished
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int i = 0;
     for (long long T = blockIdx.x; T < n_tiles; T += gridDim.x, ++i) {
 #pragma unroll 1
@@ -751,7 +754,22 @@ static int launch_wsq(QueryParams& p, cudaStream_t stream) {
   constexpr int QT = GRAD ? 32 : 128;
   const long long n_tiles = (p.n + QT - 1) / QT;
   const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count());
-  kern<<<grid, WS_THREADS, smem_bytes, stream>>>(p, lay);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(WS_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  const QueryParams pk = p;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, pk, lay);
+  if (le != cudaSuccess) {
+    set_error("wsq_decode_kernel launch: %s", cudaGetErrorString(le));
+    return PINB200_ERR_CUDA;
+  }
   return check_launch("wsq_decode_kernel");
 }
 
