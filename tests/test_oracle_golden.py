@@ -521,3 +521,51 @@ def test_dropin_query_feature_assembly_matches_reference(name, local, monkeypatc
     np.testing.assert_allclose(w.numpy(), fx[tag + ".weight"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(geo.detach().numpy(), fx[tag + ".geo"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(cert.numpy(), fx[tag + ".certainty"], rtol=1e-5, atol=1e-6)
+
+
+def test_map_arena_adoption_and_pickling():
+    """Host logic of the growth arenas (pin_slam_b200/model/neural_points.py: _MapArena): the public map tensors become
+    views of fixed-capacity buffers, tensors assigned from outside are adopted on the next reserve, and pickling a map
+    whose tensors are arena views stores the rows, not the capacity."""
+    import pickle
+
+    from pin_slam_b200.config import HotPathConfig
+    from pin_slam_b200.model import NeuralPoints
+    from pin_slam_b200.model.neural_points import _MapArena
+
+    cfg = HotPathConfig.kitti(device="cpu", buffer_size=1009)
+    npm = NeuralPoints(cfg)
+    g = torch.Generator().manual_seed(0)
+    n = 37
+    npm.neural_points = torch.randn(n, 3, generator=g)
+    npm.point_orientations = torch.randn(n, 4, generator=g)
+    npm.point_ts_create = torch.arange(n, dtype=torch.int32)
+    npm.point_ts_update = torch.arange(n, dtype=torch.int32) + 1
+    npm.point_certainties = torch.rand(n, generator=g)
+    npm.geo_features = torch.randn(n + 1, cfg.feature_dim, generator=g)
+    before = {k: getattr(npm, k).clone() for k in _MapArena.NAMES + ("geo_features",)}
+    arena = _MapArena()
+    assert not arena.owns(npm)
+    arena.reserve(npm, n + 100)
+    assert arena.owns(npm) and arena.cap >= n + 100
+    for k, v in before.items():
+        assert torch.equal(getattr(npm, k), v), k
+        assert getattr(npm, k).untyped_storage().nbytes() > v.numel() * v.element_size()  # a view of the arena
+    # in-place growth: rows behind the count are written through the buffers, bind() extends the views
+    arena.buf["neural_points"][n:n + 2] = 7.0
+    arena.bind(npm, n + 2)
+    assert npm.count() == n + 2 and float(npm.neural_points[-1, 0]) == 7.0 and npm.geo_features.shape[0] == n + 3
+    cap = arena.cap
+    arena.reserve(npm, n + 50)  # fits: no reallocation
+    assert arena.cap == cap and arena.owns(npm)
+    # a tensor assigned from outside (pruning, rehash, loop closure) is adopted
+    npm.neural_points = npm.neural_points.clone()
+    assert not arena.owns(npm)
+    arena.reserve(npm, n + 50)
+    assert arena.owns(npm) and npm.count() == n + 2
+    # pickling keeps the rows only
+    npm.__dict__["_arena"] = arena
+    blob = pickle.dumps(npm)
+    assert len(blob) < 200_000
+    back = pickle.loads(blob)
+    assert torch.equal(back.neural_points, npm.neural_points) and "_arena" not in back.__dict__
