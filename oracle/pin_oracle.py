@@ -804,3 +804,22 @@ def make_adam(param_groups, lr=0.01, eps=1e-15, weight_decay=0.0):
             {"params": ps, "lr": lr, "weight_decay": weight_decay if i == len(param_groups) - 1 else 0.0}
         )
     return torch.optim.Adam(groups, betas=(0.9, 0.99), eps=eps)
+
+
+def idw_tangent_seeds(query, nb_points, valid):
+    """Closed form of the forward-mode seeds the warp-specialised decode consumes (pin_slam_b200/csrc/query_dev.cuh:
+    tangent_seeds), restated for the tests.  For one query q with K neighbours p_k (model/neural_points.py:665-683):
+        u_k = 1 / (|q - p_k|^2 + 1e-15),  w_k = u_k / sum u   (invalid neighbours: 0)
+        omega_kj = d w_k / d q_j = w_k (c_k d_kj - sum_m w_m c_m d_mj),   c_k = -2 u_k,  d_k = q - p_k
+        P_ji = d (sum_k w_k (q - p_k))_i / d q_j = sum_k omega_kj (d_k - d_0)_i + (sum_k w_k) delta_ij
+    query [N,3], nb_points [N,K,3], valid [N,K] bool -> (w [N,K], omega [N,K,3], P [N,3,3] with P[n,j,i])."""
+    d = query.unsqueeze(1) - nb_points  # [N,K,3]
+    u = (1.0 / ((d**2).sum(-1) + 1e-15)) * valid
+    usum = u.sum(1, keepdim=True)
+    w = torch.where(usum > 0, u / usum.clamp(min=1e-300), torch.zeros_like(u))
+    c = -2.0 * u
+    S = (w.unsqueeze(-1) * c.unsqueeze(-1) * d).sum(1, keepdim=True)  # [N,1,3]
+    omega = w.unsqueeze(-1) * (c.unsqueeze(-1) * d - S)
+    e = d - d[:, :1]
+    P = torch.einsum("nkj,nki->nji", omega, e) + w.sum(1).view(-1, 1, 1) * torch.eye(3, dtype=query.dtype)
+    return w, omega, P

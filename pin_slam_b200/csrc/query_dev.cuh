@@ -353,6 +353,8 @@ static_assert(Stash::floats % 4 == 0, "stash block is copied with 16-byte access
 //   P_ji = d (x_n)_i / d q_j = sum_k omega_kj (n_k - n_0)_i + sum_k w_k (R_k e_j)_i
 // (sum_k omega_kj = 0: the shift by the nearest neighbour keeps the sums cancellation-free when neighbours coincide;
 // R_k = I before loop closure).  Block layout [field][k][lane]: omega [3 j][8 k][32], P [3 j][3 i][32].
+// The closed forms are restated in oracle/pin_oracle.py: idw_tangent_seeds and pinned against autograd on the CPU
+// (tests/test_oracle_golden.py::test_forward_mode_seeds_equal_autograd).
 struct Seeds {
   static constexpr int om = 0;
   static constexpr int P = om + WT * 24;

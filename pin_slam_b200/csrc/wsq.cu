@@ -1,16 +1,20 @@
 // K1b, warp-specialised: gather + decoder + d/dq of the split pipeline for weighted_first maps, as ONE persistent CTA
 // per SM whose warps have different jobs and only meet through mbarriers (no block-wide barrier after the prologue):
 //
-//   L  loader warps   thread per query: stash block (written by search_kernel) -> "meta" block in shared memory:
-//                     neighbour ids, IDW weights, position part of the decoder input and, when d/dq is wanted, the
-//                     derivatives of the weights  omega_kj = d w_k / d q_j  and of the position part
-//   G  gather warps   F/4 lanes per feature row (a 128-byte row = 8 lanes x LDG.128): ONE pass over the K rows gives the
-//                     IDW-interpolated feature  xbar = sum_k w_k f_k  AND its three directional derivatives
-//                     T_j = sum_k omega_kj (f_k - f_0)  -> rows of the next A tile (canonical K-major, hi / lo TF32)
-//   E  epilogue groups (2 x 4 warps, one TMEM lane quadrant per warp): thread = tile row.  Issue layer 0 as
-//                     tcgen05.mma (A from shared memory), read the accumulator with tcgen05.ld, bias / ReLU, write the
-//                     activations back to TENSOR MEMORY with tcgen05.st, issue layer 1 with the A operand IN TMEM,
-//                     output head in registers, results to global memory.
+//   L  loader warps   TMA bulk copies (cp.async.bulk, completion counted in bytes on an mbarrier) of what search_kernel
+//                     wrote for a 32-query block -- neighbour ids, IDW weights, position part of the decoder input and,
+//                     when d/dq is wanted, the forward-mode seeds  omega_kj = d w_k / d q_j  and d(position part)/dq --
+//                     into a ring of "meta" blocks in shared memory; no thread touches the data
+//   G  gather teams   (2 x 4 warps, 120 registers) F/4 lanes per feature row (a 128-byte row = 8 lanes x LDG.128): ONE pass
+//                     over the K rows gives the IDW-interpolated feature  xbar = sum_k w_k f_k  AND its three directional
+//                     derivatives  T_j = sum_k omega_kj (f_k - f_0)  -> rows of an A tile (canonical K-major, hi / lo TF32)
+//   M  MMA warps      (one per epilogue group, the elected lane issues) layer 0 as tcgen05.mma with the A tile from shared
+//                     memory, layer 1 with the A operand IN TENSOR MEMORY, chunk by chunk behind the layer-0 epilogue;
+//                     layer 0 of the next tile right behind layer 1 of this one (separate accumulator columns)
+//   E  epilogue groups (2 x 4 warps, one TMEM lane quadrant per warp): thread = tile row.  tcgen05.ld of the accumulator,
+//                     ReLU gate, hi / lo split, tcgen05.st of the next layer's A operand back to TMEM, mbarrier arrive;
+//                     last layer: output head in registers, results to global memory.  Never issues an MMA, never meets
+//                     another warp at a barrier.
 //
 // d sdf / d q is computed in FORWARD mode: a tile row is either a value row (decoder input x) or one of the three
 // tangent rows (dx / dq_j) of the same query; tangent rows go through the same weights, without bias, and are gated
@@ -21,7 +25,7 @@
 // Without d/dq (mesher, dense RGB-D queries) a tile is 128 value rows.
 //
 // Replaces model/neural_points.py:598-731 (gathers, IDW, weighted_first), model/decoder.py:61-85,112 and the autograd
-// call of utils/tools.py:247-260 for batches of >= PINB200_SPLIT_MIN_QUERIES queries.
+// call of utils/tools.py:247-260 for batches of >= PINB200_SPLIT_MIN_QUERIES_WF queries (inference mode).
 #include "query_dev.cuh"
 #include "umma_common.cuh"
 

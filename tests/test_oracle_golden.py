@@ -569,3 +569,40 @@ def test_map_arena_adoption_and_pickling():
     assert len(blob) < 200_000
     back = pickle.loads(blob)
     assert torch.equal(back.neural_points, npm.neural_points) and "_arena" not in back.__dict__
+
+
+def test_forward_mode_seeds_equal_autograd():
+    """The closed-form derivatives of the IDW weights / of the interpolated neighbour vector that search_kernel hands
+    to the tangent rows of the decode (oracle.idw_tangent_seeds) against torch.autograd in float64, incl. invalid
+    neighbours and nearly coincident ones; and the identity the forward-mode path rests on:
+    d (sum_k w_k f_k) / d q_j = sum_k omega_kj (f_k - f_0)."""
+    g = torch.Generator().manual_seed(3)
+    n, k, f = 64, 8, 5
+    q = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    nb = q.unsqueeze(1) + 0.3 * torch.randn(n, k, 3, generator=g, dtype=torch.float64)
+    nb[:4, 1] = nb[:4, 0] + 1e-9  # coincident neighbours
+    valid = torch.rand(n, k, generator=g) > 0.2
+    valid[:, 0] = True
+    feats = torch.randn(n, k, f, generator=g, dtype=torch.float64)
+    w, omega, P = po.idw_tangent_seeds(q, nb, valid)
+
+    def weights(qq):
+        d2 = ((qq.unsqueeze(1) - nb) ** 2).sum(-1)
+        u = (1.0 / (d2 + 1e-15)) * valid
+        return u / u.sum(1, keepdim=True)
+
+    qq = q.clone().requires_grad_(True)
+    ww = weights(qq)
+    assert torch.allclose(ww.detach(), w, rtol=1e-12, atol=1e-14)
+    for kk in range(k):
+        gk = torch.autograd.grad(ww[:, kk].sum(), qq, retain_graph=True)[0]
+        assert torch.allclose(gk, omega[:, kk], rtol=1e-7, atol=1e-9 * float(omega.abs().max()))
+    xn = (ww.unsqueeze(-1) * (qq.unsqueeze(1) - nb)).sum(1)  # [n,3]
+    for i in range(3):
+        gi = torch.autograd.grad(xn[:, i].sum(), qq, retain_graph=True)[0]  # d xn_i / d q_j
+        assert torch.allclose(gi, P[:, :, i], rtol=1e-7, atol=1e-8 * float(P.abs().max()))
+    xf = (ww.unsqueeze(-1) * feats).sum(1)  # [n,f]
+    T = torch.einsum("nkj,nkf->njf", omega, feats - feats[:, :1])
+    for c in range(f):
+        gc = torch.autograd.grad(xf[:, c].sum(), qq, retain_graph=True)[0]
+        assert torch.allclose(gc, T[:, :, c], rtol=1e-6, atol=1e-8 * float(T.abs().max()))
