@@ -264,12 +264,20 @@ class NeuralPoints(nn.Module):
         h = torch.fmod((cell * self.primes).sum(-1), self.buffer_size)
         return torch.where(h < 0, h + self.buffer_size, h)
 
+    _NEIGHBORHOODS = {}  # (num_nei_cells, search_alpha, device) -> (neighbor_dx int64, int32 copy)
+
     def set_search_neighborhood(self, num_nei_cells: int = 1, search_alpha: float = 1.0):
-        r = torch.arange(-num_nei_cells, num_nei_cells + 1, device=self.device, dtype=torch.int64)
-        cells = torch.stack(torch.meshgrid(r, r, r, indexing="ij"), dim=-1).reshape(-1, 3)
-        inside = (cells**2).sum(-1) < (num_nei_cells + search_alpha) ** 2
-        self.neighbor_dx = cells[inside]
-        self._probe_dx32 = self.neighbor_dx.to(torch.int32).contiguous()
+        # the mapper switches to the 7-cell neighbourhood and back around its certainty pass every frame
+        # (utils/mapper.py:388-402): the offset tables are cached, building them costs ~10 torch ops and a host sync
+        key = (int(num_nei_cells), float(search_alpha), str(self.device))
+        hit = NeuralPoints._NEIGHBORHOODS.get(key)
+        if hit is None:
+            r = torch.arange(-num_nei_cells, num_nei_cells + 1, device=self.device, dtype=torch.int64)
+            cells = torch.stack(torch.meshgrid(r, r, r, indexing="ij"), dim=-1).reshape(-1, 3)
+            inside = (cells**2).sum(-1) < (num_nei_cells + search_alpha) ** 2
+            dx = cells[inside]
+            hit = NeuralPoints._NEIGHBORHOODS[key] = (dx, dx.to(torch.int32).contiguous())
+        self.neighbor_dx, self._probe_dx32 = hit
         self.neighbor_K = self.neighbor_dx.shape[0]
         self.max_valid_dist2 = 3 * ((num_nei_cells + 1) * self.resolution) ** 2
         self._invalidate()
